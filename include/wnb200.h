@@ -1,0 +1,151 @@
+/*
+ * wnb200.h -- C ABI of libwnb200.so, the B200 (sm_100a) kernels behind the WaveNet vocoder hot paths.
+ *
+ * The reference (kan-bayashi/PytorchWaveNetVocoder v0.1.1) is pure Python on top of torch: it has no
+ * FFI layer of its own.  This header is therefore OUR drop-in boundary: each entry
+ * point replaces one piece of reference/wavenet_vocoder/nets/wavenet.py (cited per function) and is
+ * what the host-side mirror `pytorchwavenetvocoder_b200.nets.WaveNet` binds through ctypes
+ * (INTEGRATION.md shows the stub a reference maintainer would add).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless named host_*;
+ *   - the caller (PyTorch) owns every buffer; nothing is allocated or freed in here;
+ *   - kernels are enqueued on `stream` (a cudaStream_t passed as void*) and never synchronise;
+ *   - return value: 0 = WNB_OK, negative = error; wnb_last_error() gives a thread-local message;
+ *   - activations are CHANNELS-LAST fp32: (B, T, C) with C contiguous (the reference is (B, C, T));
+ *     `Ap` is n_aux rounded up to a multiple of 32 (zero padded);
+ *   - weights arrive in the PACKED layouts documented below (built from the reference state_dict by
+ *     pytorchwavenetvocoder_b200/nets/packing.py).
+ *
+ * Packed weight layouts (R=n_resch, S=n_skipch, Q=n_quantize, ks=kernel_size, K1 = ks*R + Ap)
+ *   wf   (ks, Q, R)   wf[k][q][r]     = causal.conv.weight[r][q][k]                 (wavenet.py:189)
+ *   w1   (2R, K1)     rows 0..R-1 sigmoid branch, R..2R-1 tanh branch; columns j*R+c = tap j
+ *                     (j=0 oldest, x[t-(ks-1-j)d]) of dil_{sigmoid,tanh}[l].conv.weight[o][c][j],
+ *                     columns ks*R+a = aux_1x1_{sigmoid,tanh}[l].weight[o][a][0] (zero for a>=A)
+ *   b1   (2R)         dil bias + aux bias                                            (wavenet.py:527-532)
+ *   w2   (R+S, R)     rows 0..R-1 res_1x1[l].weight, rows R.. skip_1x1[l].weight     (wavenet.py:533-534)
+ *   b2   (R+S)
+ *   wp1  (S, S), bp1 (S), wp2 (Q, S), bp2 (Q)                                        (wavenet.py:209-210)
+ *   *_t  the same matrices transposed (K-major), used by the backward and decode kernels.
+ */
+#ifndef WNB200_H_
+#define WNB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define WNB_API __attribute__((visibility("default")))
+#else
+#define WNB_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WNB_OK 0
+#define WNB_ERR_INVALID (-1)   /* bad argument / unsupported shape */
+#define WNB_ERR_CUDA (-2)      /* a CUDA runtime call or launch failed */
+#define WNB_ERR_UNSUPPORTED (-3)
+
+#define WNB_MATH_FP32 0        /* SIMT FFMA, fp32 throughout (parity mode) */
+#define WNB_MATH_TF32 1        /* tcgen05 kind::tf32 contractions, fp32 accumulate in TMEM */
+
+#define WNB_MODE_ARGMAX 0
+#define WNB_MODE_SAMPLING 1
+
+/* ---- library / device info -------------------------------------------------------------- */
+WNB_API int wnb_version(void);
+WNB_API const char* wnb_last_error(void);
+/* number of kernels this library has launched in the calling process (bench.py "gpu_launches") */
+WNB_API int64_t wnb_launch_count(void);
+
+/* ---- a1/a2: mu-law codec (wavenet.py:17-30, 33-47) -- bit exact with numpy ----------------- */
+WNB_API int wnb_mulaw_encode_f32(const float* x, int64_t* y, int64_t n, int mu, void* stream);
+WNB_API int wnb_mulaw_encode_f64(const double* x, int64_t* y, int64_t n, int mu, void* stream);
+WNB_API int wnb_mulaw_decode_f64(const int64_t* y, double* x, int64_t n, int mu, void* stream);
+
+/* ---- a4/a5/a9: OneHot + causal conv as an embedding gather (wavenet.py:78-92, 513-516) ----- */
+WNB_API int wnb_front_embed_fwd(const int64_t* x /*(B,T)*/, const float* wf, const float* bias /*(R)*/,
+                        float* out /*(B,T,R)*/, int B, int T, int Q, int R, int ks, void* stream);
+/* dwf (ks,Q,R) and dbias (R) are ACCUMULATED into (caller zeroes) */
+WNB_API int wnb_front_embed_bwd(const int64_t* x, const float* dout /*(B,T,R)*/, float* dwf, float* dbias,
+                        int B, int T, int Q, int R, int ks, void* stream);
+
+/* ---- a6: UpSampling (wavenet.py:124-154) fused with the (B,A,Tf)->(B,T,Ap) layout change ----
+ * U > 0: haux[b][tU+j][a] = h[b][a][t]*w[j] + bias[0];  U == 0: plain transpose (Tf == T). */
+WNB_API int wnb_aux_upsample_fwd(const float* h /*(B,A,Tf)*/, const float* w /*(U)*/, const float* bias /*(1)*/,
+                         float* haux /*(B,T,Ap)*/, int B, int A, int Ap, int Tf, int U, void* stream);
+/* dw (U), dbias (1) accumulated into */
+WNB_API int wnb_aux_upsample_bwd(const float* h, const float* dhaux /*(B,T,Ap)*/, float* dw, float* dbias,
+                         int B, int A, int Ap, int Tf, int U, void* stream);
+
+/* ---- a10: fused residual block forward (wavenet.py:525-536), one launch per layer ----------
+ * xout = res_1x1(z) + xin, skip (+)= skip_1x1(z), z = sigmoid(..)*tanh(..).
+ * xout may be NULL (last layer: its residual output is discarded, wavenet.py:230-238).
+ * skip_init != 0: skip = value (first layer; python `0 + s0`), else skip += value.
+ * zsave (B,T,R) may be NULL; when given, z is also stored (not used by the default backward). */
+WNB_API int wnb_resblock_fwd(const float* xin, const float* haux, const float* w1, const float* b1,
+                     const float* w2, const float* b2, float* xout, float* skip, float* zsave,
+                     int B, int T, int R, int S, int Ap, int ks, int dilation, int skip_init,
+                     int math_mode, void* stream);
+
+/* ---- a10 backward --------------------------------------------------------------------------
+ * Recomputes the gate from xin/haux, then produces dxin and accumulates weight gradients.
+ * dout = d(loss)/d(xout) (NULL for the last layer), dskip = d(loss)/d(skip_sum) (same for all layers).
+ * dhaux (B,T,Ap) accumulated into (NULL when the aux path has no trainable producer).
+ * dw1 (2R,K1), db1 (2R), dw2 (R+S,R), db2 (R+S) are ACCUMULATED into.
+ * w1t = (ks+1 blocks) transposed W1: block j<ks is (R, 2R): w1t[j][c][o] = w1[o][j*R+c];
+ *        block ks is (Ap, 2R): w1[o][ks*R+a];  w2t (R, R+S): w2t[c][o] = w2[o][c].
+ * workspace: wnb_resblock_bwd_workspace() bytes. */
+WNB_API size_t wnb_resblock_bwd_workspace(int B, int T, int R, int S, int Ap, int ks);
+WNB_API int wnb_resblock_bwd(const float* xin, const float* haux, const float* dout, const float* dskip,
+                     const float* w1, const float* b1, const float* w1t, const float* w2t,
+                     float* dxin, float* dhaux, float* dw1, float* db1, float* dw2, float* db2,
+                     void* workspace, int B, int T, int R, int S, int Ap, int ks, int dilation,
+                     int math_mode, void* stream);
+
+/* ---- a11: post network (wavenet.py:518-523) -------------------------------------------------
+ * logits (B,T,Q) = wp2 * relu(wp1 * relu(skip) + bp1) + bp2 ; r1 (B,T,S) = relu(h1) is kept when
+ * non-NULL (needed by the backward). */
+WNB_API int wnb_post_fwd(const float* skip, const float* wp1, const float* bp1, const float* wp2,
+                 const float* bp2, float* r1, float* logits, int B, int T, int S, int Q,
+                 int math_mode, void* stream);
+/* dskip (B,T,S) out; dwp1,dbp1,dwp2,dbp2 accumulated into; workspace (B,T,S) floats */
+WNB_API int wnb_post_bwd(const float* skip, const float* r1, const float* dlogits, const float* wp1t /*(S,S) [c][o]*/,
+                 const float* wp2t /*(S,Q) [c][o]*/, float* dskip, float* dwp1, float* dbp1, float* dwp2,
+                 float* dbp2, float* workspace, int B, int T, int S, int Q, int math_mode, void* stream);
+
+/* ---- a12: CrossEntropyLoss(mean) on [:, start:] fused with its gradient (bin/train.py:534-536)
+ * loss_sum (1 double, accumulated into; caller zeroes) receives the MEAN loss;
+ * dlogits (B,T,Q) may be NULL (loss only); rows t < start get zero gradient. */
+WNB_API int wnb_cross_entropy(const float* logits, const int64_t* target /*(B,T)*/, double* loss_sum,
+                      float* dlogits, int B, int T, int Q, int start, void* stream);
+
+/* ---- a14/a15/a16: persistent fast-generate kernel (wavenet.py:309-395, 397-511, 538-549) ----
+ * One launch generates every sample of every utterance.  Queues live in `queues` (caller-allocated,
+ * wnb_decode_workspace() bytes, need not be zeroed).
+ *   xs      (B, P + max_n) int32: [0,P) = the padded/seed prefix (wavenet.py:330-334), the rest is
+ *           written by the kernel (xs[b][P+i] = i-th generated sample);
+ *   h       (B, A, Th) aux features BEFORE upsampling (U>0) or at sample rate (U==0);
+ *   n_pad   number of left-replicated aux columns (wavenet.py:334): aux at padded position p is
+ *           h_up[max(p - n_pad, 0)];
+ *   n_samples (B) int32 per-utterance lengths; mode WNB_MODE_*; uniforms (B,max_n) optional
+ *           externally supplied U[0,1) draws (tests), else Philox4x32-10(seed, utterance, step);
+ *   logits_out (B, max_n, Q) optional teacher-check output (NULL in production).
+ * Decode weights are K-major: wf (ks,Q,R), w1d (L,K1,2R), b1 (L,2R), w2d (L,R,R+S), b2 (L,R+S),
+ * wp1d (S,S) [c][o], wp2d (S,Q) [c][o]. */
+WNB_API size_t wnb_decode_workspace(int B, int R, int ks, const int32_t* host_dilations, int L);
+WNB_API int wnb_decode(int32_t* xs, const float* h, const float* up_w, const float* up_b,
+               const float* wf, const float* bf, const float* w1d, const float* b1, const float* w2d,
+               const float* b2, const float* wp1d, const float* bp1, const float* wp2d, const float* bp2,
+               const int32_t* host_dilations, int L, void* queues, const int32_t* n_samples,
+               const float* uniforms, float* logits_out, int B, int P, int max_n, int n_pad, int Th,
+               int Q, int A, int Ap, int R, int S, int ks, int U, int mode, uint64_t seed,
+               void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WNB200_H_ */

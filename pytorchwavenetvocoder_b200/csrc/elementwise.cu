@@ -1,0 +1,335 @@
+// elementwise.cu -- mu-law codec, front embedding gather, aux up-sampling and the fused
+// cross-entropy (+gradient) kernel.  All HBM-bound streaming kernels: coalesced channels-last rows,
+// float4 where the row width allows, grids sized in multiples of the SM count by grid-stride loops.
+#include <stdarg.h>
+
+#include <atomic>
+
+#include "common.cuh"
+
+namespace wnb {
+
+static thread_local char g_err[512] = "";
+static std::atomic<int64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void count_launch(int n) { g_launches.fetch_add(n); }
+
+static int grid_for(int64_t work_items, int threads) {
+  int64_t blocks = (work_items + threads - 1) / threads;
+  const int64_t cap = 148 * 16;  // 16 resident 256-thread CTAs per SM is plenty for streaming kernels
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+// ------------------------------------------------------------------------------------------------
+// mu-law (wavenet.py:17-30, 33-47).  Bit exactness with numpy: numpy evaluates
+//   fx = sign(x) * log(1 + mu*|x|) / log(1 + mu);  floor((fx + 1) / 2 * mu + 0.5)
+// elementwise; for float32 input sign/abs/log stay float32 and the division by the numpy float64
+// scalar np.log(1 + mu) promotes the rest to float64 (NEP 50).  We evaluate the same expression tree
+// in the same dtypes with FMA contraction disabled.  The float32 log is computed correctly rounded
+// (double log, round to float).  numpy's own SIMD float32 log is NOT correctly rounded (~4 % of
+// inputs differ by 1 ulp, CPU-dispatch dependent), which only matters for float32 inputs sitting
+// within 1 ulp of a quantiser edge: there the reference's answer is build dependent and ours can
+// differ by one code.  On the whole PCM-16 domain (s/32768, what sf.read(dtype=float32) yields for
+// the recipes' wavs, bin/train.py:121) and on dense grids the result is bit exact
+// (tests/golden/mulaw.npz, tests/test_gpu_parity.py).
+// ------------------------------------------------------------------------------------------------
+__global__ void mulaw_encode_f32_kernel(const float* __restrict__ x, int64_t* __restrict__ y, int64_t n,
+                                        float mu, double log1pmu) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float v = x[i];
+    const float sgn = (v > 0.f) ? 1.f : ((v < 0.f) ? -1.f : 0.f);
+    // float32 part: sign(x) * log(1 + mu*|x|)   (numpy keeps float32 here)
+    const float arg = __fadd_rn(1.0f, __fmul_rn(mu, fabsf(v)));
+    const float lg = (float)log((double)arg);  // correctly rounded float32 log
+    const float num = __fmul_rn(sgn, lg);
+    // "/ np.log(1 + mu)" divides by a numpy float64 scalar: NEP-50 promotes the rest to float64
+    const double fx = __ddiv_rn((double)num, log1pmu);
+    const double q = __dadd_rn(__dmul_rn(__ddiv_rn(__dadd_rn(fx, 1.0), 2.0), (double)mu), 0.5);
+    y[i] = (int64_t)floor(q);
+  }
+}
+
+__global__ void mulaw_encode_f64_kernel(const double* __restrict__ x, int64_t* __restrict__ y, int64_t n,
+                                        double mu, double log1pmu) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const double v = x[i];
+    const double sgn = (v > 0.) ? 1. : ((v < 0.) ? -1. : 0.);
+    const double arg = __dadd_rn(1.0, __dmul_rn(mu, fabs(v)));
+    const double fx = __ddiv_rn(__dmul_rn(sgn, log(arg)), log1pmu);
+    const double q = __dadd_rn(__dmul_rn(__ddiv_rn(__dadd_rn(fx, 1.0), 2.0), mu), 0.5);
+    y[i] = (int64_t)floor(q);
+  }
+}
+
+__global__ void mulaw_decode_f64_kernel(const int64_t* __restrict__ y, double* __restrict__ x, int64_t n,
+                                        double mu) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    // fx = (y - 0.5) / mu * 2 - 1 ; x = sign(fx) / mu * ((1 + mu) ** |fx| - 1)
+    const double fx = __dadd_rn(__dmul_rn(__ddiv_rn(__dadd_rn((double)y[i], -0.5), mu), 2.0), -1.0);
+    const double sgn = (fx > 0.) ? 1. : ((fx < 0.) ? -1. : 0.);
+    const double pw = pow(1.0 + mu, fabs(fx));
+    x[i] = __dmul_rn(__ddiv_rn(sgn, mu), __dadd_rn(pw, -1.0));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// front embedding gather (wavenet.py:78-92 OneHot + :513-516 causal conv)
+//   out[b][t][r] = bias[r] + sum_k wf[k][x[b][t-(ks-1-k)] mod Q][r]   (missing history: zero)
+// One thread per 4 channels of one (b,t) row; rows are 4R bytes contiguous -> coalesced stores.
+// ------------------------------------------------------------------------------------------------
+__global__ void front_embed_fwd_kernel(const int64_t* __restrict__ x, const float* __restrict__ wf,
+                                       const float* __restrict__ bias, float* __restrict__ out, int B, int T,
+                                       int Q, int R, int ks) {
+  const int64_t total = (int64_t)B * T * R;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i % R);
+    const int64_t bt = i / R;
+    const int t = (int)(bt % T);
+    float v = bias[r];
+    for (int k = 0; k < ks; k++) {
+      const int tt = t - (ks - 1 - k);
+      if (tt >= 0) {
+        int64_t q = x[bt - (ks - 1 - k)] % Q;
+        if (q < 0) q += Q;
+        v += __ldg(wf + ((size_t)k * Q + q) * R + r);
+      }
+    }
+    out[i] = v;
+  }
+}
+
+// dwf[k][q][r] += dout[b][t][r] for q = x[b][t-(ks-1-k)];  dbias[r] += sum dout
+__global__ void front_embed_bwd_kernel(const int64_t* __restrict__ x, const float* __restrict__ dout,
+                                       float* __restrict__ dwf, float* __restrict__ dbias, int B, int T, int Q,
+                                       int R, int ks, int rows_per_block) {
+  // block handles rows [row0, row0+rows_per_block); thread -> channel r (strided), loops over rows
+  const int64_t row0 = (int64_t)blockIdx.x * rows_per_block;
+  const int64_t nrows = (int64_t)B * T;
+  for (int r = threadIdx.x; r < R; r += blockDim.x) {
+    float bsum = 0.f;
+    for (int64_t row = row0; row < row0 + rows_per_block && row < nrows; row++) {
+      const float g = dout[row * R + r];
+      bsum += g;
+      const int t = (int)(row % T);
+      for (int k = 0; k < ks; k++) {
+        const int s = ks - 1 - k;
+        if (t - s >= 0) {
+          int64_t q = x[row - s] % Q;
+          if (q < 0) q += Q;
+          atomicAdd(dwf + ((size_t)k * Q + q) * R + r, g);
+        }
+      }
+    }
+    atomicAdd(dbias + r, bsum);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// aux up-sampling + layout change (wavenet.py:124-154)
+// ------------------------------------------------------------------------------------------------
+__global__ void aux_upsample_fwd_kernel(const float* __restrict__ h, const float* __restrict__ w,
+                                        const float* __restrict__ bias, float* __restrict__ haux, int B, int A,
+                                        int Ap, int Tf, int U) {
+  const int T = (U > 0) ? Tf * U : Tf;
+  const int64_t total = (int64_t)B * T * Ap;
+  const float bv = (U > 0) ? bias[0] : 0.f;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int a = (int)(i % Ap);
+    const int64_t bt = i / Ap;
+    const int t = (int)(bt % T);
+    const int b = (int)(bt / T);
+    float v = 0.f;
+    if (a < A) {
+      if (U > 0) {
+        const int tf = t / U, j = t - tf * U;
+        v = fmaf(__ldg(h + ((size_t)b * A + a) * Tf + tf), __ldg(w + j), bv);
+      } else {
+        v = __ldg(h + ((size_t)b * A + a) * Tf + t);
+      }
+    }
+    haux[i] = v;
+  }
+}
+
+// dw[j] += sum_{b,a,tf} h[b][a][tf] * dhaux[b][tf*U+j][a] ; dbias += sum_{b,t,a<A} dhaux
+// block = one (b, tf); warp-strided over j, lanes over a.
+__global__ void aux_upsample_bwd_kernel(const float* __restrict__ h, const float* __restrict__ dhaux,
+                                        float* __restrict__ dw, float* __restrict__ dbias, int B, int A, int Ap,
+                                        int Tf, int U) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  __shared__ float sb[32];
+  float btot = 0.f;
+  for (int64_t item = blockIdx.x; item < (int64_t)B * Tf; item += gridDim.x) {
+    const int b = (int)(item / Tf), tf = (int)(item % Tf);
+    for (int j = warp; j < U; j += nwarps) {
+      const float* row = dhaux + ((size_t)b * Tf * U + (size_t)tf * U + j) * Ap;
+      float acc = 0.f, bacc = 0.f;
+      for (int a = lane; a < A; a += 32) {
+        const float g = row[a];
+        acc = fmaf(g, __ldg(h + ((size_t)b * A + a) * Tf + tf), acc);
+        bacc += g;
+      }
+      acc = warp_sum(acc);
+      bacc = warp_sum(bacc);
+      if (lane == 0) {
+        atomicAdd(dw + j, acc);
+        btot += bacc;
+      }
+    }
+  }
+  if (lane == 0) sb[warp] = btot;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int i = 0; i < nwarps; i++) s += sb[i];
+    atomicAdd(dbias, s);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// cross entropy (mean over B*(T-start) rows) + gradient; one warp per (b,t) row of Q logits
+// ------------------------------------------------------------------------------------------------
+__global__ void cross_entropy_kernel(const float* __restrict__ logits, const int64_t* __restrict__ target,
+                                     double* __restrict__ loss_sum, float* __restrict__ dlogits, int B, int T, int Q,
+                                     int start, float inv_n) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int64_t nrows = (int64_t)B * T;
+  double local = 0.0;
+  for (int64_t row = (int64_t)blockIdx.x * nwarps + warp; row < nrows; row += (int64_t)gridDim.x * nwarps) {
+    const int t = (int)(row % T);
+    const float* lg = logits + row * Q;
+    float* dl = dlogits ? dlogits + row * Q : nullptr;
+    if (t < start) {
+      if (dl)
+        for (int q = lane; q < Q; q += 32) dl[q] = 0.f;
+      continue;
+    }
+    float m = -INFINITY;
+    for (int q = lane; q < Q; q += 32) m = fmaxf(m, lg[q]);
+    m = warp_max(m);
+    float s = 0.f;
+    for (int q = lane; q < Q; q += 32) s += expf(lg[q] - m);
+    s = warp_sum(s);
+    const float lse = m + logf(s);
+    int64_t tg = target[row];
+    if (lane == 0) local += (double)(lse - lg[tg]);
+    if (dl) {
+      const float inv_s = 1.0f / s;
+      for (int q = lane; q < Q; q += 32) {
+        float p = expf(lg[q] - m) * inv_s;
+        if (q == tg) p -= 1.0f;
+        dl[q] = p * inv_n;
+      }
+    }
+  }
+  __shared__ double sl[32];
+  if (lane == 0) sl[warp] = local;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int i = 0; i < nwarps; i++) s += sl[i];
+    atomicAdd(loss_sum, s * (double)inv_n);
+  }
+}
+
+}  // namespace wnb
+
+using namespace wnb;
+
+extern "C" {
+
+WNB_API int wnb_version(void) { return 100; }
+WNB_API const char* wnb_last_error(void) { return wnb::g_err; }
+WNB_API int64_t wnb_launch_count(void) { return wnb::g_launches.load(); }
+
+WNB_API int wnb_mulaw_encode_f32(const float* x, int64_t* y, int64_t n, int mu, void* stream) {
+  WNB_REQUIRE(n >= 0 && mu >= 2, "mulaw_encode_f32: bad n/mu");
+  if (n == 0) return WNB_OK;
+  const float m = (float)(mu - 1);
+  mulaw_encode_f32_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(x, y, n, m,
+                                                                             log(1.0 + (double)(mu - 1)));
+  WNB_CHECK_LAUNCH("mulaw_encode_f32");
+  return WNB_OK;
+}
+
+WNB_API int wnb_mulaw_encode_f64(const double* x, int64_t* y, int64_t n, int mu, void* stream) {
+  WNB_REQUIRE(n >= 0 && mu >= 2, "mulaw_encode_f64: bad n/mu");
+  if (n == 0) return WNB_OK;
+  mulaw_encode_f64_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(x, y, n, (double)(mu - 1),
+                                                                             log(1.0 + (double)(mu - 1)));
+  WNB_CHECK_LAUNCH("mulaw_encode_f64");
+  return WNB_OK;
+}
+
+WNB_API int wnb_mulaw_decode_f64(const int64_t* y, double* x, int64_t n, int mu, void* stream) {
+  WNB_REQUIRE(n >= 0 && mu >= 2, "mulaw_decode_f64: bad n/mu");
+  if (n == 0) return WNB_OK;
+  mulaw_decode_f64_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(y, x, n, (double)(mu - 1));
+  WNB_CHECK_LAUNCH("mulaw_decode_f64");
+  return WNB_OK;
+}
+
+WNB_API int wnb_front_embed_fwd(const int64_t* x, const float* wf, const float* bias, float* out, int B, int T, int Q,
+                        int R, int ks, void* stream) {
+  WNB_REQUIRE(B > 0 && T > 0 && Q > 0 && R > 0 && ks >= 1, "front_embed_fwd: bad shape");
+  front_embed_fwd_kernel<<<grid_for((int64_t)B * T * R, 256), 256, 0, (cudaStream_t)stream>>>(x, wf, bias, out, B, T,
+                                                                                              Q, R, ks);
+  WNB_CHECK_LAUNCH("front_embed_fwd");
+  return WNB_OK;
+}
+
+WNB_API int wnb_front_embed_bwd(const int64_t* x, const float* dout, float* dwf, float* dbias, int B, int T, int Q, int R,
+                        int ks, void* stream) {
+  WNB_REQUIRE(B > 0 && T > 0 && Q > 0 && R > 0 && ks >= 1, "front_embed_bwd: bad shape");
+  const int rows_per_block = 64;
+  const int64_t nrows = (int64_t)B * T;
+  const int threads = R >= 256 ? 256 : ((R + 31) / 32) * 32;
+  front_embed_bwd_kernel<<<(int)cdiv64(nrows, rows_per_block), threads, 0, (cudaStream_t)stream>>>(
+      x, dout, dwf, dbias, B, T, Q, R, ks, rows_per_block);
+  WNB_CHECK_LAUNCH("front_embed_bwd");
+  return WNB_OK;
+}
+
+WNB_API int wnb_aux_upsample_fwd(const float* h, const float* w, const float* bias, float* haux, int B, int A, int Ap,
+                         int Tf, int U, void* stream) {
+  WNB_REQUIRE(B > 0 && A > 0 && Ap >= A && Tf > 0 && U >= 0, "aux_upsample_fwd: bad shape");
+  WNB_REQUIRE(U == 0 || (w && bias), "aux_upsample_fwd: U>0 needs w and bias");
+  const int64_t T = U > 0 ? (int64_t)Tf * U : Tf;
+  aux_upsample_fwd_kernel<<<grid_for((int64_t)B * T * Ap, 256), 256, 0, (cudaStream_t)stream>>>(h, w, bias, haux, B,
+                                                                                                A, Ap, Tf, U);
+  WNB_CHECK_LAUNCH("aux_upsample_fwd");
+  return WNB_OK;
+}
+
+WNB_API int wnb_aux_upsample_bwd(const float* h, const float* dhaux, float* dw, float* dbias, int B, int A, int Ap, int Tf,
+                         int U, void* stream) {
+  WNB_REQUIRE(B > 0 && A > 0 && Ap >= A && Tf > 0 && U > 0, "aux_upsample_bwd: bad shape");
+  int64_t items = (int64_t)B * Tf;
+  int grid = (int)(items < 148 * 8 ? items : 148 * 8);
+  aux_upsample_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(h, dhaux, dw, dbias, B, A, Ap, Tf, U);
+  WNB_CHECK_LAUNCH("aux_upsample_bwd");
+  return WNB_OK;
+}
+
+WNB_API int wnb_cross_entropy(const float* logits, const int64_t* target, double* loss_sum, float* dlogits, int B, int T,
+                      int Q, int start, void* stream) {
+  WNB_REQUIRE(B > 0 && T > 0 && Q > 0 && start >= 0 && start < T, "cross_entropy: bad shape (start=%d T=%d)", start,
+              T);
+  const int64_t n = (int64_t)B * (T - start);
+  const int64_t nrows = (int64_t)B * T;
+  int grid = (int)(cdiv64(nrows, 8) < 148 * 8 ? cdiv64(nrows, 8) : 148 * 8);
+  cross_entropy_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(logits, target, loss_sum, dlogits, B, T, Q, start,
+                                                              1.0f / (float)n);
+  WNB_CHECK_LAUNCH("cross_entropy");
+  return WNB_OK;
+}
+
+}  // extern "C"

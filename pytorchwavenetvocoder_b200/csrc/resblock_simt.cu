@@ -1,0 +1,515 @@
+// resblock_simt.cu -- WNB_MATH_FP32 kernels for the residual stack and the post network.
+//
+//   resblock_fwd_simt_kernel : ONE launch per residual block (wavenet.py:525-536): dilated causal conv
+//                              (both branches) + aux 1x1 + sigmoid*tanh gate + res/skip 1x1 + residual
+//                              add + running skip accumulation.  The gate tile never leaves shared memory.
+//   resblock_bwd_gate_kernel : recomputes the gate from (xin, haux), forms dz = W2^T [dout|dskip] and
+//                              writes z and dpre = [dz*th*sg*(1-sg) | dz*sg*(1-th^2)].
+//   gemm_nt_kernel           : C[t][m] = sum_seg sum_k A_seg[m][k] * B_seg[t+shift][k] (+bias, +add, relu,
+//                              mask, accumulate): used for the data gradients and the post network.
+//   gemm_tn_kernel           : weight gradients  dW[m][n] += sum_t A[t][m] * B[t+shift][n]  (split over time,
+//                              fp32 atomics), colsum_kernel: bias gradients.
+//
+// All activations are channels-last (B,T,C).  Everything here is fp32 FFMA: this is the parity path and
+// the fallback for shapes the tcgen05 path (resblock_tc.cu) does not cover.
+#include "gemm_simt.cuh"
+
+namespace wnb {
+
+// ------------------------------------------------------------------------------------------------
+// fused residual block forward
+// ------------------------------------------------------------------------------------------------
+struct FwdParams {
+  const float* xin; const float* haux; const float* w1; const float* b1; const float* w2; const float* b2;
+  float* xout; float* skip; float* zsave;
+  int B, T, R, S, Ap, ks, d, skip_init;
+};
+
+__global__ void __launch_bounds__(kThreads) resblock_fwd_simt_kernel(FwdParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  TileSmem<8>& sm = *reinterpret_cast<TileSmem<8>*>(smem_raw);
+  float* zs = reinterpret_cast<float*>(smem_raw + sizeof(TileSmem<8>));  // [R][kBsLd], k-major gate tile
+
+  const int b = blockIdx.y, t0 = blockIdx.x * kBN;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int R = p.R, S = p.S, Ap = p.Ap, ks = p.ks, d = p.d, T = p.T;
+  const int K1 = ks * R + Ap;
+  const float* xin_b = p.xin + (size_t)b * T * R;
+  const float* haux_b = p.haux + (size_t)b * T * Ap;
+
+  // ---- phase 1: pre-activations, 64 gate channels (128 interleaved W1 rows) at a time ----
+  for (int gc = 0; gc < R; gc += 64) {
+    float acc[8][kTN];
+    zero_acc<8>(acc);
+    auto fa = [&](int m, int k) -> float {
+      const int c = gc + (m >> 1);
+      if (c >= R) return 0.f;
+      const int row = (m & 1) ? R + c : c;
+      return __ldg(p.w1 + (size_t)row * K1 + k);
+    };
+    auto fb = [&](int n, int k) -> float {
+      const int t = t0 + n;
+      if (t >= T) return 0.f;
+      if (k < ks * R) {
+        const int j = k / R, c = k - j * R;
+        const int tt = t - (ks - 1 - j) * d;
+        return tt >= 0 ? __ldg(xin_b + (size_t)tt * R + c) : 0.f;
+      }
+      return __ldg(haux_b + (size_t)t * Ap + (k - ks * R));
+    };
+    tile_mainloop<8, true, true>(acc, fa, fb, K1, sm);
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const int c = gc + ty * 4 + i;
+      if (c < R) {
+        const float bs = __ldg(p.b1 + c), bt = __ldg(p.b1 + R + c);
+#pragma unroll
+        for (int j = 0; j < kTN; j++)
+          zs[c * kBsLd + tx * 4 + j] = sigmoidf_(acc[2 * i][j] + bs) * tanhf(acc[2 * i + 1][j] + bt);
+      }
+    }
+  }
+  __syncthreads();
+
+  if (p.zsave) {
+    float* zb = p.zsave + (size_t)b * T * R;
+    for (int e = tid; e < kBN * R; e += kThreads) {
+      const int c = e % R, n = e / R;
+      if (t0 + n < T) zb[(size_t)(t0 + n) * R + c] = zs[c * kBsLd + n];
+    }
+  }
+
+  // ---- phase 2: [res | skip] 1x1 on the gate tile, 128 output rows at a time ----
+  const int row_begin = p.xout ? 0 : R;  // last layer: residual output is discarded
+  const int M2 = R + S;
+  float* xout_b = p.xout ? p.xout + (size_t)b * T * R : nullptr;
+  float* skip_b = p.skip + (size_t)b * T * S;
+  for (int r0 = row_begin; r0 < M2; r0 += 128) {
+    float acc[8][kTN];
+    zero_acc<8>(acc);
+    auto fa = [&](int m, int k) -> float {
+      const int row = r0 + m;
+      return row < M2 ? __ldg(p.w2 + (size_t)row * R + k) : 0.f;
+    };
+    auto fb = [&](int n, int k) -> float { return zs[k * kBsLd + n]; };
+    tile_mainloop<8, true, false>(acc, fa, fb, R, sm);
+#pragma unroll
+    for (int j = 0; j < kTN; j++) {
+      const int t = t0 + tx * 4 + j;
+      if (t >= T) continue;
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        const int row = r0 + ty * 8 + i;
+        if (row >= M2) continue;
+        const float v = acc[i][j] + __ldg(p.b2 + row);
+        if (row < R) {
+          xout_b[(size_t)t * R + row] = v + __ldg(xin_b + (size_t)t * R + row);
+        } else {
+          float* dst = skip_b + (size_t)t * S + (row - R);
+          *dst = p.skip_init ? v : (*dst + v);
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward, gate part: recompute sg/th, dz, write z and dpre
+// ------------------------------------------------------------------------------------------------
+struct BwdGateParams {
+  const float* xin; const float* haux; const float* dout; const float* dskip;
+  const float* w1; const float* b1; const float* w2t;  // w2t (R, R+S): [c][o]
+  float* z; float* dpre;                               // (B,T,R), (B,T,2R)
+  int B, T, R, S, Ap, ks, d;
+};
+
+__global__ void __launch_bounds__(kThreads) resblock_bwd_gate_kernel(BwdGateParams p) {
+  __shared__ TileSmem<8> sm8;
+  TileSmem<4>& sm4 = *reinterpret_cast<TileSmem<4>*>(&sm8);
+  const int b = blockIdx.y, t0 = blockIdx.x * kBN, gc = blockIdx.z * 64;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int R = p.R, S = p.S, Ap = p.Ap, ks = p.ks, d = p.d, T = p.T;
+  const int K1 = ks * R + Ap, M2 = R + S;
+  const float* xin_b = p.xin + (size_t)b * T * R;
+  const float* haux_b = p.haux + (size_t)b * T * Ap;
+  const float* dout_b = p.dout ? p.dout + (size_t)b * T * R : nullptr;
+  const float* dskip_b = p.dskip + (size_t)b * T * S;
+
+  float sg[4][kTN], th[4][kTN];
+  {
+    float acc[8][kTN];
+    zero_acc<8>(acc);
+    auto fa = [&](int m, int k) -> float {
+      const int c = gc + (m >> 1);
+      if (c >= R) return 0.f;
+      const int row = (m & 1) ? R + c : c;
+      return __ldg(p.w1 + (size_t)row * K1 + k);
+    };
+    auto fb = [&](int n, int k) -> float {
+      const int t = t0 + n;
+      if (t >= T) return 0.f;
+      if (k < ks * R) {
+        const int j = k / R, c = k - j * R;
+        const int tt = t - (ks - 1 - j) * d;
+        return tt >= 0 ? __ldg(xin_b + (size_t)tt * R + c) : 0.f;
+      }
+      return __ldg(haux_b + (size_t)t * Ap + (k - ks * R));
+    };
+    tile_mainloop<8, true, true>(acc, fa, fb, K1, sm8);
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const int c = gc + ty * 4 + i;
+      const float bs = c < R ? __ldg(p.b1 + c) : 0.f, bt = c < R ? __ldg(p.b1 + R + c) : 0.f;
+#pragma unroll
+      for (int j = 0; j < kTN; j++) {
+        sg[i][j] = sigmoidf_(acc[2 * i][j] + bs);
+        th[i][j] = tanhf(acc[2 * i + 1][j] + bt);
+      }
+    }
+  }
+  float dz[4][kTN];
+  zero_acc<4>(dz);
+  {
+    const int kofs = dout_b ? 0 : R;  // last layer: no dout, only the skip rows of W2 contribute
+    auto fa = [&](int m, int k) -> float {
+      const int c = gc + m;
+      return c < R ? __ldg(p.w2t + (size_t)c * M2 + kofs + k) : 0.f;
+    };
+    auto fb = [&](int n, int k) -> float {
+      const int t = t0 + n;
+      if (t >= T) return 0.f;
+      const int kk = kofs + k;
+      return kk < R ? __ldg(dout_b + (size_t)t * R + kk) : __ldg(dskip_b + (size_t)t * S + (kk - R));
+    };
+    tile_mainloop<4, true, true>(dz, fa, fb, M2 - kofs, sm4);
+  }
+  float* z_b = p.z + (size_t)b * T * R;
+  float* dpre_b = p.dpre + (size_t)b * T * 2 * R;
+#pragma unroll
+  for (int j = 0; j < kTN; j++) {
+    const int t = t0 + tx * 4 + j;
+    if (t >= T) continue;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const int c = gc + ty * 4 + i;
+      if (c >= R) continue;
+      const float s_ = sg[i][j], h_ = th[i][j], g = dz[i][j];
+      z_b[(size_t)t * R + c] = s_ * h_;
+      dpre_b[(size_t)t * 2 * R + c] = g * h_ * s_ * (1.f - s_);
+      dpre_b[(size_t)t * 2 * R + R + c] = g * s_ * (1.f - h_ * h_);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// generic NT GEMM over channels-last activations
+// ------------------------------------------------------------------------------------------------
+struct NtSeg {
+  const float* a; int lda;   // A rows: a + m*lda + k
+  const float* b; int ldb;   // B rows: b + (batch*T + t + shift)*ldb + k, valid iff 0 <= t+shift < T
+  int shift; int K;
+};
+struct NtParams {
+  NtSeg seg[4]; int nseg;
+  int M, T, B;
+  const float* bias;               // (M) or null
+  float* c; int ldc;               // c[(batch*T+t)*ldc + m]
+  const float* add; int ldadd;     // optional residual add (same indexing), null = none
+  const float* mask; int ldmask;   // optional: multiply by (mask > 0)
+  int relu_b, relu_out, accumulate;
+};
+
+__global__ void __launch_bounds__(kThreads) gemm_nt_kernel(NtParams p) {
+  __shared__ TileSmem<8> sm;
+  const int bidx = blockIdx.z, t0 = blockIdx.x * kBN, m0 = blockIdx.y * 128;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int T = p.T;
+  float acc[8][kTN];
+  zero_acc<8>(acc);
+  for (int s = 0; s < p.nseg; s++) {
+    const NtSeg sg = p.seg[s];
+    const float* bb = sg.b + (size_t)bidx * T * sg.ldb;
+    const int relu_b = p.relu_b;
+    auto fa = [&](int m, int k) -> float {
+      return (m0 + m < p.M) ? __ldg(sg.a + (size_t)(m0 + m) * sg.lda + k) : 0.f;
+    };
+    auto fb = [&](int n, int k) -> float {
+      const int t = t0 + n + sg.shift;
+      if (t0 + n >= T || t < 0 || t >= T) return 0.f;
+      const float v = __ldg(bb + (size_t)t * sg.ldb + k);
+      return relu_b ? fmaxf(v, 0.f) : v;
+    };
+    tile_mainloop<8, true, true>(acc, fa, fb, sg.K, sm);
+  }
+#pragma unroll
+  for (int j = 0; j < kTN; j++) {
+    const int t = t0 + tx * 4 + j;
+    if (t >= T) continue;
+    const size_t row = (size_t)bidx * T + t;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      const int m = m0 + ty * 8 + i;
+      if (m >= p.M) continue;
+      float v = acc[i][j];
+      if (p.bias) v += __ldg(p.bias + m);
+      if (p.add) v += __ldg(p.add + row * p.ldadd + m);
+      if (p.relu_out) v = fmaxf(v, 0.f);
+      if (p.mask) v = (__ldg(p.mask + row * p.ldmask + m) > 0.f) ? v : 0.f;
+      float* dst = p.c + row * p.ldc + m;
+      *dst = p.accumulate ? (*dst + v) : v;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight gradient: C[m][coff+n] += sum_{b, t in split} A[b][t][m] * Bm[b][t+shift][n]
+// ------------------------------------------------------------------------------------------------
+struct TnParams {
+  const float* a; int lda; int M;
+  const float* b; int ldb; int N; int shift; int relu_b;
+  float* c; int ldc; int coff;
+  int T, B, tchunk;
+};
+
+__global__ void __launch_bounds__(kThreads) gemm_tn_kernel(TnParams p) {
+  __shared__ TileSmem<8> sm;
+  const int m0 = blockIdx.x * 128, n0 = blockIdx.y * kBN;
+  const int nsplit = (p.T + p.tchunk - 1) / p.tchunk;
+  const int bidx = blockIdx.z / nsplit, tb = (blockIdx.z % nsplit) * p.tchunk;
+  const int tlen = min(p.tchunk, p.T - tb);
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const float* ab = p.a + ((size_t)bidx * p.T + tb) * p.lda;
+  const float* bb = p.b + (size_t)bidx * p.T * p.ldb;
+  float acc[8][kTN];
+  zero_acc<8>(acc);
+  auto fa = [&](int m, int k) -> float { return (m0 + m < p.M) ? __ldg(ab + (size_t)k * p.lda + m0 + m) : 0.f; };
+  auto fb = [&](int n, int k) -> float {
+    const int t = tb + k + p.shift;
+    if (n0 + n >= p.N || t < 0 || t >= p.T) return 0.f;
+    const float v = __ldg(bb + (size_t)t * p.ldb + n0 + n);
+    return p.relu_b ? fmaxf(v, 0.f) : v;
+  };
+  tile_mainloop<8, false, false>(acc, fa, fb, tlen, sm);
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    const int m = m0 + ty * 8 + i;
+    if (m >= p.M) continue;
+#pragma unroll
+    for (int j = 0; j < kTN; j++) {
+      const int n = n0 + tx * 4 + j;
+      if (n < p.N) atomicAdd(p.c + (size_t)m * p.ldc + p.coff + n, acc[i][j]);
+    }
+  }
+}
+
+// out[m] += sum over rows of a[row][m]  (rows = B*T)
+__global__ void colsum_kernel(const float* __restrict__ a, int lda, int M, int64_t rows, int rows_per_block,
+                              float* __restrict__ out) {
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+  const int64_t r1 = min(r0 + rows_per_block, rows);
+  for (int m = threadIdx.x; m < M; m += blockDim.x) {
+    float s = 0.f;
+    for (int64_t r = r0; r < r1; r++) s += a[r * lda + m];
+    atomicAdd(out + m, s);
+  }
+}
+
+static int launch_nt(const NtParams& p, cudaStream_t st) {
+  dim3 grid(cdiv(p.T, kBN), cdiv(p.M, 128), p.B);
+  gemm_nt_kernel<<<grid, kThreads, 0, st>>>(p);
+  WNB_CHECK_LAUNCH("gemm_nt");
+  return WNB_OK;
+}
+
+static int launch_tn(const TnParams& p, cudaStream_t st) {
+  const int nsplit = cdiv(p.T, p.tchunk);
+  dim3 grid(cdiv(p.M, 128), cdiv(p.N, kBN), p.B * nsplit);
+  gemm_tn_kernel<<<grid, kThreads, 0, st>>>(p);
+  WNB_CHECK_LAUNCH("gemm_tn");
+  return WNB_OK;
+}
+
+static int launch_colsum(const float* a, int lda, int M, int64_t rows, float* out, cudaStream_t st) {
+  const int rpb = 512;
+  const int threads = M >= 256 ? 256 : ((M + 31) / 32) * 32;
+  colsum_kernel<<<(int)cdiv64(rows, rpb), threads, 0, st>>>(a, lda, M, rows, rpb, out);
+  WNB_CHECK_LAUNCH("colsum");
+  return WNB_OK;
+}
+
+static int pick_tchunk(int B, int T, int tiles) {
+  // aim for ~2 waves of CTAs over 148 SMs; chunks are multiples of 16 time steps
+  int64_t want = 148 * 2;
+  int nsplit = (int)((want + (int64_t)tiles * B - 1) / ((int64_t)tiles * B));
+  if (nsplit < 1) nsplit = 1;
+  int chunk = (T + nsplit - 1) / nsplit;
+  chunk = ((chunk + 15) / 16) * 16;
+  if (chunk < 64) chunk = 64;
+  return chunk;
+}
+
+// implemented in resblock_tc.cu
+int resblock_fwd_tc(const FwdParams& p, cudaStream_t st);
+bool resblock_fwd_tc_supported(int R, int S, int Ap, int ks);
+
+}  // namespace wnb
+
+using namespace wnb;
+
+extern "C" {
+
+WNB_API int wnb_resblock_fwd(const float* xin, const float* haux, const float* w1, const float* b1, const float* w2,
+                     const float* b2, float* xout, float* skip, float* zsave, int B, int T, int R, int S, int Ap,
+                     int ks, int dilation, int skip_init, int math_mode, void* stream) {
+  WNB_REQUIRE(B > 0 && T > 0 && R > 0 && S > 0 && Ap > 0 && ks >= 1 && dilation >= 1, "resblock_fwd: bad shape");
+  WNB_REQUIRE(xin && haux && w1 && b1 && w2 && b2 && skip, "resblock_fwd: null pointer");
+  FwdParams p{xin, haux, w1, b1, w2, b2, xout, skip, zsave, B, T, R, S, Ap, ks, dilation, skip_init};
+  if (math_mode == WNB_MATH_TF32) {
+    WNB_REQUIRE(resblock_fwd_tc_supported(R, S, Ap, ks), "resblock_fwd: shape R=%d S=%d Ap=%d ks=%d not supported by the "
+                "tcgen05 path (use WNB_MATH_FP32)", R, S, Ap, ks);
+    return resblock_fwd_tc(p, (cudaStream_t)stream);
+  }
+  WNB_REQUIRE(math_mode == WNB_MATH_FP32, "resblock_fwd: unknown math_mode %d", math_mode);
+  const size_t smem = sizeof(TileSmem<8>) + (size_t)R * kBsLd * sizeof(float);
+  WNB_REQUIRE(smem <= 227 * 1024, "resblock_fwd: n_resch=%d too large for the SIMT path", R);
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    WNB_CUDA(cudaFuncSetAttribute(resblock_fwd_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  dim3 grid(cdiv(T, kBN), B);
+  resblock_fwd_simt_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(p);
+  WNB_CHECK_LAUNCH("resblock_fwd_simt");
+  return WNB_OK;
+}
+
+WNB_API size_t wnb_resblock_bwd_workspace(int B, int T, int R, int S, int Ap, int ks) {
+  (void)S; (void)Ap; (void)ks;
+  return (size_t)B * T * 3 * R * sizeof(float);  // z (B,T,R) + dpre (B,T,2R)
+}
+
+WNB_API int wnb_resblock_bwd(const float* xin, const float* haux, const float* dout, const float* dskip, const float* w1,
+                     const float* b1, const float* w1t, const float* w2t, float* dxin, float* dhaux, float* dw1,
+                     float* db1, float* dw2, float* db2, void* workspace, int B, int T, int R, int S, int Ap, int ks,
+                     int dilation, int math_mode, void* stream) {
+  WNB_REQUIRE(B > 0 && T > 0 && R > 0 && S > 0 && Ap > 0 && ks >= 1 && dilation >= 1, "resblock_bwd: bad shape");
+  WNB_REQUIRE(xin && haux && dskip && w1 && b1 && w1t && w2t && dxin && dw1 && db1 && dw2 && db2 && workspace,
+              "resblock_bwd: null pointer");
+  (void)math_mode;  // backward is fp32 SIMT in this round for both math modes
+  cudaStream_t st = (cudaStream_t)stream;
+  float* z = (float*)workspace;
+  float* dpre = z + (size_t)B * T * R;
+  const int K1 = ks * R + Ap, M2 = R + S;
+  int rc;
+  {
+    BwdGateParams g{xin, haux, dout, dskip, w1, b1, w2t, z, dpre, B, T, R, S, Ap, ks, dilation};
+    dim3 grid(cdiv(T, kBN), B, cdiv(R, 64));
+    resblock_bwd_gate_kernel<<<grid, kThreads, 0, st>>>(g);
+    WNB_CHECK_LAUNCH("resblock_bwd_gate");
+  }
+  {  // dxin[t][c] = dout[t][c] + sum_j sum_o w1[o][j*R+c] * dpre[t+(ks-1-j)d][o]
+    NtParams p{};
+    p.nseg = ks;
+    WNB_REQUIRE(ks <= 4, "resblock_bwd: kernel_size > 4 unsupported");
+    for (int j = 0; j < ks; j++)
+      p.seg[j] = NtSeg{w1t + (size_t)j * R * 2 * R, 2 * R, dpre, 2 * R, (ks - 1 - j) * dilation, 2 * R};
+    p.M = R; p.T = T; p.B = B; p.bias = nullptr; p.c = dxin; p.ldc = R;
+    p.add = dout; p.ldadd = R; p.mask = nullptr; p.ldmask = 0; p.relu_b = 0; p.relu_out = 0; p.accumulate = 0;
+    if ((rc = launch_nt(p, st)) != WNB_OK) return rc;
+  }
+  if (dhaux) {  // dhaux[t][a] += sum_o w1[o][ks*R+a] * dpre[t][o]
+    NtParams p{};
+    p.nseg = 1;
+    p.seg[0] = NtSeg{w1t + (size_t)ks * R * 2 * R, 2 * R, dpre, 2 * R, 0, 2 * R};
+    p.M = Ap; p.T = T; p.B = B; p.bias = nullptr; p.c = dhaux; p.ldc = Ap;
+    p.add = nullptr; p.mask = nullptr; p.relu_b = 0; p.relu_out = 0; p.accumulate = 1;
+    if ((rc = launch_nt(p, st)) != WNB_OK) return rc;
+  }
+  // weight gradients
+  for (int j = 0; j < ks; j++) {
+    TnParams p{dpre, 2 * R, 2 * R, xin, R, R, -(ks - 1 - j) * dilation, 0, dw1, K1, j * R, T, B, 0};
+    p.tchunk = pick_tchunk(B, T, cdiv(2 * R, 128) * cdiv(R, kBN));
+    if ((rc = launch_tn(p, st)) != WNB_OK) return rc;
+  }
+  {
+    TnParams p{dpre, 2 * R, 2 * R, haux, Ap, Ap, 0, 0, dw1, K1, ks * R, T, B, 0};
+    p.tchunk = pick_tchunk(B, T, cdiv(2 * R, 128) * cdiv(Ap, kBN));
+    if ((rc = launch_tn(p, st)) != WNB_OK) return rc;
+  }
+  if ((rc = launch_colsum(dpre, 2 * R, 2 * R, (int64_t)B * T, db1, st)) != WNB_OK) return rc;
+  if (dout) {
+    TnParams p{dout, R, R, z, R, R, 0, 0, dw2, R, 0, T, B, 0};
+    p.tchunk = pick_tchunk(B, T, cdiv(R, 128) * cdiv(R, kBN));
+    if ((rc = launch_tn(p, st)) != WNB_OK) return rc;
+    if ((rc = launch_colsum(dout, R, R, (int64_t)B * T, db2, st)) != WNB_OK) return rc;
+  }
+  {
+    TnParams p{dskip, S, S, z, R, R, 0, 0, dw2 + (size_t)R * R, R, 0, T, B, 0};
+    p.tchunk = pick_tchunk(B, T, cdiv(S, 128) * cdiv(R, kBN));
+    if ((rc = launch_tn(p, st)) != WNB_OK) return rc;
+    if ((rc = launch_colsum(dskip, S, S, (int64_t)B * T, db2 + R, st)) != WNB_OK) return rc;
+  }
+  (void)M2;
+  return WNB_OK;
+}
+
+WNB_API int wnb_post_fwd(const float* skip, const float* wp1, const float* bp1, const float* wp2, const float* bp2,
+                 float* r1, float* logits, int B, int T, int S, int Q, int math_mode, void* stream) {
+  WNB_REQUIRE(B > 0 && T > 0 && S > 0 && Q > 0, "post_fwd: bad shape");
+  WNB_REQUIRE(skip && wp1 && bp1 && wp2 && bp2 && r1 && logits, "post_fwd: null pointer (r1 scratch is required)");
+  (void)math_mode;
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc;
+  {  // r1 = relu(wp1 * relu(skip) + bp1)
+    NtParams p{};
+    p.nseg = 1; p.seg[0] = NtSeg{wp1, S, skip, S, 0, S};
+    p.M = S; p.T = T; p.B = B; p.bias = bp1; p.c = r1; p.ldc = S; p.relu_b = 1; p.relu_out = 1;
+    if ((rc = launch_nt(p, st)) != WNB_OK) return rc;
+  }
+  {  // logits = wp2 * r1 + bp2
+    NtParams p{};
+    p.nseg = 1; p.seg[0] = NtSeg{wp2, S, r1, S, 0, S};
+    p.M = Q; p.T = T; p.B = B; p.bias = bp2; p.c = logits; p.ldc = Q;
+    if ((rc = launch_nt(p, st)) != WNB_OK) return rc;
+  }
+  return WNB_OK;
+}
+
+WNB_API int wnb_post_bwd(const float* skip, const float* r1, const float* dlogits, const float* wp1t, const float* wp2t,
+                 float* dskip, float* dwp1, float* dbp1, float* dwp2, float* dbp2, float* workspace, int B, int T,
+                 int S, int Q, int math_mode, void* stream) {
+  WNB_REQUIRE(B > 0 && T > 0 && S > 0 && Q > 0, "post_bwd: bad shape");
+  WNB_REQUIRE(skip && r1 && dlogits && wp1t && wp2t && dskip && dwp1 && dbp1 && dwp2 && dbp2 && workspace,
+              "post_bwd: null pointer");
+  (void)math_mode;
+  cudaStream_t st = (cudaStream_t)stream;
+  float* dh1 = workspace;  // (B,T,S)
+  int rc;
+  {  // dh1[t][c] = (sum_q wp2[q][c] dlogits[t][q]) * (r1 > 0)
+    NtParams p{};
+    p.nseg = 1; p.seg[0] = NtSeg{wp2t, Q, dlogits, Q, 0, Q};
+    p.M = S; p.T = T; p.B = B; p.c = dh1; p.ldc = S; p.mask = r1; p.ldmask = S;
+    if ((rc = launch_nt(p, st)) != WNB_OK) return rc;
+  }
+  {  // dskip[t][c] = (sum_o wp1[o][c] dh1[t][o]) * (skip > 0)
+    NtParams p{};
+    p.nseg = 1; p.seg[0] = NtSeg{wp1t, S, dh1, S, 0, S};
+    p.M = S; p.T = T; p.B = B; p.c = dskip; p.ldc = S; p.mask = skip; p.ldmask = S;
+    if ((rc = launch_nt(p, st)) != WNB_OK) return rc;
+  }
+  {  // dwp2[q][c] += sum_t dlogits[t][q] * r1[t][c]
+    TnParams p{dlogits, Q, Q, r1, S, S, 0, 0, dwp2, S, 0, T, B, 0};
+    p.tchunk = pick_tchunk(B, T, cdiv(Q, 128) * cdiv(S, kBN));
+    if ((rc = launch_tn(p, st)) != WNB_OK) return rc;
+    if ((rc = launch_colsum(dlogits, Q, Q, (int64_t)B * T, dbp2, st)) != WNB_OK) return rc;
+  }
+  {  // dwp1[o][c] += sum_t dh1[t][o] * relu(skip[t][c])
+    TnParams p{dh1, S, S, skip, S, S, 0, 1, dwp1, S, 0, T, B, 0};
+    p.tchunk = pick_tchunk(B, T, cdiv(S, 128) * cdiv(S, kBN));
+    if ((rc = launch_tn(p, st)) != WNB_OK) return rc;
+    if ((rc = launch_colsum(dh1, S, S, (int64_t)B * T, dbp1, st)) != WNB_OK) return rc;
+  }
+  return WNB_OK;
+}
+
+}  // extern "C"

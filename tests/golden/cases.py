@@ -65,3 +65,18 @@ def mulaw_inputs():
     x32 = np.concatenate([x64.astype(np.float32), near])
     codes = np.arange(256, dtype=np.int64)
     return x32, x64, codes
+
+
+def mulaw_pcm16_domain():
+    """Every float32 that sf.read(dtype=float32) can produce from a PCM_16 wav (bin/train.py:121)."""
+    return np.arange(-32768, 32768).astype(np.float32) / np.float32(32768)
+
+
+def mulaw_edge_mask(x32):
+    """True where a float32 input lies within 2 ulp of a quantiser edge (reference result there
+    depends on numpy's non-correctly-rounded SIMD float32 log; see csrc/elementwise.cu)."""
+    q = np.arange(1, 256) - 0.5
+    fx = q / 255.0 * 2 - 1
+    edges = (np.sign(fx) / 255.0 * (256.0 ** np.abs(fx) - 1))
+    d = np.abs(x32.astype(np.float64)[:, None] - edges[None, :]).min(axis=1)
+    return d <= 2 * np.spacing(np.abs(x32).astype(np.float32)).astype(np.float64)

@@ -24,7 +24,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, "/root/reference")
 
 from oracle import wavenet_oracle as O  # noqa: E402
-from tests.golden.cases import FORWARD_CASES, GEN_CASES, make_inputs, make_gen_inputs, mulaw_inputs  # noqa: E402
+from tests.golden.cases import FORWARD_CASES, GEN_CASES, make_inputs, make_gen_inputs, mulaw_inputs, mulaw_pcm16_domain  # noqa: E402
 from wavenet_vocoder.nets import WaveNet, decode_mu_law, encode_mu_law  # noqa: E402
 
 torch.set_num_threads(8)
@@ -44,8 +44,11 @@ def main():
     out["mulaw_enc_f32"] = encode_mu_law(x32, 256)
     out["mulaw_enc_f64"] = encode_mu_law(x64, 256)
     out["mulaw_dec"] = decode_mu_law(codes, 256)
+    out["mulaw_enc_pcm16"] = encode_mu_law(mulaw_pcm16_domain(), 256).astype(np.uint8)
     np.savez_compressed(os.path.join(HERE, "mulaw.npz"), **out)
     print("mulaw ok", out["mulaw_enc_f32"][:12], out["mulaw_dec"][:3])
+    if "--only-mulaw" in sys.argv:
+        return
 
     # ---- forward / loss / grads ----
     for name, (cfg_t, seed, B, T, start) in FORWARD_CASES.items():

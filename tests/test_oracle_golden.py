@@ -8,7 +8,7 @@ import pytest
 
 from oracle import wavenet_oracle as O
 from tests.golden.cases import (FORWARD_CASES, GEN_CASES, make_gen_inputs, make_inputs,
-                                mulaw_inputs)
+                                mulaw_inputs, mulaw_pcm16_domain)
 
 G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
@@ -19,6 +19,7 @@ def test_mulaw_bit_exact():
     assert np.array_equal(O.encode_mu_law(x32, 256), g["mulaw_enc_f32"])
     assert np.array_equal(O.encode_mu_law(x64, 256), g["mulaw_enc_f64"])
     assert np.array_equal(O.decode_mu_law(codes, 256), g["mulaw_dec"])  # float64, bit exact
+    assert np.array_equal(O.encode_mu_law(mulaw_pcm16_domain(), 256), g["mulaw_enc_pcm16"].astype(np.int64))
     # known answers quoted in SURVEY.md 8c
     kat = np.array([-1, -.5, -.1, -.01, -1e-3, 0, 1e-3, .01, .1, .5, .999, 1])
     assert O.encode_mu_law(kat).tolist() == [0, 16, 52, 98, 122, 128, 133, 157, 203, 239, 255, 255]
