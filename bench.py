@@ -1,0 +1,387 @@
+#!/usr/bin/env python
+# -*- coding: utf-8 -*-
+"""bench.py -- the driver's benchmark contract for the WaveNet hot paths on B200.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload train|decode]
+
+Default workload = BASELINE.json configs[1]: arctic/sd 16 kHz, 3x10 dilation layers, 64 res / 512 skip,
+mu-law 256, aux 28 + UpSampling(80), batch 8 x 23 040-sample windows (20 000 nominal + receptive field,
+reference bin/train.py:106-110) per GPU.  One "step" = forward + cross-entropy + backward + Adam step of
+that batch (reference bin/train.py:530-540) through ``pytorchwavenetvocoder_b200.nets.WaveNet``.
+
+  value   = train waveform-samples/s with the batch resident in HBM (whole job, all ranks);
+  e2e     = the same step fed from pinned HOST buffers (H2D of x,h,t inside the timed region) and with
+            the loss read back to the host every step (the call a user of bin/train.py makes);
+  decode  = (extra object) persistent fast-generate kernel, configs[3] shape (64 utterances), bounded
+            number of samples per utterance -- stated in the object;
+  roofline= fused residual-block FORWARD kernel: algorithmic bytes s*(2R + A + 2S) per sample-layer
+            (4 720 B fp32 at 64/512/28) x B*T per launch / mean launch time (CUDA events on
+            the launching stream, inside the timed steps) against MEASURED_PEAKS.json hbm_gbs;
+  cpu_baseline / --impl reference = oracle/torch_port.py (the reference's op sequence on torch CPU, all
+            host threads) on a bounded sample (1 window per step).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+CFG = (256, 28, 64, 512, 10, 3, 2, 80)       # BASELINE.json configs[1] / north_star shape
+BATCH, BATCH_LENGTH = 8, 20000
+FALLBACK_HBM_GBS = 6650.0
+
+
+def _peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback"
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) >= 6 and r[2 + i].lower().startswith("active")
+                                                         for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def make_model(device, math_mode, seed=20260924):
+    from oracle import wavenet_oracle as O  # only for seeded synthetic weights (same as the parity tests)
+    from pytorchwavenetvocoder_b200.nets import WaveNet
+    cfg = O.Config(*CFG)
+    p = O.make_params(cfg, seed)
+    net = WaveNet(*CFG)
+    net.load_state_dict({k: torch.from_numpy(v) for k, v in p.items()})
+    net.math_mode = math_mode
+    return cfg, net.to(device)
+
+
+def synth_batch(cfg, rank, B, pinned):
+    g = torch.Generator().manual_seed(20260924 + rank)
+    T = BATCH_LENGTH + cfg.receptive_field - 1 + 1          # bin/train.py:106-110 -> 23 069 -> trimmed below
+    T = (T // cfg.upsampling_factor) * cfg.upsampling_factor  # validate_length: multiple of U -> 23 040
+    xfull = torch.randint(0, cfg.n_quantize, (B, T + 1), generator=g, dtype=torch.int64)
+    x, t = xfull[:, :-1].contiguous(), xfull[:, 1:].contiguous()
+    h = torch.randn(B, cfg.n_aux, T // cfg.upsampling_factor, generator=g)
+    if pinned:
+        x, t, h = x.pin_memory(), t.pin_memory(), h.pin_memory()
+    return x, h, t
+
+
+def run_ours(args):
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    from pytorchwavenetvocoder_b200 import _lib
+    from pytorchwavenetvocoder_b200.nets import cross_entropy
+    from pytorchwavenetvocoder_b200.nets import wavenet as wn
+    _lib.load()
+
+    out = {}
+    if args.workload == "train":
+        cfg, net = make_model(dev, args.math)
+        net.train()
+        if world > 1:
+            from pytorchwavenetvocoder_b200.parallel import GradAllReduce
+            sync = GradAllReduce(net)
+        else:
+            sync = None
+        opt = torch.optim.Adam(net.parameters(), lr=1e-4, fused=True)
+        xh, hh, th = synth_batch(cfg, rank, BATCH, pinned=True)
+        xd, hd, td = xh.to(dev), hh.to(dev), th.to(dev)
+        rf = cfg.receptive_field
+
+        def step(x, h, t):
+            y = net(x, h)
+            loss = cross_entropy(y, t, rf)
+            opt.zero_grad(set_to_none=True)
+            loss.backward()
+            if sync is not None:
+                sync.allreduce()
+            opt.step()
+            return loss
+
+        def barrier():
+            torch.cuda.synchronize()
+            if dist is not None:
+                dist.barrier()
+                torch.cuda.synchronize()
+
+        for _ in range(args.warmup):
+            step(xd, hd, td)
+        # --- device-resident timing (value) ---
+        barrier()
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        l0 = _lib.launch_count()
+        wn.PROFILE_EVENTS = []
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            loss = step(xd, hd, td)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        launches = _lib.launch_count() - l0
+        evs = wn.PROFILE_EVENTS
+        wn.PROFILE_EVENTS = None
+        blk_ms = [a.elapsed_time(b) for a, b in evs]
+        clocks = sampler.stop() if rank == 0 else None
+        # --- end-to-end timing: pinned host -> device every step, loss read back every step ---
+        for _ in range(2):
+            float(step(xh.to(dev, non_blocking=True), hh.to(dev, non_blocking=True), th.to(dev, non_blocking=True)))
+        barrier()
+        e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e2.record()
+        last = 0.0
+        for _ in range(args.steps):
+            last = float(step(xh.to(dev, non_blocking=True), hh.to(dev, non_blocking=True),
+                              th.to(dev, non_blocking=True)))
+        e3.record()
+        barrier()
+        ms_e2e = e2.elapsed_time(e3)
+        if dist is not None:
+            tt = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms, ms_e2e = float(tt[0]), float(tt[1])
+        per_step = ms / args.steps
+        samples = world * BATCH * BATCH_LENGTH
+        hbm, how = _peaks()
+        Bq, T = xd.shape
+        s, R, S, A = 4, cfg.n_resch, cfg.n_skipch, cfg.n_aux
+        alg_bytes = float(Bq) * T * s * (2 * R + A + 2 * S)
+        blk = float(np.mean(blk_ms)) if blk_ms else None
+        ach = alg_bytes / (blk * 1e-3) / 1e9 if blk else None
+        out = {
+            "metric": "train waveform-samples/s (fwd+CE+bwd+Adam), arctic/sd 30-layer 64res/512skip",
+            "value": samples / (per_step * 1e-3), "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "tf32" if args.math == "tf32" else "f32", "data": "synthetic",
+            "config": {"workload": "configs[1]: arctic/sd 16kHz WaveNet(256,28,64,512,10,3,2,80) batch 8 x 23040 "
+                                   "(20000 + rf window) per GPU, Adam, loss on [rf:]",
+                       "global_batch": world * BATCH, "seq_len": int(T), "parallelism": "dp%d" % world,
+                       "math": args.math, "storage": "fp32 channels-last",
+                       "l2": "per-step working set ~10 GB >> 126 MB L2 (no explicit flush needed)"},
+            "e2e": {"value": samples / (ms_e2e / args.steps * 1e-3), "unit": "samples/s",
+                    "h2d_bytes_per_step": int(xh.numel() * 8 + th.numel() * 8 + hh.numel() * 4),
+                    "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps, "last_loss": last},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"kernel": "resblock_fwd (%s)" % args.math, "bound": "hbm", "achieved": ach, "peak": hbm,
+                         "unit": "GB/s", "frac": (ach / hbm) if ach else None, "traffic": TRAFFIC_NCU.get(args.math),
+                         "peak_source": how, "algorithmic_bytes_per_launch": alg_bytes,
+                         "mean_launch_ms": blk, "launches_timed": len(blk_ms)},
+        }
+    if args.workload == "decode" or (args.workload == "train" and args.with_decode):
+        dec = run_decode(args, dev, rank, world, dist)
+        if args.workload == "decode":
+            out = dec
+        else:
+            out["decode"] = dec
+    if rank == 0:
+        if world == 1:
+            out["cpu_baseline"] = cpu_baseline(args, out.get("config", {}).get("workload", ""),
+                                               decode=(args.workload == "decode"))
+        print(json.dumps(out))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the fused block kernel from the ncu --set full
+# capture committed under profiles/ (filled in by hand from that capture; None = not captured yet)
+TRAFFIC_NCU = {"fp32": None, "tf32": None}
+
+
+def run_decode(args, dev, rank, world, dist):
+    """configs[3]/[4]: batch autoregressive decode, utterances sharded over ranks (reference decode.py:261)."""
+    from pytorchwavenetvocoder_b200 import _lib
+    cfg, net = make_model(dev, "fp32")
+    net.eval()
+    n_utt_total = args.decode_utts * world        # weak scaling: fixed utterances per GPU
+    n = args.decode_samples
+    g = torch.Generator().manual_seed(20260924 + rank)
+    U = cfg.upsampling_factor
+    frames = (n + 1 + U - 1) // U
+    h_host = torch.randn(args.decode_utts, cfg.n_aux, frames, generator=g).pin_memory()
+    x_host = torch.full((args.decode_utts, 1), cfg.n_quantize // 2, dtype=torch.int64).pin_memory()
+    nl = [n] * args.decode_utts
+
+    def once(host):
+        if host:
+            x, h = x_host.to(dev, non_blocking=True), h_host.to(dev, non_blocking=True)
+        else:
+            x, h = once.xd, once.hd
+        gen = net._decode(x, h, nl, "sampling", seed=1234)
+        if host:
+            return gen.cpu()
+        return gen
+    once.xd, once.hd = x_host.to(dev), h_host.to(dev)
+    with torch.no_grad():
+        once(False)
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        l0 = _lib.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        once(False)
+        e1.record()
+        torch.cuda.synchronize()
+        launches = _lib.launch_count() - l0
+        ms = e0.elapsed_time(e1)
+        t0 = time.time()
+        once(True)
+        torch.cuda.synchronize()
+        ms_e2e = (time.time() - t0) * 1e3
+    if dist is not None:
+        tt = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = float(tt[0]), float(tt[1])
+    steps_incl_warmup = n + cfg.receptive_field - 1
+    wbytes = sum(p.numel() for p in net.parameters()) * 4
+    return {
+        "metric": "autoregressive decode samples/s (persistent fast-generate kernel, sampling mode)",
+        "value": n_utt_total * n / (ms * 1e-3), "unit": "samples/s", "n_gpus": world,
+        "ms": ms, "higher_is_better": True, "scaling": "weak", "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "configs[3]: %d utterances/GPU x %d samples (bounded from 160000), arctic/sd "
+                               "30-layer 64/512, seed 128, aux N(0,1)" % (args.decode_utts, n),
+                   "utterances": n_utt_total, "samples_per_utterance": n,
+                   "warmup_steps_in_time": cfg.receptive_field - 1},
+        "us_per_step": ms * 1e3 / steps_incl_warmup,
+        "weight_stream_GBps": (args.decode_utts * steps_incl_warmup * wbytes) / (ms * 1e-3) / 1e9,
+        "e2e": {"value": n_utt_total * n / (ms_e2e * 1e-3), "unit": "samples/s",
+                "h2d_bytes_per_step": int(h_host.numel() * 4 + x_host.numel() * 8),
+                "d2h_bytes_per_step": int(args.decode_utts * n * 4)},
+        "gpu_launches": int(launches),
+    }
+
+
+def cpu_baseline(args, workload, decode=False, steps=None):
+    """The reference's op sequence on the host cores (oracle/torch_port.py), bounded sample."""
+    from oracle import torch_port as TP
+    from oracle import wavenet_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = O.Config(*CFG)
+    if decode:
+        p = TP.params_to_torch(O.make_params(cfg, 20260924))
+        B = 8
+        g = torch.Generator().manual_seed(1)
+        x = torch.full((B, 1), 128, dtype=torch.int64)
+
+        def run(n):
+            h = torch.randn(B, cfg.n_aux, (n + 1 + 79) // 80, generator=g)
+            t0 = time.time()
+            TP.batch_fast_generate(cfg, p, x, h, [n] * B, "argmax")
+            return time.time() - t0
+        a, b = run(20), run(60)       # differencing removes the receptive-field warm-up
+        v = B * 40 / max(b - a, 1e-9)
+        return {"value": v, "unit": "samples/s", "cores": cores, "kind": "port",
+                "sample": "batch_fast_generate B=8, 60 vs 20 samples differenced, torch CPU fp32"}
+    p = TP.params_to_torch(O.make_params(cfg, 20260924), requires_grad=True)
+    opt = torch.optim.Adam(list(p.values()), lr=1e-4)
+    x, h, t = synth_batch(cfg, 0, 1, pinned=False)
+    TP.train_step(cfg, p, opt, x, h, t)
+    k = steps or 2
+    t0 = time.time()
+    for _ in range(k):
+        TP.train_step(cfg, p, opt, x, h, t)
+    dt = (time.time() - t0) / k
+    return {"value": BATCH_LENGTH / dt, "unit": "samples/s", "cores": cores, "kind": "port",
+            "sample": "%d step(s) of 1 x 23040-sample window (fwd+CE+bwd+Adam), torch CPU fp32, after 1 warm-up" % k,
+            "sec_per_step": dt}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    from oracle import wavenet_oracle as O
+    cfg = O.Config(*CFG)
+    decode = args.workload == "decode"
+    k = max(1, min(args.steps, 3))
+    cb = cpu_baseline(args, "", decode=decode, steps=k)
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    out = {
+        "impl": "reference",
+        "metric": ("autoregressive decode samples/s" if decode else
+                   "train waveform-samples/s (fwd+CE+bwd+Adam), arctic/sd 30-layer 64res/512skip"),
+        "value": cb["value"], "unit": "samples/s", "n_gpus": world, "steps": k, "warmup": 1,
+        "ms_per_step": cb.get("sec_per_step", 0) * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "configs[1] arctic/sd WaveNet(256,28,64,512,10,3,2,80); bounded sample: " + cb["sample"],
+                   "receptive_field": cfg.receptive_field},
+        "cpu_baseline": cb,
+        "e2e": {"value": cb["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="train", choices=["train", "decode"])
+    ap.add_argument("--math", default=None, choices=["fp32", "tf32"])
+    ap.add_argument("--with-decode", type=int, default=1, help="also report the decode workload (extra object)")
+    ap.add_argument("--decode-utts", type=int, default=64)
+    ap.add_argument("--decode-samples", type=int, default=8000)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+    if args.math is None:
+        from pytorchwavenetvocoder_b200.nets.wavenet import tc_supported
+        args.math = "tf32" if tc_supported(CFG) else "fp32"
+    run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -91,6 +91,9 @@ WNB_API int wnb_resblock_fwd(const float* xin, const float* haux, const float* w
                      int B, int T, int R, int S, int Ap, int ks, int dilation, int skip_init,
                      int math_mode, void* stream);
 
+/* 1 if (R,S,Ap,ks) is covered by the kernel family selected by math_mode, else 0 */
+WNB_API int wnb_resblock_fwd_supported(int R, int S, int Ap, int ks, int math_mode);
+
 /* ---- a10 backward --------------------------------------------------------------------------
  * Recomputes the gate from xin/haux, then produces dxin and accumulates weight gradients.
  * dout = d(loss)/d(xout) (NULL for the last layer), dskip = d(loss)/d(skip_sum) (same for all layers).

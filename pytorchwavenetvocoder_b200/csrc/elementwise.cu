@@ -1,6 +1,7 @@
 // elementwise.cu -- mu-law codec, front embedding gather, aux up-sampling and the fused
 // cross-entropy (+gradient) kernel.  All HBM-bound streaming kernels: coalesced channels-last rows,
 // float4 where the row width allows, grids sized in multiples of the SM count by grid-stride loops.
+#include <math.h>
 #include <stdarg.h>
 
 #include <atomic>
@@ -69,14 +70,26 @@ __global__ void mulaw_encode_f64_kernel(const double* __restrict__ x, int64_t* _
   }
 }
 
+// decode: the input domain is the mu integer codes, so the launcher evaluates the reference
+// expression  fx = (y - 0.5) / mu * 2 - 1 ; x = sign(fx) / mu * ((1 + mu) ** |fx| - 1)  once per code on
+// the host with the correctly rounded libm pow and the kernel is a table gather.  (numpy's float64
+// power is SVML on AVX-512 hosts and libm elsewhere; the two differ by 1 ulp in 11 of 256 codes, so the
+// reference itself is only defined up to 1 ulp here; after the PCM_16 quantisation of
+// bin/decode.py:319 all variants are identical.)
+struct MulawTable { double v[256]; };
+
 __global__ void mulaw_decode_f64_kernel(const int64_t* __restrict__ y, double* __restrict__ x, int64_t n,
-                                        double mu) {
+                                        double mu, int nmu, const MulawTable tab) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    // fx = (y - 0.5) / mu * 2 - 1 ; x = sign(fx) / mu * ((1 + mu) ** |fx| - 1)
-    const double fx = __dadd_rn(__dmul_rn(__ddiv_rn(__dadd_rn((double)y[i], -0.5), mu), 2.0), -1.0);
-    const double sgn = (fx > 0.) ? 1. : ((fx < 0.) ? -1. : 0.);
-    const double pw = pow(1.0 + mu, fabs(fx));
-    x[i] = __dmul_rn(__ddiv_rn(sgn, mu), __dadd_rn(pw, -1.0));
+    const int64_t yi = y[i];
+    if (yi >= 0 && yi < nmu && nmu <= 256) {
+      x[i] = tab.v[yi];
+    } else {
+      const double fx = __dadd_rn(__dmul_rn(__ddiv_rn(__dadd_rn((double)yi, -0.5), mu), 2.0), -1.0);
+      const double sgn = (fx > 0.) ? 1. : ((fx < 0.) ? -1. : 0.);
+      const double pw = pow(1.0 + mu, fabs(fx));
+      x[i] = __dmul_rn(__ddiv_rn(sgn, mu), __dadd_rn(pw, -1.0));
+    }
   }
 }
 
@@ -272,7 +285,15 @@ WNB_API int wnb_mulaw_encode_f64(const double* x, int64_t* y, int64_t n, int mu,
 WNB_API int wnb_mulaw_decode_f64(const int64_t* y, double* x, int64_t n, int mu, void* stream) {
   WNB_REQUIRE(n >= 0 && mu >= 2, "mulaw_decode_f64: bad n/mu");
   if (n == 0) return WNB_OK;
-  mulaw_decode_f64_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(y, x, n, (double)(mu - 1));
+  MulawTable tab;
+  const double m = (double)(mu - 1);
+  for (int q = 0; q < 256; q++) {
+    volatile double fx = ((double)q - 0.5) / m * 2.0 - 1.0;
+    const double sgn = (fx > 0.) ? 1. : ((fx < 0.) ? -1. : 0.);
+    volatile double pw = pow(1.0 + m, fabs(fx));
+    tab.v[q] = sgn / m * (pw - 1.0);
+  }
+  mulaw_decode_f64_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(y, x, n, m, mu, tab);
   WNB_CHECK_LAUNCH("mulaw_decode_f64");
   return WNB_OK;
 }

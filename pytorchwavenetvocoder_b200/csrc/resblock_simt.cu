@@ -383,6 +383,12 @@ WNB_API int wnb_resblock_fwd(const float* xin, const float* haux, const float* w
   return WNB_OK;
 }
 
+WNB_API int wnb_resblock_fwd_supported(int R, int S, int Ap, int ks, int math_mode) {
+  if (R <= 0 || S <= 0 || Ap <= 0 || ks < 1) return 0;
+  if (math_mode == WNB_MATH_TF32) return resblock_fwd_tc_supported(R, S, Ap, ks) ? 1 : 0;
+  return (sizeof(TileSmem<8>) + (size_t)R * kBsLd * sizeof(float)) <= 227 * 1024 ? 1 : 0;
+}
+
 WNB_API size_t wnb_resblock_bwd_workspace(int B, int T, int R, int S, int Ap, int ks) {
   (void)S; (void)Ap; (void)ks;
   return (size_t)B * T * 3 * R * sizeof(float);  // z (B,T,R) + dpre (B,T,2R)

@@ -29,6 +29,16 @@ from .._lib import MATH_FP32, MATH_TF32, MODE_ARGMAX, MODE_SAMPLING, check, ptr,
 __all__ = ["encode_mu_law", "decode_mu_law", "initialize", "OneHot", "CausalConv1d", "UpSampling",
            "WaveNet", "cross_entropy"]
 
+# bench.py sets this to a list to get (start, end) CUDA-event pairs around every fused-block launch
+PROFILE_EVENTS = None
+
+
+def tc_supported(cfg):
+    """True when the tcgen05 (tf32) fused-block kernel covers WaveNet(*cfg)."""
+    lib = _lib.load()
+    Q, A, R, S, depth, repeat, ks, U = cfg
+    return bool(lib.wnb_resblock_fwd_supported(R, S, _round_up(A, 32), ks, MATH_TF32))
+
 
 def _device():
     if not torch.cuda.is_available():
@@ -167,12 +177,19 @@ class _WaveNetFn(torch.autograd.Function):
         xs = torch.empty(nbuf, B, T, R, device=dev, dtype=torch.float32)
         check(lib.wnb_front_embed_fwd(ptr(x), ptr(wf), ptr(bf), ptr(xs[0]), B, T, Q, R, ks, st), "front_embed_fwd")
         skip = torch.empty(B, T, S, device=dev, dtype=torch.float32)
+        prof = PROFILE_EVENTS
         for l, d in enumerate(dilations):
             xin = xs[l % nbuf]
             xout = xs[(l + 1) % nbuf] if l + 1 < L else None
+            if prof is not None:
+                ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                ev[0].record()
             check(lib.wnb_resblock_fwd(ptr(xin), ptr(haux), ptr(W1[l]), ptr(b1[l]), ptr(W2[l]), ptr(b2[l]),
                                        ptr(xout), ptr(skip), None, B, T, R, S, Ap, ks, int(d),
                                        1 if l == 0 else 0, math_mode, st), "resblock_fwd")
+            if prof is not None:
+                ev[1].record()
+                prof.append(ev)
         r1 = torch.empty(B, T, S, device=dev, dtype=torch.float32)
         logits = torch.empty(B, T, Q, device=dev, dtype=torch.float32)
         check(lib.wnb_post_fwd(ptr(skip), ptr(Wp1), ptr(bp1), ptr(Wp2), ptr(bp2), ptr(r1), ptr(logits),
