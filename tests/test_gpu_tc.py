@@ -1,0 +1,99 @@
+# -*- coding: utf-8 -*-
+"""GPU tier: the tcgen05/TMA fused residual-block kernel (math_mode="tf32") against the fp32 FFMA kernel
+and the fp64 oracle.
+
+Stated tolerance for the tf32 path (tf32 multiplies = 10-bit mantissa operands, fp32 accumulate,
+tanh.approx gate):  single block |err| <= 4e-3 * max|ref|;  30-layer logits |err| <= 5e-2 abs with
+argmax agreement >= 97 % where the oracle's top-2 margin exceeds 0.1.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import wavenet_oracle as O
+from tests.util import our_model
+
+pytestmark = pytest.mark.gpu
+
+
+def _block(mode, xin, haux, W1, b1, W2, b2, d, skip0, last):
+    from pytorchwavenetvocoder_b200 import _lib
+    lib = _lib.load()
+    B, T, R = xin.shape
+    S = W2.shape[0] - R
+    xout = None if last else torch.full_like(xin, float("nan"))
+    skip = torch.zeros(B, T, S, device="cuda") if skip0 is None else skip0.clone()
+    _lib.check(lib.wnb_resblock_fwd(_lib.ptr(xin), _lib.ptr(haux), _lib.ptr(W1), _lib.ptr(b1), _lib.ptr(W2),
+                                    _lib.ptr(b2), _lib.ptr(xout), _lib.ptr(skip), None, B, T, R, S, 32, 2, d,
+                                    1 if skip0 is None else 0, mode, _lib.stream()), "resblock_fwd")
+    torch.cuda.synchronize()
+    return xout, skip
+
+
+@pytest.mark.parametrize("d,T,last,init", [(1, 256, False, True), (4, 384, False, False), (512, 1024, False, False),
+                                            (2, 200, False, False), (64, 128, True, False), (128, 23040, False, True)])
+def test_single_block_tf32_vs_fp32(d, T, last, init):
+    from pytorchwavenetvocoder_b200 import _lib
+    torch.manual_seed(d + T)
+    B, R, S, Ap = 2, 64, 512, 32
+    xin = torch.randn(B, T, R, device="cuda")
+    haux = torch.randn(B, T, Ap, device="cuda")
+    haux[:, :, 28:] = 0
+    K1 = 2 * R + Ap
+    W1 = (torch.randn(2 * R, K1, device="cuda") / np.sqrt(K1)).contiguous()
+    W2 = (torch.randn(R + S, R, device="cuda") / np.sqrt(R)).contiguous()
+    b1 = 0.1 * torch.randn(2 * R, device="cuda")
+    b2 = 0.1 * torch.randn(R + S, device="cuda")
+    skip0 = None if init else torch.randn(B, T, S, device="cuda")
+    xo_ref, sk_ref = _block(_lib.MATH_FP32, xin, haux, W1, b1, W2, b2, d, skip0, last)
+    xo, sk = _block(_lib.MATH_TF32, xin, haux, W1, b1, W2, b2, d, skip0, last)
+    tol = 4e-3
+    assert torch.isfinite(sk).all()
+    err_s = (sk - sk_ref).abs().max().item() / sk_ref.abs().max().item()
+    assert err_s < tol, ("skip", err_s)
+    if not last:
+        assert torch.isfinite(xo).all()
+        err_x = (xo - xo_ref).abs().max().item() / xo_ref.abs().max().item()
+        assert err_x < tol, ("xout", err_x)
+
+
+def test_full_forward_tf32_vs_oracle():
+    cfg = O.Config(256, 28, 64, 512, 10, 3, 2, 80)
+    p = O.make_params(cfg, 3)
+    net = our_model(cfg, p, math_mode="tf32").eval()
+    rng = np.random.RandomState(4)
+    B, T = 2, 1600
+    x = rng.randint(0, 256, size=(B, T)).astype(np.int64)
+    h = rng.standard_normal((B, 28, T // 80)).astype(np.float32)
+    with torch.no_grad():
+        y = net(torch.from_numpy(x).cuda(), torch.from_numpy(h).cuda()).cpu().numpy()
+    p64 = {k: v.astype(np.float64) for k, v in p.items()}
+    ref = O.forward(cfg, p64, x, h.astype(np.float64))
+    err = np.abs(y - ref).max()
+    assert err < 5e-2, err
+    srt = np.sort(ref, axis=-1)
+    clear = (srt[..., -1] - srt[..., -2]) > 0.1
+    agree = (y.argmax(-1) == ref.argmax(-1))[clear].mean()
+    assert agree >= 0.97, agree
+
+
+def test_training_step_tf32_close_to_fp32():
+    """forward in tf32 + backward (fp32 kernels): loss within 1e-3 and gradients within 2 % of the fp32 run."""
+    from pytorchwavenetvocoder_b200.nets import cross_entropy
+    cfg = O.Config(256, 28, 64, 128, 6, 2, 2, 16)
+    p = O.make_params(cfg, 8)
+    rng = np.random.RandomState(2)
+    B, T = 2, 512
+    x = torch.from_numpy(rng.randint(0, 256, size=(B, T)).astype(np.int64)).cuda()
+    t = torch.from_numpy(rng.randint(0, 256, size=(B, T)).astype(np.int64)).cuda()
+    h = torch.from_numpy(rng.standard_normal((B, 28, T // 16)).astype(np.float32)).cuda()
+    res = {}
+    for mode in ("fp32", "tf32"):
+        net = our_model(cfg, p, math_mode=mode).train()
+        loss = cross_entropy(net(x, h), t, 64)
+        loss.backward()
+        res[mode] = (loss.item(), {k: v.grad.clone() for k, v in net.named_parameters() if v.grad is not None})
+    assert abs(res["fp32"][0] - res["tf32"][0]) < 1e-3
+    for k, g in res["fp32"][1].items():
+        g2 = res["tf32"][1][k]
+        assert (g - g2).abs().max().item() <= 0.02 * g.abs().max().item() + 1e-7, k
