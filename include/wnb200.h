@@ -148,6 +148,21 @@ WNB_API int wnb_decode(int32_t* xs, const float* h, const float* up_w, const flo
                int Q, int A, int Ap, int R, int S, int ks, int U, int mode, uint64_t seed,
                void* stream);
 
+/* ---- a14-a16, streaming variant: same contract as wnb_decode, but the K-major matrices arrive as ONE
+ * packed stream consumed in order every step (a producer warp pushes it through a shared-memory ring
+ * with cp.async.bulk while the consumer warps run the recurrence):
+ *   per layer l: W1d [K1][O1] | W2res [R][Or] | W2skip [R][Os]   then  wp1d [S][Sp] | wp2d [S][Qp]
+ * with O1 = 2R, Or = R, Os = Sp = S, Qp = Q each rounded up to a multiple of 4 (zero padded).
+ * Returns WNB_ERR_UNSUPPORTED when the shape does not fit (caller uses wnb_decode). */
+WNB_API size_t wnb_decode_stream_floats(int Q, int Ap, int R, int S, int ks, int L);
+WNB_API int wnb_decode_stream(int32_t* xs, const float* h, const float* up_w, const float* up_b,
+                              const float* wf, const float* bf, const float* stream, const float* b1,
+                              const float* b2, const float* bp1, const float* bp2,
+                              const int32_t* host_dilations, int L, void* queues, const int32_t* n_samples,
+                              const float* uniforms, float* logits_out, int B, int P, int max_n, int n_pad,
+                              int Th, int Q, int A, int Ap, int R, int S, int ks, int U, int mode,
+                              uint64_t seed, void* stream_handle);
+
 #ifdef __cplusplus
 }
 #endif

@@ -44,6 +44,8 @@ SIGNATURES = {
     "wnb_cross_entropy": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "wnb_decode_workspace": (_c.c_size_t, [_I, _I, _I, _P, _I]),
     "wnb_decode": (_I, [_P] * 14 + [_P, _I] + [_P] * 4 + [_I] * 13 + [_c.c_uint64, _P]),
+    "wnb_decode_stream_floats": (_c.c_size_t, [_I] * 6),
+    "wnb_decode_stream": (_I, [_P] * 11 + [_P, _I] + [_P] * 4 + [_I] * 13 + [_c.c_uint64, _P]),
 }
 
 _lib = None

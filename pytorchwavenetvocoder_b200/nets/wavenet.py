@@ -482,11 +482,22 @@ class WaveNet(nn.Module):
             return F.pad(t, (0, _round_up(o, 4) - o)).contiguous()
         with torch.no_grad():
             wf, bf, W1, b1, W2, b2, Wp1, bp1, Wp2, bp2 = [t.detach().float() for t in self._pack()]
+            R = self.n_resch
             return dict(wf=wf.contiguous(), bf=bf.contiguous(), w1d=pad4(W1.transpose(1, 2)), b1=b1,
                         w2d=pad4(W2.transpose(1, 2)), b2=b2, wp1d=pad4(Wp1.t()), bp1=bp1.contiguous(),
-                        wp2d=pad4(Wp2.t()), bp2=bp2.contiguous())
+                        wp2d=pad4(Wp2.t()), bp2=bp2.contiguous(),
+                        w2d_res=pad4(W2[:, :R].transpose(1, 2)), w2d_skip=pad4(W2[:, R:].transpose(1, 2)))
 
-    def _decode(self, x, h, n_samples_list, mode, uniforms=None, return_logits=False, seed=None):
+    def _decode_stream_pack(self, w):
+        """One contiguous fp32 stream in consumption order (include/wnb200.h, wnb_decode_stream)."""
+        R = self.n_resch
+        parts = []
+        for l in range(len(self.dilations)):
+            parts += [w["w1d"][l].reshape(-1), w["w2d_res"][l].reshape(-1), w["w2d_skip"][l].reshape(-1)]
+        parts += [w["wp1d"].reshape(-1), w["wp2d"].reshape(-1)]
+        return torch.cat(parts).contiguous()
+
+    def _decode(self, x, h, n_samples_list, mode, uniforms=None, return_logits=False, seed=None, kernel="auto"):
         lib = _lib.load()
         if mode not in ("sampling", "argmax"):
             logging.error("mode should be sampling or argmax")
@@ -519,12 +530,24 @@ class WaveNet(nn.Module):
             seed = int(torch.empty((), dtype=torch.int64).random_().item())  # follows torch.manual_seed
         upw = self.upsampling.conv.weight.detach().float().contiguous().view(-1) if U > 0 else None
         upb = self.upsampling.conv.bias.detach().float().contiguous().view(-1) if U > 0 else None
-        check(lib.wnb_decode(ptr(xs), ptr(h), ptr(upw), ptr(upb), ptr(w["wf"]), ptr(w["bf"]), ptr(w["w1d"]),
-                             ptr(w["b1"]), ptr(w["w2d"]), ptr(w["b2"]), ptr(w["wp1d"]), ptr(w["bp1"]),
-                             ptr(w["wp2d"]), ptr(w["bp2"]), dil, L, ptr(queues), ptr(nsm), ptr(uni), ptr(lg),
-                             B, P, max_n, n_pad, Th, Q, A, Ap, R, S, ks, U,
-                             MODE_ARGMAX if mode == "argmax" else MODE_SAMPLING,
-                             ctypes.c_uint64(seed & 0xFFFFFFFFFFFFFFFF), stream()), "decode")
+        cmode = MODE_ARGMAX if mode == "argmax" else MODE_SAMPLING
+        cseed = ctypes.c_uint64(seed & 0xFFFFFFFFFFFFFFFF)
+        rc = -3
+        if kernel in ("auto", "stream"):
+            wstream = self._decode_stream_pack(w)
+            assert wstream.numel() == lib.wnb_decode_stream_floats(Q, Ap, R, S, ks, L)
+            rc = lib.wnb_decode_stream(ptr(xs), ptr(h), ptr(upw), ptr(upb), ptr(w["wf"]), ptr(w["bf"]), ptr(wstream),
+                                       ptr(w["b1"]), ptr(w["b2"]), ptr(w["bp1"]), ptr(w["bp2"]), dil, L, ptr(queues),
+                                       ptr(nsm), ptr(uni), ptr(lg), B, P, max_n, n_pad, Th, Q, A, Ap, R, S, ks, U,
+                                       cmode, cseed, stream())
+            if rc != -3 or kernel == "stream":
+                check(rc, "decode_stream")
+        if rc == -3:   # WNB_ERR_UNSUPPORTED: shape outside the streaming kernel -> direct-from-L2 kernel
+            check(lib.wnb_decode(ptr(xs), ptr(h), ptr(upw), ptr(upb), ptr(w["wf"]), ptr(w["bf"]), ptr(w["w1d"]),
+                                 ptr(w["b1"]), ptr(w["w2d"]), ptr(w["b2"]), ptr(w["wp1d"]), ptr(w["bp1"]),
+                                 ptr(w["wp2d"]), ptr(w["bp2"]), dil, L, ptr(queues), ptr(nsm), ptr(uni), ptr(lg),
+                                 B, P, max_n, n_pad, Th, Q, A, Ap, R, S, ks, U, cmode, cseed, stream()), "decode")
+        self.last_decode_kernel = "stream" if rc == 0 else "direct"
         gen = xs[:, P:]
         if return_logits:
             return gen, lg

@@ -114,8 +114,15 @@ def test_generation_argmax_bit_exact(name):
             nl = list(n_list)
             outs = net.batch_fast_generate(torch.from_numpy(x).cuda(), torch.from_numpy(h).cuda(), nl, mode="argmax")
             assert nl == list(n_list)
+            assert net.last_decode_kernel == "stream"
             for i, o in enumerate(outs):
                 assert np.array_equal(o, g["batch_%d" % i]), (name, i)
+            # the direct-from-L2 kernel (fallback for shapes outside the streaming kernel) gives the same
+            gen = net._decode(torch.from_numpy(x).cuda(), torch.from_numpy(h).cuda(), nl, "argmax", kernel="direct")
+            assert net.last_decode_kernel == "direct"
+            order = sorted(range(B), key=lambda b: (nl[b], b))
+            for i, b in enumerate(order):
+                assert np.array_equal(gen[b, :nl[b]].cpu().numpy(), g["batch_%d" % i]), (name, i, "direct")
         if naive:
             n = min(n_list[0], 8)
             got = net.generate(torch.from_numpy(x[:1]).cuda(), torch.from_numpy(h[:1]).cuda(), n, mode="argmax")
