@@ -233,7 +233,8 @@ def run_ours(args):
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the fused block kernel from the ncu --set full
 # capture committed under profiles/ (filled in by hand from that capture; None = not captured yet)
-TRAFFIC_NCU = {"fp32": None, "tf32": None}
+# tf32: profiles/r1_ncu_resblock_fwd_tc_summary.txt launch 1 (layer 1): 448.57 MB read + 365.57 MB write
+TRAFFIC_NCU = {"fp32": None, "tf32": 814.14e6}
 
 
 def run_decode(args, dev, rank, world, dist):

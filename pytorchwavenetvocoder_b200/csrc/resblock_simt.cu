@@ -348,6 +348,11 @@ static int pick_tchunk(int B, int T, int tiles) {
   return chunk;
 }
 
+// implemented in wgrad_tc.cu
+struct WgOperand { const float* base; int C; int c0; int groups; int shift; };
+int wgrad_tc(const WgOperand* a_ops, int na_ops, const WgOperand* b_ops, int nb_ops, float* c, int ldc, int m_valid,
+             float* db, int B, int T, cudaStream_t st);
+
 // implemented in resblock_tc.cu
 int resblock_fwd_tc(const FwdParams& p, cudaStream_t st);
 bool resblock_fwd_tc_supported(int R, int S, int Ap, int ks);
@@ -432,6 +437,28 @@ WNB_API int wnb_resblock_bwd(const float* xin, const float* haux, const float* d
     if ((rc = launch_nt(p, st)) != WNB_OK) return rc;
   }
   // weight gradients
+  const bool tc_wgrad = math_mode == WNB_MATH_TF32 && R == 64 && ks == 2 && Ap == 32 && S % 32 == 0;
+  if (tc_wgrad) {
+    {  // dW1 (128 x 160) += dpre^T [x(t-d) | x(t) | aux(t)],  db1 = column sums of dpre
+      const WgOperand a[1] = {{dpre, 2 * R, 0, 4, 0}};
+      const WgOperand b[3] = {{xin, R, 0, 2, -dilation}, {xin, R, 0, 2, 0}, {haux, Ap, 0, 1, 0}};
+      if ((rc = wgrad_tc(a, 1, b, 3, dw1, K1, 128, db1, B, T, st)) != WNB_OK) return rc;
+    }
+    // dW2 (R+S x R) += [dout | dskip]^T z in row blocks of 128,  db2 = column sums of [dout | dskip]
+    const WgOperand bz[1] = {{z, R, 0, 2, 0}};
+    const int row_first = dout ? 0 : R;
+    for (int r0 = row_first; r0 < R + S; r0 += 128) {
+      const int m_valid = (R + S - r0) < 128 ? (R + S - r0) : 128;
+      if (r0 == 0) {
+        const WgOperand a[2] = {{dout, R, 0, 2, 0}, {dskip, S, 0, 2, 0}};
+        if ((rc = wgrad_tc(a, 2, bz, 1, dw2, R, m_valid, db2, B, T, st)) != WNB_OK) return rc;
+      } else {
+        const WgOperand a[1] = {{dskip, S, r0 - R, 4, 0}};
+        if ((rc = wgrad_tc(a, 1, bz, 1, dw2 + (size_t)r0 * R, R, m_valid, db2 + r0, B, T, st)) != WNB_OK) return rc;
+      }
+    }
+    return WNB_OK;
+  }
   for (int j = 0; j < ks; j++) {
     TnParams p{dpre, 2 * R, 2 * R, xin, R, R, -(ks - 1 - j) * dilation, 0, dw1, K1, j * R, T, B, 0};
     p.tchunk = pick_tchunk(B, T, cdiv(2 * R, 128) * cdiv(R, kBN));

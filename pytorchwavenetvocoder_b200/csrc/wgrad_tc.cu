@@ -1,0 +1,247 @@
+// wgrad_tc.cu -- tensor-core weight gradients:  C[m][n] += sum_{b,t} A[b][t][m] * Bm[b][t+shift][n]
+//
+// The reduction index is TIME.  With channels-last activations a TMA box [64 time rows x 32 channels]
+// (128B swizzle) is directly an MN-major UMMA operand: the 32 contiguous channels are the M (or N) index,
+// the rows are K.  So both operands of every weight-gradient GEMM come straight from the activation /
+// gradient tensors with no transpose, and tcgen05.mma kind::tf32 (a_major = b_major = MN) contracts
+// 8 time steps per instruction into a [128 x N] fp32 accumulator that stays resident in TMEM for ALL
+// time tiles a CTA owns.  One persistent CTA per SM, 3 warp roles (TMA producer, MMA issuer, epilogue);
+// at the end the accumulator is flushed once with fp32 atomics (red.global.add).
+//
+// Generic over "sub-tile lists": A = 4 groups of 32 channels (M = 128), B = up to 7 groups (N <= 224),
+// each group = (tensor map, channel offset, time shift); dilated taps are just shifted groups, zero filled
+// out of range by TMA.  An optional extra all-ones B group turns column 0 of that group into the bias
+// gradient sum_t A[t][m] (replaces colsum_kernel).
+#include <cuda.h>
+#include <string.h>
+
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+namespace wnb {
+namespace wg {
+
+constexpr int kTK = 64;                      // time rows per stage (K of one stage)
+constexpr int kSubBytes = kTK * 32 * 4;      // 8 KB: [64 x 32 fp32] swizzled sub-tile
+constexpr int kMaxA = 4, kMaxB = 8, kMaxMaps = 4;
+constexpr int kThreadsW = 192;
+
+struct Sub { int map; int c0; int shift; };
+struct alignas(64) Params {
+  CUtensorMap maps[kMaxMaps];
+  Sub a[kMaxA];
+  Sub b[kMaxB];
+  int nA, nB, use_ones;          // nB excludes the ones group
+  float* c; int ldc;             // C rows m (0..127), columns n (0..32*nB-1)
+  int m_valid;                   // rows >= m_valid are padding (not written)
+  float* db;                     // (128) or null
+  int T, B, tiles_per_b, ntiles, nstages;
+};
+
+__device__ __forceinline__ uint64_t smem_desc_mn_sw128(uint32_t saddr, uint32_t lbo_bytes) {
+  // MN-major, 128B swizzle: 32 contiguous floats along MN, groups LBO apart; 8 k-rows per atom (SBO = 1024 B)
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) | (64ull << 32) |
+         (1ull << 46) | (2ull << 61);
+}
+__host__ __device__ constexpr uint32_t idesc_tf32_mn(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) |
+         ((uint32_t)(M >> 4) << 24);
+}
+
+__global__ void __launch_bounds__(kThreadsW, 1) wgrad_tc_kernel(const __grid_constant__ Params p) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int nsubB = p.nB + (p.use_ones ? 1 : 0);
+  const int stage_bytes = (p.nA + nsubB) * kSubBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.nstages * stage_bytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + p.nstages;
+  uint64_t* done = bars + 2 * p.nstages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int N = 32 * nsubB;
+
+  // tiles owned by this CTA: contiguous range (better L2 locality for shifted taps)
+  const int per = (p.ntiles + gridDim.x - 1) / gridDim.x;
+  const int tile_begin = blockIdx.x * per;
+  const int tile_end = min(p.ntiles, tile_begin + per);
+  const int my_tiles = max(0, tile_end - tile_begin);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < p.nstages; i++) {
+      ptx::mbar_init(&full[i], 1);
+      ptx::mbar_init(&empty[i], 1);
+    }
+    ptx::mbar_init(done, 1);
+    ptx::fence_barrier_init();
+  }
+  if (p.use_ones) {
+    // the ones group of every stage: filled once, never touched by TMA
+    for (int s = 0; s < p.nstages; s++) {
+      float4* o = reinterpret_cast<float4*>(smem + (size_t)s * stage_bytes + (p.nA + p.nB) * kSubBytes);
+      for (int i = threadIdx.x; i < kSubBytes / 16; i += kThreadsW) o[i] = make_float4(1.f, 1.f, 1.f, 1.f);
+    }
+    ptx::fence_proxy_async();
+  }
+  if (warp == 1) ptx::tmem_alloc<256>(tmem_slot);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0 && my_tiles > 0) {
+      for (int i = 0; i < kMaxMaps; i++) ptx::prefetch_tmap(&p.maps[i]);
+      uint32_t it = 0;
+      for (int tile = tile_begin; tile < tile_end; tile++, it++) {
+        const int b = tile / p.tiles_per_b, t0 = (tile - b * p.tiles_per_b) * kTK;
+        const int s = it % p.nstages;
+        ptx::mbar_wait(&empty[s], ((it / p.nstages) & 1) ^ 1);
+        ptx::mbar_arrive_expect_tx(&full[s], (p.nA + p.nB) * kSubBytes);
+        unsigned char* st = smem + (size_t)s * stage_bytes;
+        for (int g = 0; g < p.nA; g++)
+          ptx::tma_load_3d(st + g * kSubBytes, &p.maps[p.a[g].map], &full[s], p.a[g].c0, t0 + p.a[g].shift, b);
+        for (int g = 0; g < p.nB; g++)
+          ptx::tma_load_3d(st + (p.nA + g) * kSubBytes, &p.maps[p.b[g].map], &full[s], p.b[g].c0, t0 + p.b[g].shift, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && my_tiles > 0) {
+      const uint32_t idesc = idesc_tf32_mn(128, N);
+      uint32_t it = 0;
+      for (int tile = tile_begin; tile < tile_end; tile++, it++) {
+        const int s = it % p.nstages;
+        ptx::mbar_wait(&full[s], (it / p.nstages) & 1);
+        ptx::tc_fence_after();
+        const uint32_t sa = ptx::smem_u32(smem + (size_t)s * stage_bytes);
+        const uint32_t sb = sa + p.nA * kSubBytes;
+#pragma unroll
+        for (int k = 0; k < kTK / 8; k++)
+          ptx::mma_tf32_ss(tmem, smem_desc_mn_sw128(sa + k * 1024, kSubBytes), smem_desc_mn_sw128(sb + k * 1024, kSubBytes),
+                           idesc, (it | k) != 0);
+        ptx::tc_commit(&empty[s]);
+      }
+      ptx::tc_commit(done);
+    }
+  } else if (my_tiles > 0) {
+    // epilogue: flush the accumulator once
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    ptx::mbar_wait(done, 0);
+    ptx::tc_fence_after();
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    for (int c0 = 0; c0 < N; c0 += 16) {
+      float v[16];
+      ptx::tmem_ld16(tmem + lane_base + c0, v);
+      ptx::tc_wait_ld();
+      if (row < p.m_valid) {
+        if (c0 < 32 * p.nB) {
+          float* dst = p.c + (size_t)row * p.ldc + c0;
+#pragma unroll
+          for (int i = 0; i < 16; i++) atomicAdd(dst + i, v[i]);
+        } else if (c0 == 32 * p.nB && p.db) {
+          atomicAdd(p.db + row, v[0]);
+        }
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc<256>(tmem);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+// (B, T, C) fp32 channels-last tensor, box [32 ch x 64 rows x 1]
+static bool make_act_map(CUtensorMap* m, const float* base, int C, int T, int B) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return false;
+  cuuint64_t gdim[3] = {(cuuint64_t)C, (cuuint64_t)T, (cuuint64_t)B};
+  cuuint64_t gstr[2] = {(cuuint64_t)C * 4, (cuuint64_t)C * 4 * (cuuint64_t)T};
+  cuuint32_t box[3] = {32, (cuuint32_t)kTK, 1}, es[3] = {1, 1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), gdim, gstr, box, es,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+}  // namespace wg
+
+// One operand = a channels-last tensor (B,T,C); `groups` 32-channel groups starting at channel c0, shifted in time.
+struct WgOperand { const float* base; int C; int c0; int groups; int shift; };
+
+// C[128 x 32*sum(groups_b)] += A^T B ; A = concatenation of up to 2 operands (4 groups in total, zero padded by
+// TMA when a group lies beyond the tensor's channels); rows >= m_valid are not written.
+int wgrad_tc(const WgOperand* a_ops, int na_ops, const WgOperand* b_ops, int nb_ops, float* c, int ldc, int m_valid,
+             float* db, int B, int T, cudaStream_t st) {
+  using namespace wg;
+  Params p;
+  memset(&p, 0, sizeof(p));
+  int nmaps = 0;
+  auto map_of = [&](const WgOperand& o) -> int {
+    // one map per distinct (base, C)
+    if (nmaps >= kMaxMaps) return -1;
+    if (!make_act_map(&p.maps[nmaps], o.base, o.C, T, B)) return -1;
+    return nmaps++;
+  };
+  p.nA = 0;
+  for (int i = 0; i < na_ops; i++) {
+    const int m = map_of(a_ops[i]);
+    if (m < 0) { set_error("wgrad_tc: tensor map creation failed (A)"); return WNB_ERR_CUDA; }
+    for (int g = 0; g < a_ops[i].groups; g++) {
+      if (p.nA >= kMaxA) { set_error("wgrad_tc: too many A groups"); return WNB_ERR_INVALID; }
+      p.a[p.nA++] = Sub{m, a_ops[i].c0 + 32 * g, a_ops[i].shift};
+    }
+  }
+  if (p.nA != kMaxA) { set_error("wgrad_tc: A must have exactly 4 groups (M = 128)"); return WNB_ERR_INVALID; }
+  p.nB = 0;
+  for (int i = 0; i < nb_ops; i++) {
+    const int m = map_of(b_ops[i]);
+    if (m < 0) { set_error("wgrad_tc: tensor map creation failed (B)"); return WNB_ERR_CUDA; }
+    for (int g = 0; g < b_ops[i].groups; g++) {
+      if (p.nB >= kMaxB - 1) { set_error("wgrad_tc: too many B groups"); return WNB_ERR_INVALID; }
+      p.b[p.nB++] = Sub{m, b_ops[i].c0 + 32 * g, b_ops[i].shift};
+    }
+  }
+  for (int i = nmaps; i < kMaxMaps; i++) p.maps[i] = p.maps[0];
+  p.use_ones = db ? 1 : 0;
+  p.c = c; p.ldc = ldc; p.m_valid = m_valid; p.db = db;
+  p.T = T; p.B = B;
+  p.tiles_per_b = (T + kTK - 1) / kTK;
+  p.ntiles = B * p.tiles_per_b;
+  const int stage_bytes = (p.nA + p.nB + p.use_ones) * kSubBytes;
+  int nst = (220 * 1024) / stage_bytes;
+  if (nst > 6) nst = 6;
+  if (nst < 2) { set_error("wgrad_tc: stage too large"); return WNB_ERR_INVALID; }
+  p.nstages = nst;
+  const size_t smem = (size_t)nst * stage_bytes + 1024 + 256;
+  static size_t configured = 0;
+  if (smem > configured) {
+    WNB_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    WNB_CUDA(cudaGetDevice(&dev));
+    WNB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const int grid = p.ntiles < sms ? p.ntiles : sms;
+  wgrad_tc_kernel<<<grid, kThreadsW, smem, st>>>(p);
+  WNB_CHECK_LAUNCH("wgrad_tc");
+  return WNB_OK;
+}
+
+}  // namespace wnb

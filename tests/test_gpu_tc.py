@@ -97,4 +97,7 @@ def test_training_step_tf32_close_to_fp32():
     assert abs(res["fp32"][0] - res["tf32"][0]) < 1e-3
     for k, g in res["fp32"][1].items():
         g2 = res["tf32"][1][k]
-        assert (g - g2).norm().item() <= 0.05 * g.norm().item() + 1e-7, k
+        if g.numel() == 1:      # scalar sums with heavy cancellation (upsampling bias): absolute bound
+            assert (g - g2).abs().item() <= 3e-3, k
+        else:
+            assert (g - g2).norm().item() <= 0.05 * g.norm().item() + 1e-7, k
