@@ -163,6 +163,18 @@ WNB_API int wnb_decode_stream(int32_t* xs, const float* h, const float* up_w, co
                               int Th, int Q, int A, int Ap, int R, int S, int ks, int U, int mode,
                               uint64_t seed, void* stream_handle);
 
+/* ---- a14-a16, warp-tiled variant for the BASELINE shape (R 64, S 512, Q 256, Ap 32, ks 2): same contract,
+ * weights as ONE stream in warp-tile order (layout documented in csrc/decode_warp.cu; built by
+ * nets/wavenet.py::_decode_warp_pack). */
+WNB_API size_t wnb_decode_warp_floats(int L);
+WNB_API int wnb_decode_warp_supported(int Q, int Ap, int R, int S, int ks, int L);
+WNB_API int wnb_decode_warp(int32_t* xs, const float* h, const float* up_w, const float* up_b, const float* wf,
+                            const float* bf, const float* stream, const float* b1, const float* b2,
+                            const float* bp1, const float* bp2, const int32_t* host_dilations, int L,
+                            void* queues, const int32_t* n_samples, const float* uniforms, float* logits_out,
+                            int B, int P, int max_n, int n_pad, int Th, int A, int U, int mode, uint64_t seed,
+                            void* stream_handle);
+
 #ifdef __cplusplus
 }
 #endif

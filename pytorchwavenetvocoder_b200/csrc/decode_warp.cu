@@ -1,0 +1,562 @@
+// decode_warp.cu -- persistent fast-generate kernel, v3, specialised for the BASELINE arctic shape
+// (n_resch 64, n_skipch 512, n_quantize 256, aux <= 32, kernel_size 2; any depth/repeat).
+//
+// v2 (decode_stream.cu) removed the L2 latency from the chain but still spent ~14k cycles per layer in
+// six under-populated phases separated by block-wide barriers.  v3 keeps the weight-stream ring (producer
+// warp + cp.async.bulk + mbarriers) and restructures the consumers around WARPS:
+//   * the stream is packed in "warp tile" order so that every shared-memory read is a conflict-free,
+//     fully used 128-byte wavefront;
+//   * gate GEMV (128 x 160): warp w owns gate channels 8w..8w+7 (sigmoid and tanh rows), its lanes split
+//     K, and a shuffle reduce-scatter leaves each pre-activation in one lane -> the gate is evaluated in
+//     registers, no shared-memory partial sums, no extra barrier;
+//   * res GEMV (64 x 64): same scheme; the warp that owns residual channels 8w..8w+7 updates them in place
+//     and pushes them into the NEXT layer's dilation queue;
+//   * skip GEMV (512 x 64) and the post network: lanes split the OUTPUTS (2 per lane), so the running skip
+//     sum of all layers lives in registers for the whole step (python order `0 + s0 + s1 ...` kept);
+//   * two barriers per layer instead of six.
+// Per step the floor is the shared-memory read of the 8.6 MB of weights (67k cycles) or the L2->smem
+// stream, whichever is slower; utterances sharing a CTA (NU = 2, 4) reuse both.
+// Numerics identical in kind to v1/v2: fp32 FFMA, precise expf/tanhf, first-max argmax, Philox sampling.
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+namespace wnb {
+namespace dw {
+
+constexpr int kR = 64, kS = 512, kQ = 256, kAp = 32, kK1 = 160;
+constexpr int kCons = 256, kThreadsD = kCons + 32;
+constexpr int kSlot = 32 * 1024;
+constexpr int kMaxL = 64;
+// stream layout per layer (floats): W1 [5][8][32][16] | W2res [2][8][32][8] | W2skip [64][8][64]
+constexpr int kW1Floats = 5 * 8 * 32 * 16;       // 20480 (80 KB) -> chunks 32K,32K,16K bytes
+constexpr int kWresFloats = 2 * 8 * 32 * 8;      // 4096  (16 KB) -> 1 chunk
+constexpr int kWskipFloats = 64 * 8 * 64;        // 32768 (128 KB) -> 4 chunks
+constexpr int kLayerFloats = kW1Floats + kWresFloats + kWskipFloats;
+constexpr int kP1Floats = 512 * 8 * 64;          // post1 [512][8][64]  (1 MB)  -> 32 chunks
+constexpr int kP2Floats = 512 * 8 * 32;          // post2 [512][8][32]  (512 KB)-> 16 chunks
+
+struct Params {
+  int32_t* xs; const float* h; const float* up_w; const float* up_b;
+  const float *wf, *bf, *b1, *b2, *bp1, *bp2;
+  const float* stream;
+  float* queues; const int32_t* n_samples; const float* uniforms; float* logits_out;
+  int B, P, max_n, n_pad, Th, A, U, mode, L, nslot;
+  unsigned long long seed;
+  int dil[kMaxL];
+  long long qoff[kMaxL];
+  long long q_per_utt;
+};
+
+__device__ __forceinline__ void bulk_g2s(void* smem, const void* gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(ptx::smem_u32(smem)), "l"(gmem), "r"(bytes), "r"(ptx::smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void cons_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+struct Ring {
+  unsigned char* base; uint64_t* full; uint64_t* empty; int nslot; uint32_t idx;
+  __device__ __forceinline__ const float* acquire() {   // consumer: wait for the current chunk
+    const int slot = idx % nslot;
+    ptx::mbar_wait(&full[slot], (idx / nslot) & 1);
+    return reinterpret_cast<const float*>(base + (size_t)slot * kSlot);
+  }
+  __device__ __forceinline__ void release() {           // consumer: whole warp done with the current chunk
+    const int slot = idx % nslot;
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) ptx::mbar_arrive(&empty[slot]);
+    idx++;
+  }
+  __device__ __forceinline__ void push(const float* src, uint32_t bytes) {  // producer
+    const int slot = idx % nslot;
+    ptx::mbar_wait(&empty[slot], ((idx / nslot) & 1) ^ 1);
+    ptx::mbar_arrive_expect_tx(&full[slot], bytes);
+    bulk_g2s(base + (size_t)slot * kSlot, src, bytes, &full[slot]);
+    idx++;
+  }
+};
+
+// Recursive-halving reduce-scatter over the 32 lanes of a warp: every lane contributes v[0..NV); afterwards
+// the total of value j is written to dst[j] by exactly one lane.  NV in {8, 16, 32, 64}.
+template <int NV>
+__device__ __forceinline__ void warp_reduce_scatter(float (&v)[NV], float* dst, int lane) {
+  int base = 0;
+  if constexpr (NV >= 2) {
+#pragma unroll
+    for (int lvl = 0; lvl < 5; lvl++) {
+      const int off = 16 >> lvl;
+      const int n = NV >> lvl;        // values held before this level
+      if (n >= 2) {
+        const int half = n >> 1;
+        const bool up = (lane & off) != 0;
+#pragma unroll
+        for (int t = 0; t < NV / 2; t++) {
+          if (t < half) {
+            const float send = up ? v[t] : v[t + half];
+            const float keep = up ? v[t + half] : v[t];
+            v[t] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+          }
+        }
+        base += up ? half : 0;
+      } else {
+        v[0] += __shfl_xor_sync(0xffffffffu, v[0], off);
+      }
+    }
+  }
+  constexpr int kLeft = (NV >= 32) ? NV / 32 : 1;           // values per lane at the end
+  constexpr int kDup = (NV >= 32) ? 1 : 32 / NV;            // lanes holding the same total
+  if ((lane & (kDup - 1)) == 0) {
+#pragma unroll
+    for (int t = 0; t < kLeft; t++) dst[base + t] = v[t];
+  }
+}
+
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                              uint32_t k1, uint32_t (&out)[4]) {
+#pragma unroll
+  for (int i = 0; i < 10; i++) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+template <int NU>
+__global__ void __launch_bounds__(kThreadsD, 1) decode_warp_kernel(const Params p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int L = p.L;
+  unsigned char* ring_base = smem_raw;
+  uint64_t* full = reinterpret_cast<uint64_t*>(ring_base + (size_t)p.nslot * kSlot);
+  uint64_t* empty = full + p.nslot;
+  float* fw = reinterpret_cast<float*>(empty + p.nslot);
+  float* cur = fw;                          // [NU][64]
+  float* zs = cur + NU * kR;                // [NU][64]
+  float* hcol = zs + NU * kR;               // [NU][32]
+  float* skipx = hcol + NU * kAp;           // [NU][512]  relu(skip sum) / post hidden input
+  float* h1 = skipx + NU * kS;              // [NU][512]
+  float* logit = h1 + NU * kS;              // [NU][256]
+  float* pre_s = logit + NU * kQ;           // [8 warps][16*NU]
+  float* qtap = pre_s + 8 * 16 * NU;        // [NU][L][64]
+  __shared__ int s_n[NU];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int u0 = blockIdx.x * NU;
+  const int stride_xs = p.P + p.max_n;
+
+  if (tid == 0) {
+    for (int i = 0; i < p.nslot; i++) {
+      ptx::mbar_init(&full[i], 1);
+      ptx::mbar_init(&empty[i], kCons / 32);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (tid < NU) s_n[tid] = (u0 + tid < p.B) ? p.n_samples[u0 + tid] : 0;
+  __syncthreads();
+  int nmax = 0;
+#pragma unroll
+  for (int u = 0; u < NU; u++) nmax = max(nmax, s_n[u]);
+  if (nmax == 0) return;
+  const int last_pos = p.P - 1 + nmax - 1;
+  Ring ring{ring_base, full, empty, p.nslot, 0u};
+
+  if (warp == kCons / 32) {
+    // ================================ producer warp ================================
+    if (lane == 0) {
+      for (int pos = 0; pos <= last_pos; pos++) {
+        const bool want = pos >= p.P - 1;
+        for (int l = 0; l < L; l++) {
+          const float* base = p.stream + (size_t)l * kLayerFloats;
+          ring.push(base, 32768);                       // W1 j = 0,1
+          ring.push(base + 8192, 32768);                // W1 j = 2,3
+          ring.push(base + 16384, 16384);               // W1 j = 4
+          ring.push(base + kW1Floats, 16384);           // W2res
+          if (want)
+            for (int c = 0; c < 4; c++) ring.push(base + kW1Floats + kWresFloats + c * 8192, 32768);
+        }
+        if (want) {
+          const float* p1 = p.stream + (size_t)L * kLayerFloats;
+          for (int c = 0; c < 32; c++) ring.push(p1 + (size_t)c * 8192, 32768);
+          const float* p2 = p1 + kP1Floats;
+          for (int c = 0; c < 16; c++) ring.push(p2 + (size_t)c * 8192, 32768);
+        }
+      }
+    }
+    return;
+  }
+
+  // ================================ consumer warps ================================
+  float* my_pre = pre_s + warp * 16 * NU;
+  for (int pos = 0; pos <= last_pos; pos++) {
+    const bool want = pos >= p.P - 1;
+    // ---- step prologue: front gather, aux column, all queue taps ----
+    for (int e = tid; e < NU * kR; e += kCons) {
+      const int u = e >> 6, r = e & 63;
+      const int ug = min(u0 + u, p.B - 1);
+      float v = __ldg(p.bf + r);
+#pragma unroll
+      for (int k = 0; k < 2; k++) {
+        const int pp = pos - (1 - k);
+        if (pp >= 0) {
+          int q = p.xs[(size_t)ug * stride_xs + pp] % kQ;
+          if (q < 0) q += kQ;
+          v += __ldg(p.wf + ((size_t)k * kQ + q) * kR + r);
+        }
+      }
+      cur[e] = v;
+    }
+    for (int e = tid; e < NU * kAp; e += kCons) {
+      const int u = e >> 5, a = e & 31;
+      const int ug = min(u0 + u, p.B - 1);
+      float v = 0.f;
+      if (a < p.A) {
+        const int j = max(pos - p.n_pad, 0);
+        if (p.U > 0) {
+          const int tf = min(j / p.U, p.Th - 1), jj = j % p.U;
+          v = fmaf(__ldg(p.h + ((size_t)ug * p.A + a) * p.Th + tf), __ldg(p.up_w + jj), __ldg(p.up_b));
+        } else {
+          v = __ldg(p.h + ((size_t)ug * p.A + a) * p.Th + min(j, p.Th - 1));
+        }
+      }
+      hcol[e] = v;
+    }
+    for (int e = tid; e < NU * L * kR; e += kCons) {
+      const int r = e & 63;
+      const int l = (e >> 6) % L;
+      const int u = e / (L * kR);
+      const int ug = min(u0 + u, p.B - 1);
+      const int d = p.dil[l];
+      float v = 0.f;
+      // tap = this layer's input at time pos - d: ring slot (pos - d) % d == pos % d, i.e. the slot that is
+      // overwritten with the time-`pos` input later in THIS step -> all reads happen here, before the barrier
+      if (pos - d >= 0) {
+        const float* q = p.queues + (size_t)ug * p.q_per_utt + p.qoff[l];
+        v = __ldcg(q + (size_t)(pos % d) * kR + r);
+      }
+      qtap[e] = v;
+    }
+    cons_sync();
+    // layer 0's input (the front output) goes into its queue only now, after every tap has been read
+    for (int e = tid; e < NU * kR; e += kCons) {
+      const int u = e >> 6, r = e & 63;
+      if (u0 + u < p.B) {
+        float* q0 = p.queues + (size_t)(u0 + u) * p.q_per_utt + p.qoff[0];
+        __stcg(q0 + (size_t)(pos % p.dil[0]) * kR + r, cur[e]);
+      }
+    }
+
+    float skip_tot[NU][2];
+#pragma unroll
+    for (int u = 0; u < NU; u++) skip_tot[u][0] = skip_tot[u][1] = 0.f;
+
+    for (int l = 0; l < L; l++) {
+      // ---------------- phase A: gate pre-activations, split K over lanes ----------------
+      float acc[NU * 16];
+#pragma unroll
+      for (int i = 0; i < NU * 16; i++) acc[i] = 0.f;
+      const float* chunk = nullptr;
+#pragma unroll
+      for (int j = 0; j < 5; j++) {
+        if (j == 0 || j == 2 || j == 4) chunk = ring.acquire();
+        const float4* wp = reinterpret_cast<const float4*>(chunk + (size_t)((j & 1) * 8 + warp) * 512 + lane * 16);
+        const float4 w0 = wp[0], w1 = wp[1], w2 = wp[2], w3 = wp[3];
+#pragma unroll
+        for (int u = 0; u < NU; u++) {
+          const float x = (j < 2) ? qtap[((size_t)u * L + l) * kR + (j * 32 + lane)]
+                                  : (j < 4) ? cur[u * kR + (j - 2) * 32 + lane] : hcol[u * kAp + lane];
+          float* a = acc + u * 16;
+          a[0] = fmaf(w0.x, x, a[0]); a[1] = fmaf(w0.y, x, a[1]); a[2] = fmaf(w0.z, x, a[2]); a[3] = fmaf(w0.w, x, a[3]);
+          a[4] = fmaf(w1.x, x, a[4]); a[5] = fmaf(w1.y, x, a[5]); a[6] = fmaf(w1.z, x, a[6]); a[7] = fmaf(w1.w, x, a[7]);
+          a[8] = fmaf(w2.x, x, a[8]); a[9] = fmaf(w2.y, x, a[9]); a[10] = fmaf(w2.z, x, a[10]); a[11] = fmaf(w2.w, x, a[11]);
+          a[12] = fmaf(w3.x, x, a[12]); a[13] = fmaf(w3.y, x, a[13]); a[14] = fmaf(w3.z, x, a[14]); a[15] = fmaf(w3.w, x, a[15]);
+        }
+        if (j == 1 || j == 3 || j == 4) ring.release();
+      }
+      warp_reduce_scatter<NU * 16>(acc, my_pre, lane);
+      __syncwarp();
+      if (lane < 8 * NU) {
+        const int u = lane >> 3, cc = lane & 7, c = warp * 8 + cc;
+        const float a = my_pre[u * 16 + cc] + __ldg(p.b1 + (size_t)l * 128 + c);
+        const float g = my_pre[u * 16 + 8 + cc] + __ldg(p.b1 + (size_t)l * 128 + 64 + c);
+        zs[u * kR + c] = sigmoidf_(a) * tanhf(g);
+      }
+      cons_sync();
+      // ---------------- phase B: residual 1x1 (split K) ----------------
+      {
+        float racc[NU * 8];
+#pragma unroll
+        for (int i = 0; i < NU * 8; i++) racc[i] = 0.f;
+        const float* rc = ring.acquire();
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+          const float4* wp = reinterpret_cast<const float4*>(rc + (size_t)(j * 8 + warp) * 256 + lane * 8);
+          const float4 w0 = wp[0], w1 = wp[1];
+#pragma unroll
+          for (int u = 0; u < NU; u++) {
+            const float x = zs[u * kR + j * 32 + lane];
+            float* a = racc + u * 8;
+            a[0] = fmaf(w0.x, x, a[0]); a[1] = fmaf(w0.y, x, a[1]); a[2] = fmaf(w0.z, x, a[2]); a[3] = fmaf(w0.w, x, a[3]);
+            a[4] = fmaf(w1.x, x, a[4]); a[5] = fmaf(w1.y, x, a[5]); a[6] = fmaf(w1.z, x, a[6]); a[7] = fmaf(w1.w, x, a[7]);
+          }
+        }
+        ring.release();
+        warp_reduce_scatter<NU * 8>(racc, my_pre, lane);
+        __syncwarp();
+        if (lane < 8 * NU) {
+          const int u = lane >> 3, cc = lane & 7, c = warp * 8 + cc;
+          const float v = my_pre[u * 8 + cc] + __ldg(p.b2 + (size_t)l * (kR + kS) + c) + cur[u * kR + c];
+          cur[u * kR + c] = v;
+          if (l + 1 < L && u0 + u < p.B) {   // input of layer l+1 at time `pos` -> its dilation queue
+            float* q = p.queues + (size_t)(u0 + u) * p.q_per_utt + p.qoff[l + 1];
+            __stcg(q + (size_t)(pos % p.dil[l + 1]) * kR + c, v);
+          }
+        }
+      }
+      // ---------------- phase B': skip 1x1, lanes own outputs 64*warp + 2*lane (+1) ----------------
+      if (want) {
+        float s[NU][2];
+#pragma unroll
+        for (int u = 0; u < NU; u++) s[u][0] = s[u][1] = 0.f;
+#pragma unroll 1
+        for (int c4 = 0; c4 < 4; c4++) {
+          const float* sc = ring.acquire();
+#pragma unroll
+          for (int k4 = 0; k4 < 16; k4 += 4) {
+            float4 zv[NU];
+#pragma unroll
+            for (int u = 0; u < NU; u++) zv[u] = *reinterpret_cast<const float4*>(zs + u * kR + c4 * 16 + k4);
+#pragma unroll
+            for (int kk = 0; kk < 4; kk++) {
+              const float2 wv = *reinterpret_cast<const float2*>(sc + (size_t)((k4 + kk) * 8 + warp) * 64 + lane * 2);
+#pragma unroll
+              for (int u = 0; u < NU; u++) {
+                const float z = kk == 0 ? zv[u].x : kk == 1 ? zv[u].y : kk == 2 ? zv[u].z : zv[u].w;
+                s[u][0] = fmaf(wv.x, z, s[u][0]);
+                s[u][1] = fmaf(wv.y, z, s[u][1]);
+              }
+            }
+          }
+          ring.release();
+        }
+        const float2 bv = *reinterpret_cast<const float2*>(p.b2 + (size_t)l * (kR + kS) + kR + warp * 64 + lane * 2);
+#pragma unroll
+        for (int u = 0; u < NU; u++) {
+          const float s0 = s[u][0] + bv.x, s1 = s[u][1] + bv.y;
+          skip_tot[u][0] = (l == 0) ? s0 : skip_tot[u][0] + s0;   // python `0 + s0 + s1 ...`, wavenet.py:374
+          skip_tot[u][1] = (l == 0) ? s1 : skip_tot[u][1] + s1;
+        }
+      }
+      cons_sync();
+    }
+
+    if (want) {
+      // ---------------- post network ----------------
+#pragma unroll
+      for (int u = 0; u < NU; u++)
+        *reinterpret_cast<float2*>(skipx + u * kS + warp * 64 + lane * 2) =
+            make_float2(fmaxf(skip_tot[u][0], 0.f), fmaxf(skip_tot[u][1], 0.f));
+      cons_sync();
+      {
+        float s[NU][2];
+#pragma unroll
+        for (int u = 0; u < NU; u++) s[u][0] = s[u][1] = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < 32; c++) {
+          const float* pc = ring.acquire();
+#pragma unroll
+          for (int k4 = 0; k4 < 16; k4 += 4) {
+            float4 xv[NU];
+#pragma unroll
+            for (int u = 0; u < NU; u++) xv[u] = *reinterpret_cast<const float4*>(skipx + u * kS + c * 16 + k4);
+#pragma unroll
+            for (int kk = 0; kk < 4; kk++) {
+              const float2 wv = *reinterpret_cast<const float2*>(pc + (size_t)((k4 + kk) * 8 + warp) * 64 + lane * 2);
+#pragma unroll
+              for (int u = 0; u < NU; u++) {
+                const float x = kk == 0 ? xv[u].x : kk == 1 ? xv[u].y : kk == 2 ? xv[u].z : xv[u].w;
+                s[u][0] = fmaf(wv.x, x, s[u][0]);
+                s[u][1] = fmaf(wv.y, x, s[u][1]);
+              }
+            }
+          }
+          ring.release();
+        }
+        const float2 bv = *reinterpret_cast<const float2*>(p.bp1 + warp * 64 + lane * 2);
+#pragma unroll
+        for (int u = 0; u < NU; u++)
+          *reinterpret_cast<float2*>(h1 + u * kS + warp * 64 + lane * 2) =
+              make_float2(fmaxf(s[u][0] + bv.x, 0.f), fmaxf(s[u][1] + bv.y, 0.f));
+      }
+      cons_sync();
+      const int i = pos - (p.P - 1);
+      {
+        float s[NU];
+#pragma unroll
+        for (int u = 0; u < NU; u++) s[u] = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < 16; c++) {
+          const float* pc = ring.acquire();
+#pragma unroll
+          for (int k4 = 0; k4 < 32; k4 += 4) {
+            float4 xv[NU];
+#pragma unroll
+            for (int u = 0; u < NU; u++) xv[u] = *reinterpret_cast<const float4*>(h1 + u * kS + c * 32 + k4);
+#pragma unroll
+            for (int kk = 0; kk < 4; kk++) {
+              const float wv = pc[(size_t)((k4 + kk) * 8 + warp) * 32 + lane];
+#pragma unroll
+              for (int u = 0; u < NU; u++) {
+                const float x = kk == 0 ? xv[u].x : kk == 1 ? xv[u].y : kk == 2 ? xv[u].z : xv[u].w;
+                s[u] = fmaf(wv, x, s[u]);
+              }
+            }
+          }
+          ring.release();
+        }
+        const float bv = __ldg(p.bp2 + warp * 32 + lane);
+#pragma unroll
+        for (int u = 0; u < NU; u++) {
+          const float v = s[u] + bv;
+          logit[u * kQ + warp * 32 + lane] = v;
+          if (p.logits_out && u0 + u < p.B && i < s_n[u])
+            p.logits_out[((size_t)(u0 + u) * p.max_n + i) * kQ + warp * 32 + lane] = v;
+        }
+      }
+      cons_sync();
+      // ---------------- pick: warp u handles utterance u ----------------
+      if (warp < NU) {
+        const int u = warp;
+        const float* lg = logit + u * kQ;
+        const int q0 = lane * 8, q1 = q0 + 8;
+        float best = -INFINITY;
+        int bi = 0x7fffffff;
+        for (int q = q0; q < q1; q++)
+          if (lg[q] > best) { best = lg[q]; bi = q; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+          const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+          if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+        }
+        int pick = bi;
+        if (p.mode == WNB_MODE_SAMPLING) {
+          float uni;
+          if (p.uniforms) {
+            uni = p.uniforms[(size_t)min(u0 + u, p.B - 1) * p.max_n + min(i, p.max_n - 1)];
+          } else {
+            uint32_t rr[4];
+            philox4x32_10((uint32_t)i, (uint32_t)(u0 + u), 0u, 0u, (uint32_t)p.seed, (uint32_t)(p.seed >> 32), rr);
+            uni = (float)(rr[0] >> 8) * (1.0f / 16777216.0f);
+          }
+          float lsum = 0.f;
+          for (int q = q0; q < q1; q++) lsum += expf(lg[q] - best);
+          float incl = lsum;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const float v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+          }
+          const float total = __shfl_sync(0xffffffffu, incl, 31);
+          const float target = uni * total;
+          const float excl = incl - lsum;
+          int cand = 0x7fffffff;
+          if (target < incl && target >= excl) {
+            float c = excl;
+            cand = q1 - 1;
+            for (int q = q0; q < q1; q++) {
+              c += expf(lg[q] - best);
+              if (c > target) { cand = q; break; }
+            }
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) cand = min(cand, __shfl_xor_sync(0xffffffffu, cand, o));
+          pick = (cand == 0x7fffffff) ? kQ - 1 : cand;
+        }
+        if (lane == 0 && u0 + u < p.B && i < s_n[u]) p.xs[(size_t)(u0 + u) * stride_xs + pos + 1] = pick;
+      }
+      cons_sync();
+    }
+  }
+}
+
+}  // namespace dw
+
+int decode_warp_launch(dw::Params& p, cudaStream_t st) {
+  using namespace dw;
+  int NU = 1;
+  if (p.B > 148 * 2) NU = 4; else if (p.B > 148) NU = 2;
+  size_t work = 0;
+  int nslot = 0;
+  for (;;) {
+    work = ((size_t)NU * (kR * 2 + kAp + 2 * kS + kQ + (size_t)p.L * kR) + 8 * 16 * NU) * sizeof(float);
+    const long avail = 227L * 1024 - 256 - (long)work - 16 * 16;
+    nslot = (int)(avail / kSlot);
+    if (nslot > 6) nslot = 6;
+    if (nslot >= 3 || NU == 1) break;
+    NU >>= 1;
+  }
+  if (nslot < 2) return WNB_ERR_UNSUPPORTED;
+  p.nslot = nslot;
+  const size_t smem = (size_t)nslot * kSlot + 2 * nslot * sizeof(uint64_t) + work;
+  const int grid = cdiv(p.B, NU);
+#define WNB_LAUNCH_DW(N)                                                                                       \
+  do {                                                                                                         \
+    WNB_CUDA(cudaFuncSetAttribute(decode_warp_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    decode_warp_kernel<N><<<grid, kThreadsD, smem, st>>>(p);                                                   \
+  } while (0)
+  if (NU == 4) WNB_LAUNCH_DW(4);
+  else if (NU == 2) WNB_LAUNCH_DW(2);
+  else WNB_LAUNCH_DW(1);
+#undef WNB_LAUNCH_DW
+  WNB_CHECK_LAUNCH("decode_warp");
+  return WNB_OK;
+}
+
+}  // namespace wnb
+
+using namespace wnb;
+
+extern "C" {
+
+// floats of the warp-tiled decode stream (layout: csrc/decode_warp.cu header) for L layers
+WNB_API size_t wnb_decode_warp_floats(int L) {
+  return (size_t)L * dw::kLayerFloats + dw::kP1Floats + dw::kP2Floats;
+}
+
+// 1 when the warp-tiled kernel covers the configuration
+WNB_API int wnb_decode_warp_supported(int Q, int Ap, int R, int S, int ks, int L) {
+  return (Q == dw::kQ && Ap == dw::kAp && R == dw::kR && S == dw::kS && ks == 2 && L >= 1 && L <= dw::kMaxL) ? 1 : 0;
+}
+
+WNB_API int wnb_decode_warp(int32_t* xs, const float* h, const float* up_w, const float* up_b, const float* wf,
+                            const float* bf, const float* stream, const float* b1, const float* b2, const float* bp1,
+                            const float* bp2, const int32_t* host_dilations, int L, void* queues,
+                            const int32_t* n_samples, const float* uniforms, float* logits_out, int B, int P,
+                            int max_n, int n_pad, int Th, int A, int U, int mode, uint64_t seed, void* stream_handle) {
+  WNB_REQUIRE(B > 0 && P >= 1 && max_n >= 1 && Th >= 1 && A > 0 && A <= dw::kAp && U >= 0 && L >= 1 && L <= dw::kMaxL,
+              "decode_warp: bad shape");
+  WNB_REQUIRE(xs && h && wf && bf && stream && b1 && b2 && bp1 && bp2 && n_samples && queues,
+              "decode_warp: null pointer");
+  WNB_REQUIRE(U == 0 || (up_w && up_b), "decode_warp: U>0 needs upsampling weight and bias");
+  WNB_REQUIRE(mode == WNB_MODE_ARGMAX || mode == WNB_MODE_SAMPLING, "decode_warp: mode should be sampling or argmax");
+  dw::Params p{};
+  p.xs = xs; p.h = h; p.up_w = up_w; p.up_b = up_b; p.wf = wf; p.bf = bf; p.b1 = b1; p.b2 = b2; p.bp1 = bp1;
+  p.bp2 = bp2; p.stream = stream; p.queues = (float*)queues; p.n_samples = n_samples; p.uniforms = uniforms;
+  p.logits_out = logits_out;
+  p.B = B; p.P = P; p.max_n = max_n; p.n_pad = n_pad; p.Th = Th; p.A = A; p.U = U; p.mode = mode; p.L = L;
+  p.seed = seed;
+  long long off = 0;
+  for (int l = 0; l < L; l++) {
+    p.dil[l] = host_dilations[l];
+    p.qoff[l] = off;
+    off += (long long)host_dilations[l] * dw::kR;
+  }
+  p.q_per_utt = off;
+  int rc = decode_warp_launch(p, (cudaStream_t)stream_handle);
+  if (rc == WNB_ERR_UNSUPPORTED) set_error("decode_warp: not enough shared memory for this depth");
+  return rc;
+}
+
+}  // extern "C"

@@ -1,7 +1,7 @@
 // wgrad_tc.cu -- tensor-core weight gradients:  C[m][n] += sum_{b,t} A[b][t][m] * Bm[b][t+shift][n]
 //
 // The reduction index is TIME.  With channels-last activations a TMA box [64 time rows x 32 channels]
-// (128B swizzle) is directly an MN-major UMMA operand: the 32 contiguous channels are the M (or N) index,
+// (128B swizzle with 32B atoms, the only swizzle tf32 MN-major operands accept) is directly an MN-major UMMA operand: the 32 contiguous channels are the M (or N) index,
 // the rows are K.  So both operands of every weight-gradient GEMM come straight from the activation /
 // gradient tensors with no transpose, and tcgen05.mma kind::tf32 (a_major = b_major = MN) contracts
 // 8 time steps per instruction into a [128 x N] fp32 accumulator that stays resident in TMEM for ALL
@@ -39,9 +39,12 @@ struct alignas(64) Params {
 };
 
 __device__ __forceinline__ uint64_t smem_desc_mn_sw128(uint32_t saddr, uint32_t lbo_bytes) {
-  // MN-major, 128B swizzle: 32 contiguous floats along MN, groups LBO apart; 8 k-rows per atom (SBO = 1024 B)
-  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) | (64ull << 32) |
-         (1ull << 46) | (2ull << 61);
+  // MN-major tf32 operands have exactly one legal swizzled layout: SWIZZLE_128B_BASE32B (layout type 1), the
+  // smem image of a TMA box written with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B: rows of 32 contiguous floats
+  // (the MN index) at 128 B pitch, 32-byte atoms XOR-ed with (row & 3); canonical form
+  // ((4,8,m),(4,k)):((1,4,LBO),(32,SBO)) in floats: MN groups LBO apart, 4-row k-groups SBO = 512 B apart.
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) | (32ull << 32) |
+         (1ull << 46) | (1ull << 61);
 }
 __host__ __device__ constexpr uint32_t idesc_tf32_mn(int M, int N) {
   return (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) |
@@ -173,7 +176,7 @@ static bool make_act_map(CUtensorMap* m, const float* base, int C, int T, int B)
   cuuint64_t gstr[2] = {(cuuint64_t)C * 4, (cuuint64_t)C * 4 * (cuuint64_t)T};
   cuuint32_t box[3] = {32, (cuuint32_t)kTK, 1}, es[3] = {1, 1, 1};
   return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), gdim, gstr, box, es,
-             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 

@@ -497,6 +497,20 @@ class WaveNet(nn.Module):
         parts += [w["wp1d"].reshape(-1), w["wp2d"].reshape(-1)]
         return torch.cat(parts).contiguous()
 
+    def _decode_warp_pack(self):
+        """Warp-tile ordered stream for wnb_decode_warp (layout: csrc/decode_warp.cu)."""
+        with torch.no_grad():
+            wf, bf, W1, b1, W2, b2, Wp1, bp1, Wp2, bp2 = [t.detach().float() for t in self._pack()]
+            L = W1.size(0)
+            # W1 (L,128,160)[o][k] -> [j][w][lane][16]: k = 32j+lane, 16 = (sigmoid 8w..8w+7, tanh 8w..8w+7)
+            t1 = W1.reshape(L, 2, 8, 8, 5, 32).permute(0, 4, 2, 5, 1, 3).reshape(L, -1)
+            # W2 res rows (L,64,64)[o][k] -> [j][w][lane][8]: k = 32j+lane, o = 8w+cc
+            tr = W2[:, :64, :].reshape(L, 8, 8, 2, 32).permute(0, 3, 1, 4, 2).reshape(L, -1)
+            # W2 skip rows (L,512,64)[o][k] -> [k][w][64]
+            ts = W2[:, 64:, :].transpose(1, 2).reshape(L, -1)
+            per_layer = torch.cat([t1, tr, ts], 1).reshape(-1)
+            return torch.cat([per_layer, Wp1.t().reshape(-1), Wp2.t().reshape(-1)]).contiguous()
+
     def _decode(self, x, h, n_samples_list, mode, uniforms=None, return_logits=False, seed=None, kernel="auto"):
         lib = _lib.load()
         if mode not in ("sampling", "argmax"):
@@ -533,7 +547,20 @@ class WaveNet(nn.Module):
         cmode = MODE_ARGMAX if mode == "argmax" else MODE_SAMPLING
         cseed = ctypes.c_uint64(seed & 0xFFFFFFFFFFFFFFFF)
         rc = -3
-        if kernel in ("auto", "stream"):
+        self.last_decode_kernel = None
+        if kernel in ("auto", "warp") and lib.wnb_decode_warp_supported(Q, Ap, R, S, ks, L):
+            wstream = self._decode_warp_pack()
+            assert wstream.numel() == lib.wnb_decode_warp_floats(L)
+            rc = lib.wnb_decode_warp(ptr(xs), ptr(h), ptr(upw), ptr(upb), ptr(w["wf"]), ptr(w["bf"]), ptr(wstream),
+                                     ptr(w["b1"]), ptr(w["b2"]), ptr(w["bp1"]), ptr(w["bp2"]), dil, L, ptr(queues),
+                                     ptr(nsm), ptr(uni), ptr(lg), B, P, max_n, n_pad, Th, A, U, cmode, cseed, stream())
+            if rc != -3 or kernel == "warp":
+                check(rc, "decode_warp")
+            if rc == 0:
+                self.last_decode_kernel = "warp"
+        elif kernel == "warp":
+            raise _lib.WnbError("decode kernel 'warp' does not cover this configuration")
+        if rc == -3 and kernel in ("auto", "stream"):
             wstream = self._decode_stream_pack(w)
             assert wstream.numel() == lib.wnb_decode_stream_floats(Q, Ap, R, S, ks, L)
             rc = lib.wnb_decode_stream(ptr(xs), ptr(h), ptr(upw), ptr(upb), ptr(w["wf"]), ptr(w["bf"]), ptr(wstream),
@@ -547,7 +574,8 @@ class WaveNet(nn.Module):
                                  ptr(w["b1"]), ptr(w["w2d"]), ptr(w["b2"]), ptr(w["wp1d"]), ptr(w["bp1"]),
                                  ptr(w["wp2d"]), ptr(w["bp2"]), dil, L, ptr(queues), ptr(nsm), ptr(uni), ptr(lg),
                                  B, P, max_n, n_pad, Th, Q, A, Ap, R, S, ks, U, cmode, cseed, stream()), "decode")
-        self.last_decode_kernel = "stream" if rc == 0 else "direct"
+        if self.last_decode_kernel is None:
+            self.last_decode_kernel = "stream" if rc == 0 else "direct"
         gen = xs[:, P:]
         if return_logits:
             return gen, lg

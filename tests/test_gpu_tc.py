@@ -101,3 +101,37 @@ def test_training_step_tf32_close_to_fp32():
             assert (g - g2).abs().item() <= 3e-3, k
         else:
             assert (g - g2).norm().item() <= 0.05 * g.norm().item() + 1e-7, k
+
+
+def test_block_backward_tf32_vs_fp32_single_layer():
+    """wnb_resblock_bwd in tf32 mode (tcgen05 weight gradients) vs the all-FFMA path, one block."""
+    from pytorchwavenetvocoder_b200 import _lib
+    lib = _lib.load()
+    torch.manual_seed(5)
+    B, T, R, S, Ap, d = 2, 1000, 64, 512, 32, 4
+    K1 = 2 * R + Ap
+    xin = torch.randn(B, T, R, device="cuda")
+    haux = torch.randn(B, T, Ap, device="cuda"); haux[:, :, 28:] = 0
+    dout = torch.randn(B, T, R, device="cuda")
+    dskip = torch.randn(B, T, S, device="cuda")
+    W1 = (torch.randn(2 * R, K1, device="cuda") / np.sqrt(K1)).contiguous()
+    W2 = (torch.randn(R + S, R, device="cuda") / np.sqrt(R)).contiguous()
+    b1 = 0.1 * torch.randn(2 * R, device="cuda")
+    w1t, w2t = W1.t().contiguous(), W2.t().contiguous()
+    ws = torch.empty(lib.wnb_resblock_bwd_workspace(B, T, R, S, Ap, 2) // 4, device="cuda")
+    out = {}
+    for mode in (_lib.MATH_FP32, _lib.MATH_TF32):
+        dx = torch.empty(B, T, R, device="cuda")
+        dh = torch.zeros(B, T, Ap, device="cuda")
+        dw1, db1 = torch.zeros(2 * R, K1, device="cuda"), torch.zeros(2 * R, device="cuda")
+        dw2, db2 = torch.zeros(R + S, R, device="cuda"), torch.zeros(R + S, device="cuda")
+        _lib.check(lib.wnb_resblock_bwd(_lib.ptr(xin), _lib.ptr(haux), _lib.ptr(dout), _lib.ptr(dskip), _lib.ptr(W1),
+                                        _lib.ptr(b1), _lib.ptr(w1t), _lib.ptr(w2t), _lib.ptr(dx), _lib.ptr(dh),
+                                        _lib.ptr(dw1), _lib.ptr(db1), _lib.ptr(dw2), _lib.ptr(db2), _lib.ptr(ws),
+                                        B, T, R, S, Ap, 2, d, mode, _lib.stream()), "resblock_bwd")
+        torch.cuda.synchronize()
+        out[mode] = dict(dx=dx, dh=dh, dw1=dw1, db1=db1, dw2=dw2, db2=db2)
+    for k, ref in out[_lib.MATH_FP32].items():
+        got = out[_lib.MATH_TF32][k]
+        rel = (got - ref).norm().item() / ref.norm().item()
+        assert rel < 5e-3, (k, rel)
