@@ -110,9 +110,10 @@ WNB_API int wnb_resblock_bwd(const float* xin, const float* haux, const float* d
                      int math_mode, void* stream);
 
 /* ---- a11: post network (wavenet.py:518-523) -------------------------------------------------
- * logits (B,T,Q) = wp2 * relu(wp1 * relu(skip) + bp1) + bp2 ; r1 (B,T,S) = relu(h1) is kept when
- * non-NULL (needed by the backward). */
-WNB_API int wnb_post_fwd(const float* skip, const float* wp1, const float* bp1, const float* wp2,
+ * logits (B,T,Q) = wp2 * relu(wp1 * relu(skip) + bp1) + bp2 ; r1 (B,T,S) = relu(h1) is kept (needed by the
+ * backward).  With WNB_MATH_TF32 `skip` is rectified IN PLACE first (its sign pattern -- all that
+ * wnb_post_bwd needs from it -- is unchanged; wnb_post_bwd in tf32 mode relies on it). */
+WNB_API int wnb_post_fwd(float* skip, const float* wp1, const float* bp1, const float* wp2,
                  const float* bp2, float* r1, float* logits, int B, int T, int S, int Q,
                  int math_mode, void* stream);
 /* dskip (B,T,S) out; dwp1,dbp1,dwp2,dbp2 accumulated into; workspace (B,T,S) floats */

@@ -1,0 +1,361 @@
+// gemm_nt_tc.cu -- tensor-core GEMM over channels-last activations:
+//     D[t][n] = epi( sum_seg sum_k A_seg[t + shift_seg][k] * W_seg[n][k] )          n < N <= 512
+// A rows are time steps (K-major operand straight from the (B,T,C) tensor, TMA zero fill outside [0,T) =
+// causal / anti-causal padding), W is a row-major [N][K] weight matrix (K-major operand).  tcgen05.mma
+// kind::tf32, fp32 accumulate in TMEM (whole 128 x N tile; double buffered when N <= 256).
+// Epilogue (4 warps, one TMEM lane quarter each): + bias, ReLU, * (mask > 0), + residual, then a swizzled
+// per-warp staging box and a TMA store or TMA reduce-add (.add.f32) into the (B,T,N) output.
+// Used for: the post network forward (wavenet.py:518-523) and backward, the residual-stream data
+// gradient dX (two time-shifted segments) and the aux gradient dhaux (reduce-add).
+#include <cuda.h>
+#include <string.h>
+
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+namespace wnb {
+namespace nt {
+
+constexpr int kTM = 128;
+constexpr int kASub = kTM * 32 * 4;      // 16 KB
+constexpr int kStg = 32 * 32 * 4;        // 4 KB
+constexpr int kThreadsN = 192;
+constexpr int kMaxSeg = 3;
+
+struct Seg { int amap; int shift; int K; int bmap; int b_k0; int b_n0; };
+struct alignas(64) Params {
+  CUtensorMap maps[8];    // [0..2] A tensors, [3..5] weight matrices, [6] output, [7] second output (gate mode)
+  Seg seg[kMaxSeg];
+  int nseg, N, T, B, nstages, nacc;
+  const float* bias; const float* mask; int ldmask; const float* add; int ldadd;
+  int relu_out, accumulate;
+  // gate-backward epilogue (N == 128 = [sigmoid pre | tanh pre], R = 64): dz (B,T,64) in, z -> maps[6], dpre -> maps[7]
+  const float* gate_dz;
+};
+
+enum { BAR_FULL0 = 0 };  // layout: full[nstages] empty[nstages] dfull[2] dempty[2]
+
+__global__ void __launch_bounds__(kThreadsN, 1) gemm_nt_tc_kernel(const __grid_constant__ Params p) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int N = p.N;
+  const int stage_bytes = kASub + N * 128;
+  unsigned char* stg_base = smem + (size_t)p.nstages * stage_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stg_base + 4 * 2 * kStg);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + p.nstages;
+  uint64_t* dfull = bars + 2 * p.nstages;
+  uint64_t* dempty = dfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dempty + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_per_b = (p.T + kTM - 1) / kTM;
+  const int ntiles = p.B * tiles_per_b;
+  int kchunks = 0;
+  for (int s = 0; s < p.nseg; s++) kchunks += p.seg[s].K / 32;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < p.nstages; i++) {
+      ptx::mbar_init(&full[i], 1);
+      ptx::mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; i++) {
+      ptx::mbar_init(&dfull[i], 1);
+      ptx::mbar_init(&dempty[i], 128);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) ptx::tmem_alloc<512>(tmem_slot);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int i = 0; i < 8; i++) ptx::prefetch_tmap(&p.maps[i]);
+      uint32_t g = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int b = tile / tiles_per_b, t0 = (tile - b * tiles_per_b) * kTM;
+        for (int s = 0; s < p.nseg; s++) {
+          const Seg sg = p.seg[s];
+          for (int kc = 0; kc < sg.K / 32; kc++, g++) {
+            const int st = g % p.nstages;
+            ptx::mbar_wait(&empty[st], ((g / p.nstages) & 1) ^ 1);
+            ptx::mbar_arrive_expect_tx(&full[st], stage_bytes);
+            unsigned char* dst = smem + (size_t)st * stage_bytes;
+            ptx::tma_load_3d(dst, &p.maps[sg.amap], &full[st], kc * 32, t0 + sg.shift, b);
+            for (int n0 = 0; n0 < N; n0 += 256)
+              ptx::tma_load_2d(dst + kASub + n0 * 128, &p.maps[sg.bmap], &full[st], sg.b_k0 + kc * 32, sg.b_n0 + n0);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const int nmma = N > 256 ? 256 : N;
+      const uint32_t idesc = ptx::idesc_tf32(128, nmma);
+      uint32_t g = 0, it = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
+        const uint32_t buf = (p.nacc == 2) ? (it & 1) : 0;
+        const uint32_t use = (p.nacc == 2) ? (it >> 1) : it;
+        ptx::mbar_wait(&dempty[buf], (use & 1) ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t dcol = buf * N;
+        for (int kc = 0; kc < kchunks; kc++, g++) {
+          const int st = g % p.nstages;
+          ptx::mbar_wait(&full[st], (g / p.nstages) & 1);
+          ptx::tc_fence_after();
+          const uint32_t sa = ptx::smem_u32(smem + (size_t)st * stage_bytes);
+          const uint32_t sb = sa + kASub;
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            for (int n0 = 0; n0 < N; n0 += 256)
+              ptx::mma_tf32_ss(tmem + dcol + n0, ptx::smem_desc_k_sw128(sa + k * 32),
+                               ptx::smem_desc_k_sw128(sb + n0 * 128 + k * 32), idesc, (kc | k) != 0);
+          }
+          ptx::tc_commit(&empty[st]);
+        }
+        ptx::tc_commit(&dfull[buf]);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    unsigned char* stg = stg_base + (warp - 2) * 2 * kStg;
+    uint32_t it = 0, nstore = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
+      const int b = tile / tiles_per_b, t0 = (tile - b * tiles_per_b) * kTM;
+      const int t = t0 + q * 32 + lane;
+      const bool row_ok = t < p.T;
+      const size_t grow = (size_t)b * p.T + (row_ok ? t : 0);
+      const uint32_t buf = (p.nacc == 2) ? (it & 1) : 0;
+      const uint32_t use = (p.nacc == 2) ? (it >> 1) : it;
+      ptx::mbar_wait(&dfull[buf], use & 1);
+      ptx::tc_fence_after();
+      if (p.gate_dz) {
+        // ---- gate backward: pair sigmoid column c with tanh column 64 + c ----
+        for (int c0 = 0; c0 < 64; c0 += 32) {
+          float a[32], g[32];
+          {
+            float lo[16], hi[16];
+            ptx::tmem_ld16(tmem + lane_base + buf * N + c0, lo);
+            ptx::tmem_ld16(tmem + lane_base + buf * N + c0 + 16, hi);
+            ptx::tc_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 16; i++) { a[i] = lo[i]; a[16 + i] = hi[i]; }
+            ptx::tmem_ld16(tmem + lane_base + buf * N + 64 + c0, lo);
+            ptx::tmem_ld16(tmem + lane_base + buf * N + 64 + c0 + 16, hi);
+            ptx::tc_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 16; i++) { g[i] = lo[i]; g[16 + i] = hi[i]; }
+          }
+          if (c0 == 32) {
+            ptx::tc_fence_before();
+            ptx::mbar_arrive(&dempty[buf]);
+          }
+          float dzv[32];
+          if (row_ok) {
+            const float4* dr = reinterpret_cast<const float4*>(p.gate_dz + grow * 64 + c0);
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+              const float4 d4 = __ldg(dr + j);
+              dzv[4 * j] = d4.x; dzv[4 * j + 1] = d4.y; dzv[4 * j + 2] = d4.z; dzv[4 * j + 3] = d4.w;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; i++) dzv[i] = 0.f;
+          }
+#pragma unroll
+          for (int i = 0; i < 32; i++) {
+            const float sg = 0.5f * ptx::tanh_approx(0.5f * (a[i] + __ldg(p.bias + c0 + i))) + 0.5f;
+            const float th = ptx::tanh_approx(g[i] + __ldg(p.bias + 64 + c0 + i));
+            const float dz = dzv[i];
+            a[i] = dz * th * sg * (1.f - sg);      // d pre-sigmoid
+            g[i] = dz * sg * (1.f - th * th);      // d pre-tanh
+            dzv[i] = sg * th;                      // z
+          }
+#pragma unroll
+          for (int which = 0; which < 3; which++) {
+            const float* src = which == 0 ? dzv : (which == 1 ? a : g);
+            unsigned char* sb = stg + (nstore & 1) * kStg;
+            if (lane == 0) ptx::bulk_wait_read<1>();
+            __syncwarp();
+            float4* dstrow = reinterpret_cast<float4*>(sb + lane * 128);
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+              dstrow[j ^ (lane & 7)] = make_float4(src[4 * j], src[4 * j + 1], src[4 * j + 2], src[4 * j + 3]);
+            ptx::fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              if (which == 0) ptx::tma_store_3d(&p.maps[6], sb, c0, t0 + q * 32, b);
+              else ptx::tma_store_3d(&p.maps[7], sb, (which == 1 ? 0 : 64) + c0, t0 + q * 32, b);
+              ptx::bulk_commit();
+            }
+            nstore++;
+          }
+        }
+        continue;
+      }
+      for (int c0 = 0; c0 < N; c0 += 32) {
+        float v[32];
+        {
+          float lo[16], hi[16];
+          ptx::tmem_ld16(tmem + lane_base + buf * N + c0, lo);
+          ptx::tmem_ld16(tmem + lane_base + buf * N + c0 + 16, hi);
+          ptx::tc_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 16; i++) { v[i] = lo[i]; v[16 + i] = hi[i]; }
+        }
+        if (c0 + 32 >= N) {  // last chunk in registers: the accumulator can be overwritten
+          ptx::tc_fence_before();
+          ptx::mbar_arrive(&dempty[buf]);
+        }
+        if (p.bias) {
+#pragma unroll
+          for (int i = 0; i < 32; i++) v[i] += __ldg(p.bias + c0 + i);
+        }
+        if (p.add && row_ok) {
+          const float4* ar = reinterpret_cast<const float4*>(p.add + grow * p.ldadd + c0);
+#pragma unroll
+          for (int j = 0; j < 8; j++) {
+            const float4 a = __ldg(ar + j);
+            v[4 * j] += a.x; v[4 * j + 1] += a.y; v[4 * j + 2] += a.z; v[4 * j + 3] += a.w;
+          }
+        }
+        if (p.relu_out) {
+#pragma unroll
+          for (int i = 0; i < 32; i++) v[i] = fmaxf(v[i], 0.f);
+        }
+        if (p.mask && row_ok) {
+          const float4* mr = reinterpret_cast<const float4*>(p.mask + grow * p.ldmask + c0);
+#pragma unroll
+          for (int j = 0; j < 8; j++) {
+            const float4 m = __ldg(mr + j);
+            v[4 * j] = m.x > 0.f ? v[4 * j] : 0.f; v[4 * j + 1] = m.y > 0.f ? v[4 * j + 1] : 0.f;
+            v[4 * j + 2] = m.z > 0.f ? v[4 * j + 2] : 0.f; v[4 * j + 3] = m.w > 0.f ? v[4 * j + 3] : 0.f;
+          }
+        }
+        unsigned char* sb = stg + (nstore & 1) * kStg;
+        if (lane == 0) ptx::bulk_wait_read<1>();
+        __syncwarp();
+        float4* dstrow = reinterpret_cast<float4*>(sb + lane * 128);
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+          dstrow[j ^ (lane & 7)] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        ptx::fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          if (p.accumulate) ptx::tma_reduce_add_3d(&p.maps[6], sb, c0, t0 + q * 32, b);
+          else ptx::tma_store_3d(&p.maps[6], sb, c0, t0 + q * 32, b);
+          ptx::bulk_commit();
+        }
+        nstore++;
+      }
+    }
+    if (lane == 0) ptx::bulk_wait<0>();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc<512>(tmem);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+static bool map3(CUtensorMap* m, const float* base, int C, int T, int B, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return false;
+  cuuint64_t gdim[3] = {(cuuint64_t)C, (cuuint64_t)T, (cuuint64_t)B};
+  cuuint64_t gstr[2] = {(cuuint64_t)C * 4, (cuuint64_t)C * 4 * (cuuint64_t)T};
+  cuuint32_t box[3] = {32, (cuuint32_t)box_rows, 1}, es[3] = {1, 1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), gdim, gstr, box, es,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+static bool map2(CUtensorMap* m, const float* base, int K, int Nrows, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return false;
+  cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)Nrows};
+  cuuint64_t gstr[1] = {(cuuint64_t)K * 4};
+  cuuint32_t box[2] = {32, (cuuint32_t)box_rows}, es[2] = {1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstr, box, es,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+}  // namespace nt
+
+// One segment: activation tensor (B,T,CA) read at rows t+shift, channels [0,K); weight matrix w (rows x ldw,
+// K-contiguous) rows [n0, n0+N), columns [k0, k0+K).
+struct NtTcSeg { const float* a; int CA; int shift; int K; const float* w; int w_rows; int w_cols; int k0; int n0; };
+
+int gemm_nt_tc(const NtTcSeg* segs, int nseg, int N, float* out, int ld_out, const float* bias, const float* mask,
+               int ldmask, const float* add, int ldadd, int relu_out, int accumulate, int B, int T, cudaStream_t st,
+               const float* gate_dz = nullptr, float* gate_dpre = nullptr) {
+  using namespace nt;
+  if (nseg < 1 || nseg > kMaxSeg || N % 32 != 0 || N < 32 || N > 512 || (N > 256 && N != 512) || ld_out % 4 != 0) {
+    set_error("gemm_nt_tc: unsupported shape (nseg=%d N=%d)", nseg, N);
+    return WNB_ERR_INVALID;
+  }
+  Params p;
+  memset(&p, 0, sizeof(p));
+  const int nbox = N > 256 ? 256 : N;
+  for (int s = 0; s < nseg; s++) {
+    if (segs[s].K % 32 != 0) { set_error("gemm_nt_tc: K must be a multiple of 32"); return WNB_ERR_INVALID; }
+    if (!map3(&p.maps[s], segs[s].a, segs[s].CA, T, B, kTM) ||
+        !map2(&p.maps[3 + s], segs[s].w, segs[s].w_cols, segs[s].w_rows, nbox)) {
+      set_error("gemm_nt_tc: tensor map creation failed");
+      return WNB_ERR_CUDA;
+    }
+    p.seg[s] = Seg{s, segs[s].shift, segs[s].K, 3 + s, segs[s].k0, segs[s].n0};
+  }
+  for (int s = nseg; s < 3; s++) { p.maps[s] = p.maps[0]; p.maps[3 + s] = p.maps[3]; }
+  if (!map3(&p.maps[6], out, ld_out, T, B, 32)) { set_error("gemm_nt_tc: output map failed"); return WNB_ERR_CUDA; }
+  p.maps[7] = p.maps[6];
+  if (gate_dz) {
+    if (N != 128 || !gate_dpre || !bias || !map3(&p.maps[7], gate_dpre, 128, T, B, 32)) {
+      set_error("gemm_nt_tc: bad gate-backward configuration");
+      return WNB_ERR_INVALID;
+    }
+    p.gate_dz = gate_dz;
+  }
+  p.nseg = nseg; p.N = N; p.T = T; p.B = B;
+  p.bias = bias; p.mask = mask; p.ldmask = ldmask; p.add = add; p.ldadd = ldadd;
+  p.relu_out = relu_out; p.accumulate = accumulate;
+  p.nacc = N <= 256 ? 2 : 1;
+  const int stage_bytes = kASub + N * 128;
+  int nst = (int)((227 * 1024 - 1024 - 512 - 4 * 2 * kStg) / stage_bytes);
+  if (nst > 4) nst = 4;
+  if (nst < 2) { set_error("gemm_nt_tc: N too large"); return WNB_ERR_INVALID; }
+  p.nstages = nst;
+  const size_t smem = (size_t)nst * stage_bytes + 4 * 2 * kStg + 512 + 1024;
+  static size_t configured = 0;
+  if (smem > configured) {
+    WNB_CUDA(cudaFuncSetAttribute(gemm_nt_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    WNB_CUDA(cudaGetDevice(&dev));
+    WNB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const int ntiles = B * ((T + kTM - 1) / kTM);
+  const int grid = ntiles < sms ? ntiles : sms;
+  gemm_nt_tc_kernel<<<grid, kThreadsN, smem, st>>>(p);
+  WNB_CHECK_LAUNCH("gemm_nt_tc");
+  return WNB_OK;
+}
+
+}  // namespace wnb

@@ -353,6 +353,41 @@ struct WgOperand { const float* base; int C; int c0; int groups; int shift; };
 int wgrad_tc(const WgOperand* a_ops, int na_ops, const WgOperand* b_ops, int nb_ops, float* c, int ldc, int m_valid,
              float* db, int B, int T, cudaStream_t st);
 
+// implemented in gemm_nt_tc.cu
+struct NtTcSeg { const float* a; int CA; int shift; int K; const float* w; int w_rows; int w_cols; int k0; int n0; };
+int gemm_nt_tc(const NtTcSeg* segs, int nseg, int N, float* out, int ld_out, const float* bias, const float* mask,
+               int ldmask, const float* add, int ldadd, int relu_out, int accumulate, int B, int T, cudaStream_t st,
+               const float* gate_dz = nullptr, float* gate_dpre = nullptr);
+
+static bool nt_tc_n_ok(int N) { return N % 32 == 0 && N >= 32 && (N <= 256 || N == 512); }
+
+__global__ void relu_inplace_kernel(float4* __restrict__ x, int64_t n4) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 v = x[i];
+    v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+    x[i] = v;
+  }
+}
+
+// weight gradient C (M x N) += A^T B for arbitrary M (blocks of 128 rows, TMA zero fill past the tensor) and
+// N (chunks of <= 7 groups of 32), optional bias gradient db (M) = column sums of A
+static int wgrad_tc_full(const float* a, int CA, int M, const float* b, int CB, int N, float* c, int ldc, float* db,
+                         int B, int T, cudaStream_t st) {
+  int rc;
+  for (int m0 = 0; m0 < M; m0 += 128) {
+    const int m_valid = (M - m0) < 128 ? (M - m0) : 128;
+    const WgOperand ao[1] = {{a, CA, m0, 4, 0}};
+    for (int n0 = 0; n0 < N; n0 += 224) {
+      const int groups = ((N - n0) < 224 ? (N - n0) : 224) / 32;
+      const WgOperand bo[1] = {{b, CB, n0, groups, 0}};
+      if ((rc = wgrad_tc(ao, 1, bo, 1, c + (size_t)m0 * ldc + n0, ldc, m_valid, (n0 == 0 && db) ? db + m0 : nullptr, B, T,
+                         st)) != WNB_OK)
+        return rc;
+    }
+  }
+  return WNB_OK;
+}
+
 // implemented in resblock_tc.cu
 int resblock_fwd_tc(const FwdParams& p, cudaStream_t st);
 bool resblock_fwd_tc_supported(int R, int S, int Ap, int ks);
@@ -412,12 +447,37 @@ WNB_API int wnb_resblock_bwd(const float* xin, const float* haux, const float* d
   float* dpre = z + (size_t)B * T * R;
   const int K1 = ks * R + Ap, M2 = R + S;
   int rc;
-  {
+  const bool tc_bwd = math_mode == WNB_MATH_TF32 && R == 64 && ks == 2 && Ap == 32 && S % 32 == 0;
+  if (tc_bwd) {
+    // dz[t][c] = sum_r w2[r][c] dout[t][r] + sum_s w2[R+s][c] dskip[t][s]   (w2t: rows c, cols o)
+    float* dz = dxin;   // dxin is not produced until the dX GEMM below: use it as the (B,T,64) scratch for dz
+    if (dout) {
+      const NtTcSeg sz[2] = {{dout, R, 0, R, w2t, R, R + S, 0, 0}, {dskip, S, 0, S, w2t, R, R + S, R, 0}};
+      if ((rc = gemm_nt_tc(sz, 2, R, dz, R, nullptr, nullptr, 0, nullptr, 0, 0, 0, B, T, st)) != WNB_OK) return rc;
+    } else {
+      const NtTcSeg sz[1] = {{dskip, S, 0, S, w2t, R, R + S, R, 0}};
+      if ((rc = gemm_nt_tc(sz, 1, R, dz, R, nullptr, nullptr, 0, nullptr, 0, 0, 0, B, T, st)) != WNB_OK) return rc;
+    }
+    // gate recompute (pre = W1 [x(t-d) | x(t) | aux]) fused with z and dpre in the epilogue
+    const NtTcSeg sg[3] = {{xin, R, -dilation, R, w1, 2 * R, K1, 0, 0}, {xin, R, 0, R, w1, 2 * R, K1, R, 0},
+                           {haux, Ap, 0, Ap, w1, 2 * R, K1, 2 * R, 0}};
+    if ((rc = gemm_nt_tc(sg, 3, 2 * R, z, R, b1, nullptr, 0, nullptr, 0, 0, 0, B, T, st, dz, dpre)) != WNB_OK) return rc;
+  } else {
     BwdGateParams g{xin, haux, dout, dskip, w1, b1, w2t, z, dpre, B, T, R, S, Ap, ks, dilation};
     dim3 grid(cdiv(T, kBN), B, cdiv(R, 64));
     resblock_bwd_gate_kernel<<<grid, kThreads, 0, st>>>(g);
     WNB_CHECK_LAUNCH("resblock_bwd_gate");
   }
+  if (tc_bwd) {
+    // dxin = dout + dpre(t+d) W1[:, tap0]  + dpre(t) W1[:, tap1]      (w1t rows: 0-63 tap0, 64-127 tap1, 128-159 aux)
+    const NtTcSeg sx[2] = {{dpre, 2 * R, dilation, 2 * R, w1t, K1, 2 * R, 0, 0},
+                           {dpre, 2 * R, 0, 2 * R, w1t, K1, 2 * R, 0, R}};
+    if ((rc = gemm_nt_tc(sx, 2, R, dxin, R, nullptr, nullptr, 0, dout, R, 0, 0, B, T, st)) != WNB_OK) return rc;
+    if (dhaux) {
+      const NtTcSeg sh[1] = {{dpre, 2 * R, 0, 2 * R, w1t, K1, 2 * R, 0, 2 * R}};
+      if ((rc = gemm_nt_tc(sh, 1, Ap, dhaux, Ap, nullptr, nullptr, 0, nullptr, 0, 0, 1, B, T, st)) != WNB_OK) return rc;
+    }
+  } else {
   {  // dxin[t][c] = dout[t][c] + sum_j sum_o w1[o][j*R+c] * dpre[t+(ks-1-j)d][o]
     NtParams p{};
     p.nseg = ks;
@@ -435,6 +495,7 @@ WNB_API int wnb_resblock_bwd(const float* xin, const float* haux, const float* d
     p.M = Ap; p.T = T; p.B = B; p.bias = nullptr; p.c = dhaux; p.ldc = Ap;
     p.add = nullptr; p.mask = nullptr; p.relu_b = 0; p.relu_out = 0; p.accumulate = 1;
     if ((rc = launch_nt(p, st)) != WNB_OK) return rc;
+  }
   }
   // weight gradients
   const bool tc_wgrad = math_mode == WNB_MATH_TF32 && R == 64 && ks == 2 && Ap == 32 && S % 32 == 0;
@@ -486,13 +547,23 @@ WNB_API int wnb_resblock_bwd(const float* xin, const float* haux, const float* d
   return WNB_OK;
 }
 
-WNB_API int wnb_post_fwd(const float* skip, const float* wp1, const float* bp1, const float* wp2, const float* bp2,
+WNB_API int wnb_post_fwd(float* skip, const float* wp1, const float* bp1, const float* wp2, const float* bp2,
                  float* r1, float* logits, int B, int T, int S, int Q, int math_mode, void* stream) {
   WNB_REQUIRE(B > 0 && T > 0 && S > 0 && Q > 0, "post_fwd: bad shape");
   WNB_REQUIRE(skip && wp1 && bp1 && wp2 && bp2 && r1 && logits, "post_fwd: null pointer (r1 scratch is required)");
-  (void)math_mode;
   cudaStream_t st = (cudaStream_t)stream;
   int rc;
+  if (math_mode == WNB_MATH_TF32 && nt_tc_n_ok(S) && nt_tc_n_ok(Q)) {
+    // rectify the skip sum in place (its sign pattern, all the backward needs, is unchanged), then two
+    // tensor-core GEMMs with fused bias / ReLU epilogues
+    const int64_t n4 = (int64_t)B * T * S / 4;
+    relu_inplace_kernel<<<148 * 8, 256, 0, st>>>(reinterpret_cast<float4*>(skip), n4);
+    WNB_CHECK_LAUNCH("relu_inplace");
+    const NtTcSeg s1[1] = {{skip, S, 0, S, wp1, S, S, 0, 0}};
+    if ((rc = gemm_nt_tc(s1, 1, S, r1, S, bp1, nullptr, 0, nullptr, 0, 1, 0, B, T, st)) != WNB_OK) return rc;
+    const NtTcSeg s2[1] = {{r1, S, 0, S, wp2, Q, S, 0, 0}};
+    return gemm_nt_tc(s2, 1, Q, logits, Q, bp2, nullptr, 0, nullptr, 0, 0, 0, B, T, st);
+  }
   {  // r1 = relu(wp1 * relu(skip) + bp1)
     NtParams p{};
     p.nseg = 1; p.seg[0] = NtSeg{wp1, S, skip, S, 0, S};
@@ -514,10 +585,18 @@ WNB_API int wnb_post_bwd(const float* skip, const float* r1, const float* dlogit
   WNB_REQUIRE(B > 0 && T > 0 && S > 0 && Q > 0, "post_bwd: bad shape");
   WNB_REQUIRE(skip && r1 && dlogits && wp1t && wp2t && dskip && dwp1 && dbp1 && dwp2 && dbp2 && workspace,
               "post_bwd: null pointer");
-  (void)math_mode;
   cudaStream_t st = (cudaStream_t)stream;
   float* dh1 = workspace;  // (B,T,S)
   int rc;
+  if (math_mode == WNB_MATH_TF32 && nt_tc_n_ok(S) && nt_tc_n_ok(Q)) {
+    // (skip was rectified in place by the tf32 forward, so it doubles as relu(skip) and as the sign mask)
+    const NtTcSeg s1[1] = {{dlogits, Q, 0, Q, wp2t, S, Q, 0, 0}};
+    if ((rc = gemm_nt_tc(s1, 1, S, dh1, S, nullptr, r1, S, nullptr, 0, 0, 0, B, T, st)) != WNB_OK) return rc;
+    const NtTcSeg s2[1] = {{dh1, S, 0, S, wp1t, S, S, 0, 0}};
+    if ((rc = gemm_nt_tc(s2, 1, S, dskip, S, nullptr, skip, S, nullptr, 0, 0, 0, B, T, st)) != WNB_OK) return rc;
+    if ((rc = wgrad_tc_full(dlogits, Q, Q, r1, S, S, dwp2, S, dbp2, B, T, st)) != WNB_OK) return rc;
+    return wgrad_tc_full(dh1, S, S, skip, S, S, dwp1, S, dbp1, B, T, st);
+  }
   {  // dh1[t][c] = (sum_q wp2[q][c] dlogits[t][q]) * (r1 > 0)
     NtParams p{};
     p.nseg = 1; p.seg[0] = NtSeg{wp2t, Q, dlogits, Q, 0, Q};

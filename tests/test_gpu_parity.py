@@ -246,3 +246,36 @@ def test_arctic_shape_forward_vs_oracle():
     with torch.no_grad():
         y2 = net(torch.from_numpy(x2).cuda(), torch.from_numpy(h).cuda()).cpu().numpy()
     assert np.array_equal(y[:, :1000], y2[:, :1000])
+
+
+def test_decode_arctic_shape_all_kernels():
+    """BASELINE decode shape (30 layers, 64/512, U=80): the warp-tiled kernel (v3), the streaming kernel (v2) and
+    the direct kernel (v1) against the oracle: per-step logits within 1e-4, identical argmax samples."""
+    cfg = O.Config(256, 28, 64, 512, 10, 3, 2, 80)
+    p = O.make_params(cfg, 11)
+    net = our_model(cfg, p).eval()
+    rng = np.random.RandomState(12)
+    B, n = 3, 24
+    x = np.full((B, 1), 128, np.int64)
+    h = rng.standard_normal((B, 28, 1)).astype(np.float32)
+    nl = [n, n - 5, n]
+    outs, olg = O.batch_fast_generate(cfg, p, x, h, list(nl), mode="argmax", return_logits=True)
+    order = sorted(range(B), key=lambda b: (nl[b], b))
+    for kern in ("warp", "stream", "direct"):
+        with torch.no_grad():
+            gen, lg = net._decode(torch.from_numpy(x).cuda(), torch.from_numpy(h).cuda(), nl, "argmax",
+                                  return_logits=True, kernel=kern)
+        assert net.last_decode_kernel == kern
+        gen, lg = gen.cpu().numpy(), lg.cpu().numpy()
+        for i, b in enumerate(order):
+            assert np.array_equal(gen[b, :nl[b]], outs[i]), (kern, b)
+            np.testing.assert_allclose(lg[b, :nl[b]], olg[b, :nl[b]], atol=1e-4, rtol=0, err_msg=kern)
+    # many utterances per CTA (NU = 2 / 4 paths): 300 utterances, identical inputs -> identical outputs
+    Bm = 300
+    xm = np.full((Bm, 1), 128, np.int64)
+    hm = np.repeat(h[:1], Bm, axis=0)
+    with torch.no_grad():
+        gm = net._decode(torch.from_numpy(xm).cuda(), torch.from_numpy(hm).cuda(), [6] * Bm, "argmax", kernel="warp")
+    gm = gm.cpu().numpy()
+    assert np.array_equal(gm, np.repeat(gm[:1], Bm, axis=0))
+    assert np.array_equal(gm[0, :6], outs[order.index(0)][:6])

