@@ -382,7 +382,7 @@ def main():
     ap.add_argument("--with-decode", type=int, default=1, help="also report the decode workload (extra object)")
     ap.add_argument("--cpu-baseline", type=int, default=1)
     ap.add_argument("--decode-utts", type=int, default=64)
-    ap.add_argument("--decode-samples", type=int, default=8000)
+    ap.add_argument("--decode-samples", type=int, default=32000)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -27,7 +27,8 @@ constexpr int kR = 64, kS = 512, kQ = 256, kAp = 32, kK1 = 160;
 constexpr int kCons = 256, kThreadsD = kCons + 32;
 constexpr int kSlot = 32 * 1024;
 constexpr int kMaxL = 64;
-// stream layout per layer (floats): W1 [5][8][32][16] | W2res [2][8][32][8] | W2skip [64][8][64]
+// stream layout per layer (floats): W1 [5 j][8 warp][4 g][32 lane][4] | W2res [2 j][8 warp][2 g][32 lane][4] |
+// W2skip [64 k][8 warp][64]   (value index of a lane = 4 g + e)
 constexpr int kW1Floats = 5 * 8 * 32 * 16;       // 20480 (80 KB) -> chunks 32K,32K,16K bytes
 constexpr int kWresFloats = 2 * 8 * 32 * 8;      // 4096  (16 KB) -> 1 chunk
 constexpr int kWskipFloats = 64 * 8 * 64;        // 32768 (128 KB) -> 4 chunks
@@ -260,8 +261,9 @@ __global__ void __launch_bounds__(kThreadsD, 1) decode_warp_kernel(const Params 
 #pragma unroll
       for (int j = 0; j < 5; j++) {
         if (j == 0 || j == 2 || j == 4) chunk = ring.acquire();
-        const float4* wp = reinterpret_cast<const float4*>(chunk + (size_t)((j & 1) * 8 + warp) * 512 + lane * 16);
-        const float4 w0 = wp[0], w1 = wp[1], w2 = wp[2], w3 = wp[3];
+        // [j][warp][group g][lane][4]: consecutive lanes read consecutive 16 B -> conflict-free LDS.128
+        const float4* wp = reinterpret_cast<const float4*>(chunk + (size_t)((j & 1) * 8 + warp) * 512) + lane;
+        const float4 w0 = wp[0], w1 = wp[32], w2 = wp[64], w3 = wp[96];
 #pragma unroll
         for (int u = 0; u < NU; u++) {
           const float x = (j < 2) ? qtap[((size_t)u * L + l) * kR + (j * 32 + lane)]
@@ -291,8 +293,8 @@ __global__ void __launch_bounds__(kThreadsD, 1) decode_warp_kernel(const Params 
         const float* rc = ring.acquire();
 #pragma unroll
         for (int j = 0; j < 2; j++) {
-          const float4* wp = reinterpret_cast<const float4*>(rc + (size_t)(j * 8 + warp) * 256 + lane * 8);
-          const float4 w0 = wp[0], w1 = wp[1];
+          const float4* wp = reinterpret_cast<const float4*>(rc + (size_t)(j * 8 + warp) * 256) + lane;
+          const float4 w0 = wp[0], w1 = wp[32];
 #pragma unroll
           for (int u = 0; u < NU; u++) {
             const float x = zs[u * kR + j * 32 + lane];

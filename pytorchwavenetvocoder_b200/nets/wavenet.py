@@ -502,10 +502,13 @@ class WaveNet(nn.Module):
         with torch.no_grad():
             wf, bf, W1, b1, W2, b2, Wp1, bp1, Wp2, bp2 = [t.detach().float() for t in self._pack()]
             L = W1.size(0)
-            # W1 (L,128,160)[o][k] -> [j][w][lane][16]: k = 32j+lane, 16 = (sigmoid 8w..8w+7, tanh 8w..8w+7)
-            t1 = W1.reshape(L, 2, 8, 8, 5, 32).permute(0, 4, 2, 5, 1, 3).reshape(L, -1)
-            # W2 res rows (L,64,64)[o][k] -> [j][w][lane][8]: k = 32j+lane, o = 8w+cc
-            tr = W2[:, :64, :].reshape(L, 8, 8, 2, 32).permute(0, 3, 1, 4, 2).reshape(L, -1)
+            # W1 (L,128,160)[o][k] -> [j][w][g][lane][4]: k = 32j+lane; the lane's 16 values (index 4g+e) are
+            # (sigmoid rows 8w..8w+7, tanh rows 8w..8w+7); consecutive lanes are 16 B apart (conflict-free LDS.128)
+            t1 = W1.reshape(L, 2, 8, 8, 5, 32).permute(0, 4, 2, 1, 3, 5)          # [L][j][w][br][cc][lane]
+            t1 = t1.reshape(L, 5, 8, 4, 4, 32).permute(0, 1, 2, 3, 5, 4).reshape(L, -1)   # [j][w][g][lane][e]
+            # W2 res rows (L,64,64)[o][k] -> [j][w][g][lane][4]: k = 32j+lane, o = 8w + 4g + e
+            tr = W2[:, :64, :].reshape(L, 8, 8, 2, 32).permute(0, 3, 1, 2, 4)     # [L][j][w][cc][lane]
+            tr = tr.reshape(L, 2, 8, 2, 4, 32).permute(0, 1, 2, 3, 5, 4).reshape(L, -1)
             # W2 skip rows (L,512,64)[o][k] -> [k][w][64]
             ts = W2[:, 64:, :].transpose(1, 2).reshape(L, -1)
             per_layer = torch.cat([t1, tr, ts], 1).reshape(-1)
