@@ -114,6 +114,7 @@ def run_ours(args):
     dist = None
     if world > 1:
         import torch.distributed as dist
+        os.environ["NCCL_DEBUG"] = os.environ.get("WNB_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     from pytorchwavenetvocoder_b200 import _lib
     from pytorchwavenetvocoder_b200.nets import cross_entropy
@@ -150,13 +151,13 @@ def run_ours(args):
                 dist.barrier()
                 torch.cuda.synchronize()
 
+        sampler = ClockSampler(local)     # samples clocks under load: warm-up + timed region
+        if rank == 0:
+            sampler.start()
         for _ in range(args.warmup):
             step(xd, hd, td)
         # --- device-resident timing (value) ---
         barrier()
-        sampler = ClockSampler(local)
-        if rank == 0:
-            sampler.start()
         l0 = _lib.launch_count()
         wn.PROFILE_EVENTS = []
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -173,14 +174,14 @@ def run_ours(args):
         clocks = sampler.stop() if rank == 0 else None
         # --- end-to-end timing: pinned host -> device every step, loss read back every step ---
         for _ in range(2):
-            float(step(xh.to(dev, non_blocking=True), hh.to(dev, non_blocking=True), th.to(dev, non_blocking=True)))
+            float(step(xh.to(dev, non_blocking=True), hh.to(dev, non_blocking=True), th.to(dev, non_blocking=True)).detach())
         barrier()
         e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e2.record()
         last = 0.0
         for _ in range(args.steps):
             last = float(step(xh.to(dev, non_blocking=True), hh.to(dev, non_blocking=True),
-                              th.to(dev, non_blocking=True)))
+                              th.to(dev, non_blocking=True)).detach())
         e3.record()
         barrier()
         ms_e2e = e2.elapsed_time(e3)

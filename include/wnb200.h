@@ -168,6 +168,8 @@ WNB_API int wnb_decode_stream(int32_t* xs, const float* h, const float* up_w, co
  * weights as ONE stream in warp-tile order (layout documented in csrc/decode_warp.cu; built by
  * nets/wavenet.py::_decode_warp_pack). */
 WNB_API size_t wnb_decode_warp_floats(int L);
+/* debug aid: per-phase cycle counters of the free-running steps (16 int64 per CTA; NULL = off) */
+WNB_API void wnb_decode_warp_set_timing(long long* device_buf);
 WNB_API int wnb_decode_warp_supported(int Q, int Ap, int R, int S, int ks, int L);
 WNB_API int wnb_decode_warp(int32_t* xs, const float* h, const float* up_w, const float* up_b, const float* wf,
                             const float* bf, const float* stream, const float* b1, const float* b2,

@@ -46,7 +46,17 @@ struct Params {
   int dil[kMaxL];
   long long qoff[kMaxL];
   long long q_per_utt;
+  long long* timing;   // optional (debug): 16 cycle counters per CTA, filled by warp 0 lane 0
 };
+
+#define WNB_T(slot)                                           \
+  do {                                                        \
+    if (p.timing && tid == 0) {                               \
+      const long long now__ = clock64();                      \
+      tacc[slot] += now__ - tlast;                            \
+      tlast = now__;                                          \
+    }                                                         \
+  } while (0)
 
 __device__ __forceinline__ void bulk_g2s(void* smem, const void* gmem, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -190,8 +200,14 @@ __global__ void __launch_bounds__(kThreadsD, 1) decode_warp_kernel(const Params 
 
   // ================================ consumer warps ================================
   float* my_pre = pre_s + warp * 16 * NU;
+  long long tacc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  long long tlast = clock64();
   for (int pos = 0; pos <= last_pos; pos++) {
     const bool want = pos >= p.P - 1;
+    if (pos == p.P - 1 && p.timing && tid == 0) {   // time only the free-running steps
+      for (int i = 0; i < 12; i++) tacc[i] = 0;
+      tlast = clock64();
+    }
     // ---- step prologue: front gather, aux column, all queue taps ----
     for (int e = tid; e < NU * kR; e += kCons) {
       const int u = e >> 6, r = e & 63;
@@ -238,7 +254,9 @@ __global__ void __launch_bounds__(kThreadsD, 1) decode_warp_kernel(const Params 
       }
       qtap[e] = v;
     }
+    WNB_T(0);
     cons_sync();
+    WNB_T(1);
     // layer 0's input (the front output) goes into its queue only now, after every tap has been read
     for (int e = tid; e < NU * kR; e += kCons) {
       const int u = e >> 6, r = e & 63;
@@ -276,6 +294,7 @@ __global__ void __launch_bounds__(kThreadsD, 1) decode_warp_kernel(const Params 
         }
         if (j == 1 || j == 3 || j == 4) ring.release();
       }
+      WNB_T(2);
       warp_reduce_scatter<NU * 16>(acc, my_pre, lane);
       __syncwarp();
       if (lane < 8 * NU) {
@@ -284,7 +303,9 @@ __global__ void __launch_bounds__(kThreadsD, 1) decode_warp_kernel(const Params 
         const float g = my_pre[u * 16 + 8 + cc] + __ldg(p.b1 + (size_t)l * 128 + 64 + c);
         zs[u * kR + c] = sigmoidf_(a) * tanhf(g);
       }
+      WNB_T(3);
       cons_sync();
+      WNB_T(4);
       // ---------------- phase B: residual 1x1 (split K) ----------------
       {
         float racc[NU * 8];
@@ -316,6 +337,7 @@ __global__ void __launch_bounds__(kThreadsD, 1) decode_warp_kernel(const Params 
           }
         }
       }
+      WNB_T(5);
       // ---------------- phase B': skip 1x1, lanes own outputs 64*warp + 2*lane (+1) ----------------
       if (want) {
         float s[NU][2];
@@ -350,7 +372,9 @@ __global__ void __launch_bounds__(kThreadsD, 1) decode_warp_kernel(const Params 
           skip_tot[u][1] = (l == 0) ? s1 : skip_tot[u][1] + s1;
         }
       }
+      WNB_T(6);
       cons_sync();
+      WNB_T(7);
     }
 
     if (want) {
@@ -392,6 +416,7 @@ __global__ void __launch_bounds__(kThreadsD, 1) decode_warp_kernel(const Params 
               make_float2(fmaxf(s[u][0] + bv.x, 0.f), fmaxf(s[u][1] + bv.y, 0.f));
       }
       cons_sync();
+      WNB_T(8);
       const int i = pos - (p.P - 1);
       {
         float s[NU];
@@ -427,6 +452,7 @@ __global__ void __launch_bounds__(kThreadsD, 1) decode_warp_kernel(const Params 
         }
       }
       cons_sync();
+      WNB_T(9);
       // ---------------- pick: warp u handles utterance u ----------------
       if (warp < NU) {
         const int u = warp;
@@ -479,8 +505,11 @@ __global__ void __launch_bounds__(kThreadsD, 1) decode_warp_kernel(const Params 
         if (lane == 0 && u0 + u < p.B && i < s_n[u]) p.xs[(size_t)(u0 + u) * stride_xs + pos + 1] = pick;
       }
       cons_sync();
+      WNB_T(10);
     }
   }
+  if (p.timing && tid == 0)
+    for (int i = 0; i < 12; i++) p.timing[(size_t)blockIdx.x * 16 + i] = tacc[i];
 }
 
 }  // namespace dw
@@ -527,6 +556,12 @@ WNB_API size_t wnb_decode_warp_floats(int L) {
   return (size_t)L * dw::kLayerFloats + dw::kP1Floats + dw::kP2Floats;
 }
 
+// debug: device buffer (16 int64 per CTA) that the next wnb_decode_warp launches fill with per-phase cycle
+// counts of the free-running steps (NULL switches it off).  Slots: 0 prologue, 1 sync, 2 gate GEMV, 3 reduce+gate,
+// 4 sync, 5 res GEMV, 6 skip GEMV, 7 sync, 8 post1 (+relu+sync), 9 post2 (+sync), 10 pick (+sync)
+static long long* g_decode_timing = nullptr;
+WNB_API void wnb_decode_warp_set_timing(long long* buf) { g_decode_timing = buf; }
+
 // 1 when the warp-tiled kernel covers the configuration
 WNB_API int wnb_decode_warp_supported(int Q, int Ap, int R, int S, int ks, int L) {
   return (Q == dw::kQ && Ap == dw::kAp && R == dw::kR && S == dw::kS && ks == 2 && L >= 1 && L <= dw::kMaxL) ? 1 : 0;
@@ -549,6 +584,7 @@ WNB_API int wnb_decode_warp(int32_t* xs, const float* h, const float* up_w, cons
   p.logits_out = logits_out;
   p.B = B; p.P = P; p.max_n = max_n; p.n_pad = n_pad; p.Th = Th; p.A = A; p.U = U; p.mode = mode; p.L = L;
   p.seed = seed;
+  p.timing = g_decode_timing;
   long long off = 0;
   for (int l = 0; l < L; l++) {
     p.dil[l] = host_dilations[l];

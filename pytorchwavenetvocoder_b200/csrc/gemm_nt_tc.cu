@@ -31,6 +31,9 @@ struct alignas(64) Params {
   int relu_out, accumulate;
   // gate-backward epilogue (N == 128 = [sigmoid pre | tanh pre], R = 64): dz (B,T,64) in, z -> maps[6], dpre -> maps[7]
   const float* gate_dz;
+  // split output: columns >= out2_col0 (> 0) are reduce-added into maps[7] at column c - out2_col0; bias / add /
+  // mask / ReLU apply to the primary columns only
+  int out2_col0;
 };
 
 enum { BAR_FULL0 = 0 };  // layout: full[nstages] empty[nstages] dfull[2] dempty[2]
@@ -210,11 +213,12 @@ __global__ void __launch_bounds__(kThreadsN, 1) gemm_nt_tc_kernel(const __grid_c
           ptx::tc_fence_before();
           ptx::mbar_arrive(&dempty[buf]);
         }
-        if (p.bias) {
+        const bool second = p.out2_col0 > 0 && c0 >= p.out2_col0;
+        if (p.bias && !second) {
 #pragma unroll
           for (int i = 0; i < 32; i++) v[i] += __ldg(p.bias + c0 + i);
         }
-        if (p.add && row_ok) {
+        if (p.add && row_ok && !second) {
           const float4* ar = reinterpret_cast<const float4*>(p.add + grow * p.ldadd + c0);
 #pragma unroll
           for (int j = 0; j < 8; j++) {
@@ -222,11 +226,11 @@ __global__ void __launch_bounds__(kThreadsN, 1) gemm_nt_tc_kernel(const __grid_c
             v[4 * j] += a.x; v[4 * j + 1] += a.y; v[4 * j + 2] += a.z; v[4 * j + 3] += a.w;
           }
         }
-        if (p.relu_out) {
+        if (p.relu_out && !second) {
 #pragma unroll
           for (int i = 0; i < 32; i++) v[i] = fmaxf(v[i], 0.f);
         }
-        if (p.mask && row_ok) {
+        if (p.mask && row_ok && !second) {
           const float4* mr = reinterpret_cast<const float4*>(p.mask + grow * p.ldmask + c0);
 #pragma unroll
           for (int j = 0; j < 8; j++) {
@@ -245,7 +249,8 @@ __global__ void __launch_bounds__(kThreadsN, 1) gemm_nt_tc_kernel(const __grid_c
         ptx::fence_proxy_async();
         __syncwarp();
         if (lane == 0) {
-          if (p.accumulate) ptx::tma_reduce_add_3d(&p.maps[6], sb, c0, t0 + q * 32, b);
+          if (second) ptx::tma_reduce_add_3d(&p.maps[7], sb, c0 - p.out2_col0, t0 + q * 32, b);
+          else if (p.accumulate) ptx::tma_reduce_add_3d(&p.maps[6], sb, c0, t0 + q * 32, b);
           else ptx::tma_store_3d(&p.maps[6], sb, c0, t0 + q * 32, b);
           ptx::bulk_commit();
         }
@@ -302,7 +307,8 @@ struct NtTcSeg { const float* a; int CA; int shift; int K; const float* w; int w
 
 int gemm_nt_tc(const NtTcSeg* segs, int nseg, int N, float* out, int ld_out, const float* bias, const float* mask,
                int ldmask, const float* add, int ldadd, int relu_out, int accumulate, int B, int T, cudaStream_t st,
-               const float* gate_dz = nullptr, float* gate_dpre = nullptr) {
+               const float* gate_dz = nullptr, float* gate_dpre = nullptr, float* out2 = nullptr, int ld_out2 = 0,
+               int out2_col0 = 0) {
   using namespace nt;
   if (nseg < 1 || nseg > kMaxSeg || N % 32 != 0 || N < 32 || N > 512 || (N > 256 && N != 512) || ld_out % 4 != 0) {
     set_error("gemm_nt_tc: unsupported shape (nseg=%d N=%d)", nseg, N);
@@ -329,6 +335,13 @@ int gemm_nt_tc(const NtTcSeg* segs, int nseg, int N, float* out, int ld_out, con
       return WNB_ERR_INVALID;
     }
     p.gate_dz = gate_dz;
+  }
+  if (out2) {
+    if (gate_dz || out2_col0 <= 0 || out2_col0 % 32 != 0 || out2_col0 >= N || !map3(&p.maps[7], out2, ld_out2, T, B, 32)) {
+      set_error("gemm_nt_tc: bad split-output configuration");
+      return WNB_ERR_INVALID;
+    }
+    p.out2_col0 = out2_col0;
   }
   p.nseg = nseg; p.N = N; p.T = T; p.B = B;
   p.bias = bias; p.mask = mask; p.ldmask = ldmask; p.add = add; p.ldadd = ldadd;

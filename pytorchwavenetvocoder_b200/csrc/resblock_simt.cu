@@ -350,6 +350,9 @@ static int pick_tchunk(int B, int T, int tiles) {
 
 // implemented in wgrad_tc.cu
 struct WgOperand { const float* base; int C; int c0; int groups; int shift; };
+struct WgBlock { WgOperand ops[2]; int nops; float* c; int m_valid; float* db; };
+int wgrad_tc_blocks(const WgBlock* blocks, int nblocks, const WgOperand* b_ops, int nb_ops, int ldc, int B, int T,
+                    cudaStream_t st);
 int wgrad_tc(const WgOperand* a_ops, int na_ops, const WgOperand* b_ops, int nb_ops, float* c, int ldc, int m_valid,
              float* db, int B, int T, cudaStream_t st);
 
@@ -357,7 +360,8 @@ int wgrad_tc(const WgOperand* a_ops, int na_ops, const WgOperand* b_ops, int nb_
 struct NtTcSeg { const float* a; int CA; int shift; int K; const float* w; int w_rows; int w_cols; int k0; int n0; };
 int gemm_nt_tc(const NtTcSeg* segs, int nseg, int N, float* out, int ld_out, const float* bias, const float* mask,
                int ldmask, const float* add, int ldadd, int relu_out, int accumulate, int B, int T, cudaStream_t st,
-               const float* gate_dz = nullptr, float* gate_dpre = nullptr);
+               const float* gate_dz = nullptr, float* gate_dpre = nullptr, float* out2 = nullptr, int ld_out2 = 0,
+               int out2_col0 = 0);
 
 static bool nt_tc_n_ok(int N) { return N % 32 == 0 && N >= 32 && (N <= 256 || N == 512); }
 
@@ -469,13 +473,19 @@ WNB_API int wnb_resblock_bwd(const float* xin, const float* haux, const float* d
     WNB_CHECK_LAUNCH("resblock_bwd_gate");
   }
   if (tc_bwd) {
-    // dxin = dout + dpre(t+d) W1[:, tap0]  + dpre(t) W1[:, tap1]      (w1t rows: 0-63 tap0, 64-127 tap1, 128-159 aux)
-    const NtTcSeg sx[2] = {{dpre, 2 * R, dilation, 2 * R, w1t, K1, 2 * R, 0, 0},
-                           {dpre, 2 * R, 0, 2 * R, w1t, K1, 2 * R, 0, R}};
-    if ((rc = gemm_nt_tc(sx, 2, R, dxin, R, nullptr, nullptr, 0, dout, R, 0, 0, B, T, st)) != WNB_OK) return rc;
+    // dxin = dout + dpre(t+d) W1[:, tap0] + dpre(t) W1[:, tap1]   and   dhaux += dpre(t) W1[:, aux]
+    // (w1t rows: 0-63 tap0, 64-127 tap1, 128-159 aux).  One GEMM with N = 96: the tap-0 segment sees w1t as a
+    // 64-row matrix, so its rows 64-95 are TMA zero fill and only tap 1 feeds the aux columns.
     if (dhaux) {
-      const NtTcSeg sh[1] = {{dpre, 2 * R, 0, 2 * R, w1t, K1, 2 * R, 0, 2 * R}};
-      if ((rc = gemm_nt_tc(sh, 1, Ap, dhaux, Ap, nullptr, nullptr, 0, nullptr, 0, 0, 1, B, T, st)) != WNB_OK) return rc;
+      const NtTcSeg sx[2] = {{dpre, 2 * R, dilation, 2 * R, w1t, R, 2 * R, 0, 0},
+                             {dpre, 2 * R, 0, 2 * R, w1t, K1, 2 * R, 0, R}};
+      if ((rc = gemm_nt_tc(sx, 2, R + Ap, dxin, R, nullptr, nullptr, 0, dout, R, 0, 0, B, T, st, nullptr, nullptr,
+                           dhaux, Ap, R)) != WNB_OK)
+        return rc;
+    } else {
+      const NtTcSeg sx[2] = {{dpre, 2 * R, dilation, 2 * R, w1t, K1, 2 * R, 0, 0},
+                             {dpre, 2 * R, 0, 2 * R, w1t, K1, 2 * R, 0, R}};
+      if ((rc = gemm_nt_tc(sx, 2, R, dxin, R, nullptr, nullptr, 0, dout, R, 0, 0, B, T, st)) != WNB_OK) return rc;
     }
   } else {
   {  // dxin[t][c] = dout[t][c] + sum_j sum_o w1[o][j*R+c] * dpre[t+(ks-1-j)d][o]
@@ -505,17 +515,28 @@ WNB_API int wnb_resblock_bwd(const float* xin, const float* haux, const float* d
       const WgOperand b[3] = {{xin, R, 0, 2, -dilation}, {xin, R, 0, 2, 0}, {haux, Ap, 0, 1, 0}};
       if ((rc = wgrad_tc(a, 1, b, 3, dw1, K1, 128, db1, B, T, st)) != WNB_OK) return rc;
     }
-    // dW2 (R+S x R) += [dout | dskip]^T z in row blocks of 128,  db2 = column sums of [dout | dskip]
+    // dW2 (R+S x R) += [dout | dskip]^T z,  db2 = column sums of [dout | dskip]: row blocks of 128, up to 5 per
+    // launch (their accumulators share TMEM, so z and dskip are streamed once)
     const WgOperand bz[1] = {{z, R, 0, 2, 0}};
     const int row_first = dout ? 0 : R;
+    WgBlock blk[5];
+    int nblk = 0;
     for (int r0 = row_first; r0 < R + S; r0 += 128) {
-      const int m_valid = (R + S - r0) < 128 ? (R + S - r0) : 128;
+      WgBlock& bk = blk[nblk];
+      bk.m_valid = (R + S - r0) < 128 ? (R + S - r0) : 128;
+      bk.c = dw2 + (size_t)r0 * R;
+      bk.db = db2 + r0;
       if (r0 == 0) {
-        const WgOperand a[2] = {{dout, R, 0, 2, 0}, {dskip, S, 0, 2, 0}};
-        if ((rc = wgrad_tc(a, 2, bz, 1, dw2, R, m_valid, db2, B, T, st)) != WNB_OK) return rc;
+        bk.nops = 2;
+        bk.ops[0] = WgOperand{dout, R, 0, 2, 0};
+        bk.ops[1] = WgOperand{dskip, S, 0, 2, 0};
       } else {
-        const WgOperand a[1] = {{dskip, S, r0 - R, 4, 0}};
-        if ((rc = wgrad_tc(a, 1, bz, 1, dw2 + (size_t)r0 * R, R, m_valid, db2 + r0, B, T, st)) != WNB_OK) return rc;
+        bk.nops = 1;
+        bk.ops[0] = WgOperand{dskip, S, r0 - R, 4, 0};
+      }
+      if (++nblk == 5 || r0 + 128 >= R + S) {
+        if ((rc = wgrad_tc_blocks(blk, nblk, bz, 1, R, B, T, st)) != WNB_OK) return rc;
+        nblk = 0;
       }
     }
     return WNB_OK;

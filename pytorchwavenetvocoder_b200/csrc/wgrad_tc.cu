@@ -21,21 +21,21 @@
 namespace wnb {
 namespace wg {
 
-constexpr int kTK = 64;                      // time rows per stage (K of one stage)
-constexpr int kSubBytes = kTK * 32 * 4;      // 8 KB: [64 x 32 fp32] swizzled sub-tile
-constexpr int kMaxA = 4, kMaxB = 8, kMaxMaps = 4;
+constexpr int kMaxMB = 5;                    // M-blocks (128 rows each) sharing one B operand per launch
+constexpr int kMaxA = 4 * kMaxMB, kMaxB = 8, kMaxMaps = 4;
 constexpr int kThreadsW = 192;
 
 struct Sub { int map; int c0; int shift; };
 struct alignas(64) Params {
   CUtensorMap maps[kMaxMaps];
-  Sub a[kMaxA];
+  Sub a[kMaxA];                  // 4 groups per M-block
   Sub b[kMaxB];
-  int nA, nB, use_ones;          // nB excludes the ones group
-  float* c; int ldc;             // C rows m (0..127), columns n (0..32*nB-1)
-  int m_valid;                   // rows >= m_valid are padding (not written)
-  float* db;                     // (128) or null
+  int nMB, nB, use_ones;         // nB excludes the ones group
+  float* c[kMaxMB]; int ldc;     // per block: C rows m (0..127), columns n (0..32*nB-1)
+  int m_valid[kMaxMB];           // rows >= m_valid are padding (not written)
+  float* db[kMaxMB];             // per block (128) or null
   int T, B, tiles_per_b, ntiles, nstages;
+  int tk;                        // time rows per stage (K of one stage): 64 or 32
 };
 
 __device__ __forceinline__ uint64_t smem_desc_mn_sw128(uint32_t saddr, uint32_t lbo_bytes) {
@@ -55,7 +55,9 @@ __global__ void __launch_bounds__(kThreadsW, 1) wgrad_tc_kernel(const __grid_con
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int nsubB = p.nB + (p.use_ones ? 1 : 0);
-  const int stage_bytes = (p.nA + nsubB) * kSubBytes;
+  const int kSubBytes = p.tk * 128;          // [tk x 32 fp32] swizzled sub-tile
+  const int nA = 4 * p.nMB;
+  const int stage_bytes = (nA + nsubB) * kSubBytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.nstages * stage_bytes);
   uint64_t* full = bars;
   uint64_t* empty = bars + p.nstages;
@@ -81,12 +83,12 @@ __global__ void __launch_bounds__(kThreadsW, 1) wgrad_tc_kernel(const __grid_con
   if (p.use_ones) {
     // the ones group of every stage: filled once, never touched by TMA
     for (int s = 0; s < p.nstages; s++) {
-      float4* o = reinterpret_cast<float4*>(smem + (size_t)s * stage_bytes + (p.nA + p.nB) * kSubBytes);
+      float4* o = reinterpret_cast<float4*>(smem + (size_t)s * stage_bytes + (nA + p.nB) * kSubBytes);
       for (int i = threadIdx.x; i < kSubBytes / 16; i += kThreadsW) o[i] = make_float4(1.f, 1.f, 1.f, 1.f);
     }
     ptx::fence_proxy_async();
   }
-  if (warp == 1) ptx::tmem_alloc<256>(tmem_slot);
+  if (warp == 1) ptx::tmem_alloc<512>(tmem_slot);
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -97,15 +99,15 @@ __global__ void __launch_bounds__(kThreadsW, 1) wgrad_tc_kernel(const __grid_con
       for (int i = 0; i < kMaxMaps; i++) ptx::prefetch_tmap(&p.maps[i]);
       uint32_t it = 0;
       for (int tile = tile_begin; tile < tile_end; tile++, it++) {
-        const int b = tile / p.tiles_per_b, t0 = (tile - b * p.tiles_per_b) * kTK;
+        const int b = tile / p.tiles_per_b, t0 = (tile - b * p.tiles_per_b) * p.tk;
         const int s = it % p.nstages;
         ptx::mbar_wait(&empty[s], ((it / p.nstages) & 1) ^ 1);
-        ptx::mbar_arrive_expect_tx(&full[s], (p.nA + p.nB) * kSubBytes);
+        ptx::mbar_arrive_expect_tx(&full[s], (nA + p.nB) * kSubBytes);
         unsigned char* st = smem + (size_t)s * stage_bytes;
-        for (int g = 0; g < p.nA; g++)
+        for (int g = 0; g < nA; g++)
           ptx::tma_load_3d(st + g * kSubBytes, &p.maps[p.a[g].map], &full[s], p.a[g].c0, t0 + p.a[g].shift, b);
         for (int g = 0; g < p.nB; g++)
-          ptx::tma_load_3d(st + (p.nA + g) * kSubBytes, &p.maps[p.b[g].map], &full[s], p.b[g].c0, t0 + p.b[g].shift, b);
+          ptx::tma_load_3d(st + (nA + g) * kSubBytes, &p.maps[p.b[g].map], &full[s], p.b[g].c0, t0 + p.b[g].shift, b);
       }
     }
   } else if (warp == 1) {
@@ -117,11 +119,11 @@ __global__ void __launch_bounds__(kThreadsW, 1) wgrad_tc_kernel(const __grid_con
         ptx::mbar_wait(&full[s], (it / p.nstages) & 1);
         ptx::tc_fence_after();
         const uint32_t sa = ptx::smem_u32(smem + (size_t)s * stage_bytes);
-        const uint32_t sb = sa + p.nA * kSubBytes;
-#pragma unroll
-        for (int k = 0; k < kTK / 8; k++)
-          ptx::mma_tf32_ss(tmem, smem_desc_mn_sw128(sa + k * 1024, kSubBytes), smem_desc_mn_sw128(sb + k * 1024, kSubBytes),
-                           idesc, (it | k) != 0);
+        const uint32_t sb = sa + nA * kSubBytes;
+        for (int mb = 0; mb < p.nMB; mb++)
+          for (int k = 0; k < p.tk / 8; k++)
+            ptx::mma_tf32_ss(tmem + mb * N, smem_desc_mn_sw128(sa + mb * 4 * kSubBytes + k * 1024, kSubBytes),
+                             smem_desc_mn_sw128(sb + k * 1024, kSubBytes), idesc, (it | k) != 0);
         ptx::tc_commit(&empty[s]);
       }
       ptx::tc_commit(done);
@@ -133,24 +135,29 @@ __global__ void __launch_bounds__(kThreadsW, 1) wgrad_tc_kernel(const __grid_con
     ptx::mbar_wait(done, 0);
     ptx::tc_fence_after();
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-    for (int c0 = 0; c0 < N; c0 += 16) {
-      float v[16];
-      ptx::tmem_ld16(tmem + lane_base + c0, v);
-      ptx::tc_wait_ld();
-      if (row < p.m_valid) {
-        if (c0 < 32 * p.nB) {
-          float* dst = p.c + (size_t)row * p.ldc + c0;
+    const int nchunk = N / 16;
+    for (int mb = 0; mb < p.nMB; mb++) {
+      for (int ci = 0; ci < nchunk; ci++) {
+        // every CTA flushes the same addresses: start at a CTA-dependent chunk so the atomics spread out
+        const int c0 = ((ci + blockIdx.x) % nchunk) * 16;
+        float v[16];
+        ptx::tmem_ld16(tmem + lane_base + mb * N + c0, v);
+        ptx::tc_wait_ld();
+        if (row < p.m_valid[mb]) {
+          if (c0 < 32 * p.nB) {
+            float* dst = p.c[mb] + (size_t)row * p.ldc + c0;
 #pragma unroll
-          for (int i = 0; i < 16; i++) atomicAdd(dst + i, v[i]);
-        } else if (c0 == 32 * p.nB && p.db) {
-          atomicAdd(p.db + row, v[0]);
+            for (int i = 0; i < 16; i++) atomicAdd(dst + i, v[i]);
+          } else if (c0 == 32 * p.nB && p.db[mb]) {
+            atomicAdd(p.db[mb] + row, v[0]);
+          }
         }
       }
     }
   }
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 1) ptx::tmem_dealloc<256>(tmem);
+  if (warp == 1) ptx::tmem_dealloc<512>(tmem);
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -169,12 +176,12 @@ static EncodeTiledFn get_encode() {
 }
 
 // (B, T, C) fp32 channels-last tensor, box [32 ch x 64 rows x 1]
-static bool make_act_map(CUtensorMap* m, const float* base, int C, int T, int B) {
+static bool make_act_map(CUtensorMap* m, const float* base, int C, int T, int B, int tk) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return false;
   cuuint64_t gdim[3] = {(cuuint64_t)C, (cuuint64_t)T, (cuuint64_t)B};
   cuuint64_t gstr[2] = {(cuuint64_t)C * 4, (cuuint64_t)C * 4 * (cuuint64_t)T};
-  cuuint32_t box[3] = {32, (cuuint32_t)kTK, 1}, es[3] = {1, 1, 1};
+  cuuint32_t box[3] = {32, (cuuint32_t)tk, 1}, es[3] = {1, 1, 1};
   return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), gdim, gstr, box, es,
              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
@@ -184,51 +191,72 @@ static bool make_act_map(CUtensorMap* m, const float* base, int C, int T, int B)
 
 // One operand = a channels-last tensor (B,T,C); `groups` 32-channel groups starting at channel c0, shifted in time.
 struct WgOperand { const float* base; int C; int c0; int groups; int shift; };
+// One M-block: 128 output rows = 4 groups taken from up to 2 operands (TMA zero fill past a tensor's channels).
+struct WgBlock { WgOperand ops[2]; int nops; float* c; int m_valid; float* db; };
 
-// C[128 x 32*sum(groups_b)] += A^T B ; A = concatenation of up to 2 operands (4 groups in total, zero padded by
-// TMA when a group lies beyond the tensor's channels); rows >= m_valid are not written.
-int wgrad_tc(const WgOperand* a_ops, int na_ops, const WgOperand* b_ops, int nb_ops, float* c, int ldc, int m_valid,
-             float* db, int B, int T, cudaStream_t st) {
+// For every block i:  C_i[128 x 32*sum(groups_b)] += A_i^T B   (+ db_i = column sums of A_i), one launch.
+int wgrad_tc_blocks(const WgBlock* blocks, int nblocks, const WgOperand* b_ops, int nb_ops, int ldc, int B, int T,
+                    cudaStream_t st) {
   using namespace wg;
+  if (nblocks < 1 || nblocks > kMaxMB) { set_error("wgrad_tc: 1..%d M-blocks per launch", kMaxMB); return WNB_ERR_INVALID; }
   Params p;
   memset(&p, 0, sizeof(p));
-  int nmaps = 0;
-  auto map_of = [&](const WgOperand& o) -> int {
-    // one map per distinct (base, C)
-    if (nmaps >= kMaxMaps) return -1;
-    if (!make_act_map(&p.maps[nmaps], o.base, o.C, T, B)) return -1;
-    return nmaps++;
-  };
-  p.nA = 0;
-  for (int i = 0; i < na_ops; i++) {
-    const int m = map_of(a_ops[i]);
-    if (m < 0) { set_error("wgrad_tc: tensor map creation failed (A)"); return WNB_ERR_CUDA; }
-    for (int g = 0; g < a_ops[i].groups; g++) {
-      if (p.nA >= kMaxA) { set_error("wgrad_tc: too many A groups"); return WNB_ERR_INVALID; }
-      p.a[p.nA++] = Sub{m, a_ops[i].c0 + 32 * g, a_ops[i].shift};
-    }
-  }
-  if (p.nA != kMaxA) { set_error("wgrad_tc: A must have exactly 4 groups (M = 128)"); return WNB_ERR_INVALID; }
+  p.nMB = nblocks;
   p.nB = 0;
-  for (int i = 0; i < nb_ops; i++) {
-    const int m = map_of(b_ops[i]);
-    if (m < 0) { set_error("wgrad_tc: tensor map creation failed (B)"); return WNB_ERR_CUDA; }
-    for (int g = 0; g < b_ops[i].groups; g++) {
-      if (p.nB >= kMaxB - 1) { set_error("wgrad_tc: too many B groups"); return WNB_ERR_INVALID; }
-      p.b[p.nB++] = Sub{m, b_ops[i].c0 + 32 * g, b_ops[i].shift};
-    }
-  }
-  for (int i = nmaps; i < kMaxMaps; i++) p.maps[i] = p.maps[0];
-  p.use_ones = db ? 1 : 0;
-  p.c = c; p.ldc = ldc; p.m_valid = m_valid; p.db = db;
-  p.T = T; p.B = B;
-  p.tiles_per_b = (T + kTK - 1) / kTK;
-  p.ntiles = B * p.tiles_per_b;
-  const int stage_bytes = (p.nA + p.nB + p.use_ones) * kSubBytes;
+  for (int i = 0; i < nb_ops; i++) p.nB += b_ops[i].groups;
+  bool any_db = false;
+  for (int i = 0; i < nblocks; i++) any_db |= blocks[i].db != nullptr;
+  p.use_ones = any_db ? 1 : 0;
+  if (p.nB < 1 || p.nB > kMaxB - 1) { set_error("wgrad_tc: 1..7 B groups"); return WNB_ERR_INVALID; }
+  const int N = 32 * (p.nB + p.use_ones);
+  if (N * nblocks > 512) { set_error("wgrad_tc: accumulators exceed TMEM (%d x %d columns)", nblocks, N); return WNB_ERR_INVALID; }
+  // rows per stage: the largest of {64, 32} that leaves at least 2 stages
+  int tk = 64;
+  if ((220 * 1024) / ((4 * nblocks + p.nB + p.use_ones) * 64 * 128) < 2) tk = 32;
+  const int sub = tk * 128;
+  const int stage_bytes = (4 * nblocks + p.nB + p.use_ones) * sub;
   int nst = (220 * 1024) / stage_bytes;
   if (nst > 6) nst = 6;
   if (nst < 2) { set_error("wgrad_tc: stage too large"); return WNB_ERR_INVALID; }
+  p.tk = tk;
   p.nstages = nst;
+
+  int nmaps = 0;
+  const float* map_base[kMaxMaps];
+  int map_c[kMaxMaps];
+  auto map_of = [&](const WgOperand& o) -> int {
+    for (int i = 0; i < nmaps; i++)
+      if (map_base[i] == o.base && map_c[i] == o.C) return i;
+    if (nmaps >= kMaxMaps) return -1;
+    if (!make_act_map(&p.maps[nmaps], o.base, o.C, T, B, tk)) return -1;
+    map_base[nmaps] = o.base; map_c[nmaps] = o.C;
+    return nmaps++;
+  };
+  for (int bi = 0; bi < nblocks; bi++) {
+    int ng = 0;
+    for (int i = 0; i < blocks[bi].nops; i++) {
+      const WgOperand& o = blocks[bi].ops[i];
+      const int m = map_of(o);
+      if (m < 0) { set_error("wgrad_tc: tensor map creation failed (A)"); return WNB_ERR_CUDA; }
+      for (int g = 0; g < o.groups; g++) {
+        if (ng >= 4) { set_error("wgrad_tc: more than 4 groups in an M-block"); return WNB_ERR_INVALID; }
+        p.a[bi * 4 + ng++] = Sub{m, o.c0 + 32 * g, o.shift};
+      }
+    }
+    if (ng != 4) { set_error("wgrad_tc: an M-block needs exactly 4 groups"); return WNB_ERR_INVALID; }
+    p.c[bi] = blocks[bi].c; p.m_valid[bi] = blocks[bi].m_valid; p.db[bi] = blocks[bi].db;
+  }
+  int nb = 0;
+  for (int i = 0; i < nb_ops; i++) {
+    const int m = map_of(b_ops[i]);
+    if (m < 0) { set_error("wgrad_tc: tensor map creation failed (B)"); return WNB_ERR_CUDA; }
+    for (int g = 0; g < b_ops[i].groups; g++) p.b[nb++] = Sub{m, b_ops[i].c0 + 32 * g, b_ops[i].shift};
+  }
+  for (int i = nmaps; i < kMaxMaps; i++) p.maps[i] = p.maps[0];
+  p.ldc = ldc;
+  p.T = T; p.B = B;
+  p.tiles_per_b = (T + tk - 1) / tk;
+  p.ntiles = B * p.tiles_per_b;
   const size_t smem = (size_t)nst * stage_bytes + 1024 + 256;
   static size_t configured = 0;
   if (smem > configured) {
@@ -245,6 +273,17 @@ int wgrad_tc(const WgOperand* a_ops, int na_ops, const WgOperand* b_ops, int nb_
   wgrad_tc_kernel<<<grid, kThreadsW, smem, st>>>(p);
   WNB_CHECK_LAUNCH("wgrad_tc");
   return WNB_OK;
+}
+
+// single M-block convenience wrapper
+int wgrad_tc(const WgOperand* a_ops, int na_ops, const WgOperand* b_ops, int nb_ops, float* c, int ldc, int m_valid,
+             float* db, int B, int T, cudaStream_t st) {
+  if (na_ops < 1 || na_ops > 2) { set_error("wgrad_tc: 1 or 2 A operands"); return WNB_ERR_INVALID; }
+  WgBlock blk;
+  blk.nops = na_ops;
+  for (int i = 0; i < na_ops; i++) blk.ops[i] = a_ops[i];
+  blk.c = c; blk.m_valid = m_valid; blk.db = db;
+  return wgrad_tc_blocks(&blk, 1, b_ops, nb_ops, ldc, B, T, st);
 }
 
 }  // namespace wnb
