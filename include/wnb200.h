@@ -176,7 +176,9 @@ WNB_API int wnb_decode_warp(int32_t* xs, const float* h, const float* up_w, cons
                             const float* bp1, const float* bp2, const int32_t* host_dilations, int L,
                             void* queues, const int32_t* n_samples, const float* uniforms, float* logits_out,
                             int B, int P, int max_n, int n_pad, int Th, int A, int U, int mode, uint64_t seed,
-                            void* stream_handle);
+                            int W, void* stream_handle);
+/* consumer warps (8 or 16) the launcher uses for B utterances; the stream layout depends on it */
+WNB_API int wnb_decode_warp_plan(int B);
 
 #ifdef __cplusplus
 }

@@ -49,7 +49,8 @@ SIGNATURES = {
     "wnb_decode_warp_floats": (_c.c_size_t, [_I]),
     "wnb_decode_warp_set_timing": (None, [_P]),
     "wnb_decode_warp_supported": (_I, [_I] * 6),
-    "wnb_decode_warp": (_I, [_P] * 11 + [_P, _I] + [_P] * 4 + [_I] * 8 + [_c.c_uint64, _P]),
+    "wnb_decode_warp": (_I, [_P] * 11 + [_P, _I] + [_P] * 4 + [_I] * 8 + [_c.c_uint64, _I, _P]),
+    "wnb_decode_warp_plan": (_I, [_I]),
 }
 
 _lib = None

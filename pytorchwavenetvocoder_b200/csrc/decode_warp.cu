@@ -17,6 +17,8 @@
 // Per step the floor is the shared-memory read of the 8.6 MB of weights (67k cycles) or the L2->smem
 // stream, whichever is slower; utterances sharing a CTA (NU = 2, 4) reuse both.
 // Numerics identical in kind to v1/v2: fp32 FFMA, precise expf/tanhf, first-max argmax, Philox sampling.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "tc_ptx.cuh"
 
@@ -24,11 +26,13 @@ namespace wnb {
 namespace dw {
 
 constexpr int kR = 64, kS = 512, kQ = 256, kAp = 32, kK1 = 160;
-constexpr int kCons = 256, kThreadsD = kCons + 32;
+// W = consumer warps (8 or 16).  More warps = more latency hiding for the dependent smem->FMA chains
+// (the kernel is issue-latency bound, the weight stream is always ahead: see profiles/r1_decode_notes.md).
 constexpr int kSlot = 32 * 1024;
 constexpr int kMaxL = 64;
-// stream layout per layer (floats): W1 [5 j][8 warp][4 g][32 lane][4] | W2res [2 j][8 warp][2 g][32 lane][4] |
-// W2skip [64 k][8 warp][64]   (value index of a lane = 4 g + e)
+// stream layout per layer (floats), G = 32 / W groups of 4 gate values, H = 16 / W groups of 4 res values:
+//   W1 [5 j][W warp][G g][32 lane][4] | W2res [2 j][W warp][H g][32 lane][4] | W2skip [64 k][512]
+// (value index of a lane = 4 g + e; skip / post matrices are plain K-major, warp w owns columns 512/W * w ...)
 constexpr int kW1Floats = 5 * 8 * 32 * 16;       // 20480 (80 KB) -> chunks 32K,32K,16K bytes
 constexpr int kWresFloats = 2 * 8 * 32 * 8;      // 4096  (16 KB) -> 1 chunk
 constexpr int kWskipFloats = 64 * 8 * 64;        // 32768 (128 KB) -> 4 chunks
@@ -41,7 +45,7 @@ struct Params {
   const float *wf, *bf, *b1, *b2, *bp1, *bp2;
   const float* stream;
   float* queues; const int32_t* n_samples; const float* uniforms; float* logits_out;
-  int B, P, max_n, n_pad, Th, A, U, mode, L, nslot;
+  int B, P, max_n, n_pad, Th, A, U, mode, L, nslot, split;
   unsigned long long seed;
   int dil[kMaxL];
   long long qoff[kMaxL];
@@ -63,13 +67,19 @@ __device__ __forceinline__ void bulk_g2s(void* smem, const void* gmem, uint32_t 
                ::"r"(ptx::smem_u32(smem)), "l"(gmem), "r"(bytes), "r"(ptx::smem_u32(bar))
                : "memory");
 }
-__device__ __forceinline__ void cons_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+template <int W>
+__device__ __forceinline__ void cons_sync_w() { asm volatile("bar.sync 1, %0;" ::"n"(W * 32) : "memory"); }
 
 struct Ring {
-  unsigned char* base; uint64_t* full; uint64_t* empty; int nslot; uint32_t idx;
+  unsigned char* base; uint64_t* full; uint64_t* empty; int nslot; uint32_t idx; int split;
+  long long waited;                                      // debug: cycles spent blocked in acquire()
   __device__ __forceinline__ const float* acquire() {   // consumer: wait for the current chunk
     const int slot = idx % nslot;
-    ptx::mbar_wait(&full[slot], (idx / nslot) & 1);
+    if (!ptx::mbar_try_wait(&full[slot], (idx / nslot) & 1)) {
+      const long long t0 = clock64();
+      ptx::mbar_wait(&full[slot], (idx / nslot) & 1);
+      waited += clock64() - t0;
+    }
     return reinterpret_cast<const float*>(base + (size_t)slot * kSlot);
   }
   __device__ __forceinline__ void release() {           // consumer: whole warp done with the current chunk
@@ -82,7 +92,11 @@ struct Ring {
     const int slot = idx % nslot;
     ptx::mbar_wait(&empty[slot], ((idx / nslot) & 1) ^ 1);
     ptx::mbar_arrive_expect_tx(&full[slot], bytes);
-    bulk_g2s(base + (size_t)slot * kSlot, src, bytes, &full[slot]);
+    // several smaller bulk copies per chunk keep more L2 requests in flight than one large copy
+    const uint32_t part = bytes / split;
+    for (int i = 0; i < split; i++)
+      bulk_g2s(base + (size_t)slot * kSlot + (size_t)i * part, reinterpret_cast<const unsigned char*>(src) + (size_t)i * part,
+               part, &full[slot]);
     idx++;
   }
 };
@@ -135,8 +149,15 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
   out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
-template <int NU>
-__global__ void __launch_bounds__(kThreadsD, 1) decode_warp_kernel(const Params p) {
+template <int NU, int W>
+__global__ void __launch_bounds__(W * 32 + 32, 1) decode_warp_kernel(const Params p) {
+  constexpr int kCons = W * 32;          // consumer threads
+  constexpr int CH = kR / W;             // gate / residual channels owned by a warp (8 or 4)
+  constexpr int GV = 2 * CH;             // gate values per lane: [sigmoid CH | tanh CH]
+  constexpr int SV = kS / W;             // skip / post-1 outputs per warp (64 or 32)
+  constexpr int SL = SV / 32;            // ... per lane (2 or 1)
+  constexpr int QV = kQ / W;             // logits per warp (32 or 16)
+  constexpr int KS = 32 / QV;            // post-2: lanes sharing one logit split K this many ways (1 or 2)
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int L = p.L;
   unsigned char* ring_base = smem_raw;
@@ -149,8 +170,8 @@ __global__ void __launch_bounds__(kThreadsD, 1) decode_warp_kernel(const Params 
   float* skipx = hcol + NU * kAp;           // [NU][512]  relu(skip sum) / post hidden input
   float* h1 = skipx + NU * kS;              // [NU][512]
   float* logit = h1 + NU * kS;              // [NU][256]
-  float* pre_s = logit + NU * kQ;           // [8 warps][16*NU]
-  float* qtap = pre_s + 8 * 16 * NU;        // [NU][L][64]
+  float* pre_s = logit + NU * kQ;           // [W warps][GV*NU]   (= 128*NU floats for any W)
+  float* qtap = pre_s + 128 * NU;           // [NU][L][64]
   __shared__ int s_n[NU];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -160,7 +181,7 @@ __global__ void __launch_bounds__(kThreadsD, 1) decode_warp_kernel(const Params 
   if (tid == 0) {
     for (int i = 0; i < p.nslot; i++) {
       ptx::mbar_init(&full[i], 1);
-      ptx::mbar_init(&empty[i], kCons / 32);
+      ptx::mbar_init(&empty[i], W);
     }
     ptx::fence_barrier_init();
   }
@@ -171,9 +192,9 @@ __global__ void __launch_bounds__(kThreadsD, 1) decode_warp_kernel(const Params 
   for (int u = 0; u < NU; u++) nmax = max(nmax, s_n[u]);
   if (nmax == 0) return;
   const int last_pos = p.P - 1 + nmax - 1;
-  Ring ring{ring_base, full, empty, p.nslot, 0u};
+  Ring ring{ring_base, full, empty, p.nslot, 0u, p.split, 0ll};
 
-  if (warp == kCons / 32) {
+  if (warp == W) {
     // ================================ producer warp ================================
     if (lane == 0) {
       for (int pos = 0; pos <= last_pos; pos++) {
@@ -199,7 +220,7 @@ __global__ void __launch_bounds__(kThreadsD, 1) decode_warp_kernel(const Params 
   }
 
   // ================================ consumer warps ================================
-  float* my_pre = pre_s + warp * 16 * NU;
+  float* my_pre = pre_s + warp * GV * NU;
   long long tacc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   long long tlast = clock64();
   for (int pos = 0; pos <= last_pos; pos++) {
@@ -207,6 +228,7 @@ __global__ void __launch_bounds__(kThreadsD, 1) decode_warp_kernel(const Params 
     if (pos == p.P - 1 && p.timing && tid == 0) {   // time only the free-running steps
       for (int i = 0; i < 12; i++) tacc[i] = 0;
       tlast = clock64();
+      ring.waited = 0;
     }
     // ---- step prologue: front gather, aux column, all queue taps ----
     for (int e = tid; e < NU * kR; e += kCons) {
@@ -255,7 +277,7 @@ __global__ void __launch_bounds__(kThreadsD, 1) decode_warp_kernel(const Params 
       qtap[e] = v;
     }
     WNB_T(0);
-    cons_sync();
+    cons_sync_w<W>();
     WNB_T(1);
     // layer 0's input (the front output) goes into its queue only now, after every tap has been read
     for (int e = tid; e < NU * kR; e += kCons) {
@@ -266,70 +288,80 @@ __global__ void __launch_bounds__(kThreadsD, 1) decode_warp_kernel(const Params 
       }
     }
 
-    float skip_tot[NU][2];
+    float skip_tot[NU][SL];
 #pragma unroll
-    for (int u = 0; u < NU; u++) skip_tot[u][0] = skip_tot[u][1] = 0.f;
+    for (int u = 0; u < NU; u++)
+#pragma unroll
+      for (int e = 0; e < SL; e++) skip_tot[u][e] = 0.f;
 
     for (int l = 0; l < L; l++) {
       // ---------------- phase A: gate pre-activations, split K over lanes ----------------
-      float acc[NU * 16];
+      float acc[NU * GV];
 #pragma unroll
-      for (int i = 0; i < NU * 16; i++) acc[i] = 0.f;
+      for (int i = 0; i < NU * GV; i++) acc[i] = 0.f;
       const float* chunk = nullptr;
 #pragma unroll
       for (int j = 0; j < 5; j++) {
         if (j == 0 || j == 2 || j == 4) chunk = ring.acquire();
         // [j][warp][group g][lane][4]: consecutive lanes read consecutive 16 B -> conflict-free LDS.128
-        const float4* wp = reinterpret_cast<const float4*>(chunk + (size_t)((j & 1) * 8 + warp) * 512) + lane;
-        const float4 w0 = wp[0], w1 = wp[32], w2 = wp[64], w3 = wp[96];
+        const float4* wp = reinterpret_cast<const float4*>(chunk + (size_t)((j & 1) * W + warp) * (GV * 32)) + lane;
+        float4 wv[GV / 4];
+#pragma unroll
+        for (int g = 0; g < GV / 4; g++) wv[g] = wp[g * 32];
 #pragma unroll
         for (int u = 0; u < NU; u++) {
           const float x = (j < 2) ? qtap[((size_t)u * L + l) * kR + (j * 32 + lane)]
                                   : (j < 4) ? cur[u * kR + (j - 2) * 32 + lane] : hcol[u * kAp + lane];
-          float* a = acc + u * 16;
-          a[0] = fmaf(w0.x, x, a[0]); a[1] = fmaf(w0.y, x, a[1]); a[2] = fmaf(w0.z, x, a[2]); a[3] = fmaf(w0.w, x, a[3]);
-          a[4] = fmaf(w1.x, x, a[4]); a[5] = fmaf(w1.y, x, a[5]); a[6] = fmaf(w1.z, x, a[6]); a[7] = fmaf(w1.w, x, a[7]);
-          a[8] = fmaf(w2.x, x, a[8]); a[9] = fmaf(w2.y, x, a[9]); a[10] = fmaf(w2.z, x, a[10]); a[11] = fmaf(w2.w, x, a[11]);
-          a[12] = fmaf(w3.x, x, a[12]); a[13] = fmaf(w3.y, x, a[13]); a[14] = fmaf(w3.z, x, a[14]); a[15] = fmaf(w3.w, x, a[15]);
+          float* a = acc + u * GV;
+#pragma unroll
+          for (int g = 0; g < GV / 4; g++) {
+            a[4 * g] = fmaf(wv[g].x, x, a[4 * g]); a[4 * g + 1] = fmaf(wv[g].y, x, a[4 * g + 1]);
+            a[4 * g + 2] = fmaf(wv[g].z, x, a[4 * g + 2]); a[4 * g + 3] = fmaf(wv[g].w, x, a[4 * g + 3]);
+          }
         }
         if (j == 1 || j == 3 || j == 4) ring.release();
       }
       WNB_T(2);
-      warp_reduce_scatter<NU * 16>(acc, my_pre, lane);
+      warp_reduce_scatter<NU * GV>(acc, my_pre, lane);
       __syncwarp();
-      if (lane < 8 * NU) {
-        const int u = lane >> 3, cc = lane & 7, c = warp * 8 + cc;
-        const float a = my_pre[u * 16 + cc] + __ldg(p.b1 + (size_t)l * 128 + c);
-        const float g = my_pre[u * 16 + 8 + cc] + __ldg(p.b1 + (size_t)l * 128 + 64 + c);
+      if (lane < CH * NU) {
+        const int u = lane / CH, cc = lane % CH, c = warp * CH + cc;
+        const float a = my_pre[u * GV + cc] + __ldg(p.b1 + (size_t)l * 128 + c);
+        const float g = my_pre[u * GV + CH + cc] + __ldg(p.b1 + (size_t)l * 128 + 64 + c);
         zs[u * kR + c] = sigmoidf_(a) * tanhf(g);
       }
       WNB_T(3);
-      cons_sync();
+      cons_sync_w<W>();
       WNB_T(4);
       // ---------------- phase B: residual 1x1 (split K) ----------------
       {
-        float racc[NU * 8];
+        float racc[NU * CH];
 #pragma unroll
-        for (int i = 0; i < NU * 8; i++) racc[i] = 0.f;
+        for (int i = 0; i < NU * CH; i++) racc[i] = 0.f;
         const float* rc = ring.acquire();
 #pragma unroll
         for (int j = 0; j < 2; j++) {
-          const float4* wp = reinterpret_cast<const float4*>(rc + (size_t)(j * 8 + warp) * 256) + lane;
-          const float4 w0 = wp[0], w1 = wp[32];
+          const float4* wp = reinterpret_cast<const float4*>(rc + (size_t)(j * W + warp) * (CH * 32)) + lane;
+          float4 wv[CH / 4];
+#pragma unroll
+          for (int g = 0; g < CH / 4; g++) wv[g] = wp[g * 32];
 #pragma unroll
           for (int u = 0; u < NU; u++) {
             const float x = zs[u * kR + j * 32 + lane];
-            float* a = racc + u * 8;
-            a[0] = fmaf(w0.x, x, a[0]); a[1] = fmaf(w0.y, x, a[1]); a[2] = fmaf(w0.z, x, a[2]); a[3] = fmaf(w0.w, x, a[3]);
-            a[4] = fmaf(w1.x, x, a[4]); a[5] = fmaf(w1.y, x, a[5]); a[6] = fmaf(w1.z, x, a[6]); a[7] = fmaf(w1.w, x, a[7]);
+            float* a = racc + u * CH;
+#pragma unroll
+            for (int g = 0; g < CH / 4; g++) {
+              a[4 * g] = fmaf(wv[g].x, x, a[4 * g]); a[4 * g + 1] = fmaf(wv[g].y, x, a[4 * g + 1]);
+              a[4 * g + 2] = fmaf(wv[g].z, x, a[4 * g + 2]); a[4 * g + 3] = fmaf(wv[g].w, x, a[4 * g + 3]);
+            }
           }
         }
         ring.release();
-        warp_reduce_scatter<NU * 8>(racc, my_pre, lane);
+        warp_reduce_scatter<NU * CH>(racc, my_pre, lane);
         __syncwarp();
-        if (lane < 8 * NU) {
-          const int u = lane >> 3, cc = lane & 7, c = warp * 8 + cc;
-          const float v = my_pre[u * 8 + cc] + __ldg(p.b2 + (size_t)l * (kR + kS) + c) + cur[u * kR + c];
+        if (lane < CH * NU) {
+          const int u = lane / CH, cc = lane % CH, c = warp * CH + cc;
+          const float v = my_pre[u * CH + cc] + __ldg(p.b2 + (size_t)l * (kR + kS) + c) + cur[u * kR + c];
           cur[u * kR + c] = v;
           if (l + 1 < L && u0 + u < p.B) {   // input of layer l+1 at time `pos` -> its dilation queue
             float* q = p.queues + (size_t)(u0 + u) * p.q_per_utt + p.qoff[l + 1];
@@ -338,14 +370,16 @@ __global__ void __launch_bounds__(kThreadsD, 1) decode_warp_kernel(const Params 
         }
       }
       WNB_T(5);
-      // ---------------- phase B': skip 1x1, lanes own outputs 64*warp + 2*lane (+1) ----------------
+      // ---------------- phase B': skip 1x1, lanes own outputs SV*warp + SL*lane (+e) ----------------
       if (want) {
-        float s[NU][2];
+        float s[NU][SL];
 #pragma unroll
-        for (int u = 0; u < NU; u++) s[u][0] = s[u][1] = 0.f;
+        for (int u = 0; u < NU; u++)
+#pragma unroll
+          for (int e = 0; e < SL; e++) s[u][e] = 0.f;
 #pragma unroll 1
         for (int c4 = 0; c4 < 4; c4++) {
-          const float* sc = ring.acquire();
+          const float* sc = ring.acquire() + warp * SV + lane * SL;
 #pragma unroll
           for (int k4 = 0; k4 < 16; k4 += 4) {
             float4 zv[NU];
@@ -353,27 +387,35 @@ __global__ void __launch_bounds__(kThreadsD, 1) decode_warp_kernel(const Params 
             for (int u = 0; u < NU; u++) zv[u] = *reinterpret_cast<const float4*>(zs + u * kR + c4 * 16 + k4);
 #pragma unroll
             for (int kk = 0; kk < 4; kk++) {
-              const float2 wv = *reinterpret_cast<const float2*>(sc + (size_t)((k4 + kk) * 8 + warp) * 64 + lane * 2);
+              float wv[SL];
+              if constexpr (SL == 2) {
+                const float2 t2 = *reinterpret_cast<const float2*>(sc + (size_t)(k4 + kk) * kS);
+                wv[0] = t2.x; wv[1] = t2.y;
+              } else {
+                wv[0] = sc[(size_t)(k4 + kk) * kS];
+              }
 #pragma unroll
               for (int u = 0; u < NU; u++) {
                 const float z = kk == 0 ? zv[u].x : kk == 1 ? zv[u].y : kk == 2 ? zv[u].z : zv[u].w;
-                s[u][0] = fmaf(wv.x, z, s[u][0]);
-                s[u][1] = fmaf(wv.y, z, s[u][1]);
+#pragma unroll
+                for (int e = 0; e < SL; e++) s[u][e] = fmaf(wv[e], z, s[u][e]);
               }
             }
           }
           ring.release();
         }
-        const float2 bv = *reinterpret_cast<const float2*>(p.b2 + (size_t)l * (kR + kS) + kR + warp * 64 + lane * 2);
 #pragma unroll
-        for (int u = 0; u < NU; u++) {
-          const float s0 = s[u][0] + bv.x, s1 = s[u][1] + bv.y;
-          skip_tot[u][0] = (l == 0) ? s0 : skip_tot[u][0] + s0;   // python `0 + s0 + s1 ...`, wavenet.py:374
-          skip_tot[u][1] = (l == 0) ? s1 : skip_tot[u][1] + s1;
+        for (int e = 0; e < SL; e++) {
+          const float bv = __ldg(p.b2 + (size_t)l * (kR + kS) + kR + warp * SV + lane * SL + e);
+#pragma unroll
+          for (int u = 0; u < NU; u++) {
+            const float sv = s[u][e] + bv;
+            skip_tot[u][e] = (l == 0) ? sv : skip_tot[u][e] + sv;   // python `0 + s0 + s1 ...`, wavenet.py:374
+          }
         }
       }
       WNB_T(6);
-      cons_sync();
+      cons_sync_w<W>();
       WNB_T(7);
     }
 
@@ -381,16 +423,18 @@ __global__ void __launch_bounds__(kThreadsD, 1) decode_warp_kernel(const Params 
       // ---------------- post network ----------------
 #pragma unroll
       for (int u = 0; u < NU; u++)
-        *reinterpret_cast<float2*>(skipx + u * kS + warp * 64 + lane * 2) =
-            make_float2(fmaxf(skip_tot[u][0], 0.f), fmaxf(skip_tot[u][1], 0.f));
-      cons_sync();
-      {
-        float s[NU][2];
 #pragma unroll
-        for (int u = 0; u < NU; u++) s[u][0] = s[u][1] = 0.f;
+        for (int e = 0; e < SL; e++) skipx[u * kS + warp * SV + lane * SL + e] = fmaxf(skip_tot[u][e], 0.f);
+      cons_sync_w<W>();
+      {
+        float s[NU][SL];
+#pragma unroll
+        for (int u = 0; u < NU; u++)
+#pragma unroll
+          for (int e = 0; e < SL; e++) s[u][e] = 0.f;
 #pragma unroll 1
         for (int c = 0; c < 32; c++) {
-          const float* pc = ring.acquire();
+          const float* pc = ring.acquire() + warp * SV + lane * SL;
 #pragma unroll
           for (int k4 = 0; k4 < 16; k4 += 4) {
             float4 xv[NU];
@@ -398,33 +442,42 @@ __global__ void __launch_bounds__(kThreadsD, 1) decode_warp_kernel(const Params 
             for (int u = 0; u < NU; u++) xv[u] = *reinterpret_cast<const float4*>(skipx + u * kS + c * 16 + k4);
 #pragma unroll
             for (int kk = 0; kk < 4; kk++) {
-              const float2 wv = *reinterpret_cast<const float2*>(pc + (size_t)((k4 + kk) * 8 + warp) * 64 + lane * 2);
+              float wv[SL];
+              if constexpr (SL == 2) {
+                const float2 t2 = *reinterpret_cast<const float2*>(pc + (size_t)(k4 + kk) * kS);
+                wv[0] = t2.x; wv[1] = t2.y;
+              } else {
+                wv[0] = pc[(size_t)(k4 + kk) * kS];
+              }
 #pragma unroll
               for (int u = 0; u < NU; u++) {
                 const float x = kk == 0 ? xv[u].x : kk == 1 ? xv[u].y : kk == 2 ? xv[u].z : xv[u].w;
-                s[u][0] = fmaf(wv.x, x, s[u][0]);
-                s[u][1] = fmaf(wv.y, x, s[u][1]);
+#pragma unroll
+                for (int e = 0; e < SL; e++) s[u][e] = fmaf(wv[e], x, s[u][e]);
               }
             }
           }
           ring.release();
         }
-        const float2 bv = *reinterpret_cast<const float2*>(p.bp1 + warp * 64 + lane * 2);
 #pragma unroll
-        for (int u = 0; u < NU; u++)
-          *reinterpret_cast<float2*>(h1 + u * kS + warp * 64 + lane * 2) =
-              make_float2(fmaxf(s[u][0] + bv.x, 0.f), fmaxf(s[u][1] + bv.y, 0.f));
+        for (int e = 0; e < SL; e++) {
+          const float bv = __ldg(p.bp1 + warp * SV + lane * SL + e);
+#pragma unroll
+          for (int u = 0; u < NU; u++) h1[u * kS + warp * SV + lane * SL + e] = fmaxf(s[u][e] + bv, 0.f);
+        }
       }
-      cons_sync();
+      cons_sync_w<W>();
       WNB_T(8);
       const int i = pos - (p.P - 1);
       {
+        // logit o = QV*warp + (lane % QV); when QV == 16 the two half-warps split K (even / odd k)
+        const int lo = lane % QV, ksel = lane / QV;
         float s[NU];
 #pragma unroll
         for (int u = 0; u < NU; u++) s[u] = 0.f;
 #pragma unroll 1
         for (int c = 0; c < 16; c++) {
-          const float* pc = ring.acquire();
+          const float* pc = ring.acquire() + warp * QV + lo;
 #pragma unroll
           for (int k4 = 0; k4 < 32; k4 += 4) {
             float4 xv[NU];
@@ -432,26 +485,32 @@ __global__ void __launch_bounds__(kThreadsD, 1) decode_warp_kernel(const Params 
             for (int u = 0; u < NU; u++) xv[u] = *reinterpret_cast<const float4*>(h1 + u * kS + c * 32 + k4);
 #pragma unroll
             for (int kk = 0; kk < 4; kk++) {
-              const float wv = pc[(size_t)((k4 + kk) * 8 + warp) * 32 + lane];
+              if (KS == 1 || (kk & 1) == ksel) {
+                const float wv = pc[(size_t)(k4 + kk) * kQ];
 #pragma unroll
-              for (int u = 0; u < NU; u++) {
-                const float x = kk == 0 ? xv[u].x : kk == 1 ? xv[u].y : kk == 2 ? xv[u].z : xv[u].w;
-                s[u] = fmaf(wv, x, s[u]);
+                for (int u = 0; u < NU; u++) {
+                  const float x = kk == 0 ? xv[u].x : kk == 1 ? xv[u].y : kk == 2 ? xv[u].z : xv[u].w;
+                  s[u] = fmaf(wv, x, s[u]);
+                }
               }
             }
           }
           ring.release();
         }
-        const float bv = __ldg(p.bp2 + warp * 32 + lane);
+        const float bv = __ldg(p.bp2 + warp * QV + lo);
 #pragma unroll
         for (int u = 0; u < NU; u++) {
-          const float v = s[u] + bv;
-          logit[u * kQ + warp * 32 + lane] = v;
-          if (p.logits_out && u0 + u < p.B && i < s_n[u])
-            p.logits_out[((size_t)(u0 + u) * p.max_n + i) * kQ + warp * 32 + lane] = v;
+          float v = s[u];
+          if (KS == 2) v += __shfl_xor_sync(0xffffffffu, v, 16);
+          v += bv;
+          if (ksel == 0) {
+            logit[u * kQ + warp * QV + lo] = v;
+            if (p.logits_out && u0 + u < p.B && i < s_n[u])
+              p.logits_out[((size_t)(u0 + u) * p.max_n + i) * kQ + warp * QV + lo] = v;
+          }
         }
       }
-      cons_sync();
+      cons_sync_w<W>();
       WNB_T(9);
       // ---------------- pick: warp u handles utterance u ----------------
       if (warp < NU) {
@@ -504,42 +563,56 @@ __global__ void __launch_bounds__(kThreadsD, 1) decode_warp_kernel(const Params 
         }
         if (lane == 0 && u0 + u < p.B && i < s_n[u]) p.xs[(size_t)(u0 + u) * stride_xs + pos + 1] = pick;
       }
-      cons_sync();
+      cons_sync_w<W>();
       WNB_T(10);
     }
   }
-  if (p.timing && tid == 0)
+  if (p.timing && tid == 0) {
     for (int i = 0; i < 12; i++) p.timing[(size_t)blockIdx.x * 16 + i] = tacc[i];
+    p.timing[(size_t)blockIdx.x * 16 + 12] = ring.waited;
+  }
 }
 
 }  // namespace dw
 
-int decode_warp_launch(dw::Params& p, cudaStream_t st) {
+// utterances per CTA and consumer warps for a batch of B utterances (shared by the packer and the launcher)
+static void decode_warp_plan(int B, int* NU, int* W) {
+  int nu = 1;
+  if (B > 148 * 2) nu = 4; else if (B > 148) nu = 2;
+  *NU = nu;
+  *W = (nu == 4) ? 8 : 16;   // 16 warps hide the smem->FMA latency; NU = 4 needs the registers of the 8-warp form
+}
+
+int decode_warp_launch(dw::Params& p, int W_packed, cudaStream_t st) {
   using namespace dw;
-  int NU = 1;
-  if (p.B > 148 * 2) NU = 4; else if (p.B > 148) NU = 2;
-  size_t work = 0;
-  int nslot = 0;
-  for (;;) {
-    work = ((size_t)NU * (kR * 2 + kAp + 2 * kS + kQ + (size_t)p.L * kR) + 8 * 16 * NU) * sizeof(float);
-    const long avail = 227L * 1024 - 256 - (long)work - 16 * 16;
-    nslot = (int)(avail / kSlot);
-    if (nslot > 6) nslot = 6;
-    if (nslot >= 3 || NU == 1) break;
-    NU >>= 1;
+  int NU, W;
+  decode_warp_plan(p.B, &NU, &W);
+  if (W != W_packed) {
+    set_error("decode_warp: stream packed for %d consumer warps but the plan for B=%d is %d", W_packed, p.B, W);
+    return WNB_ERR_INVALID;
   }
-  if (nslot < 2) return WNB_ERR_UNSUPPORTED;
+  const size_t work = ((size_t)NU * (kR * 2 + kAp + 2 * kS + kQ + (size_t)p.L * kR) + 128 * NU) * sizeof(float);
+  const long avail = 227L * 1024 - 256 - (long)work - 16 * 16;
+  int nslot = (int)(avail / kSlot);
+  if (nslot > 6) nslot = 6;
+  if (nslot < 3) return WNB_ERR_UNSUPPORTED;
   p.nslot = nslot;
+  {
+    const char* e = getenv("WNB_DECODE_SPLIT");
+    int sp = e ? atoi(e) : 1;
+    if (sp != 1 && sp != 2 && sp != 4 && sp != 8) sp = 1;
+    p.split = sp;
+  }
   const size_t smem = (size_t)nslot * kSlot + 2 * nslot * sizeof(uint64_t) + work;
   const int grid = cdiv(p.B, NU);
-#define WNB_LAUNCH_DW(N)                                                                                       \
-  do {                                                                                                         \
-    WNB_CUDA(cudaFuncSetAttribute(decode_warp_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    decode_warp_kernel<N><<<grid, kThreadsD, smem, st>>>(p);                                                   \
+#define WNB_LAUNCH_DW(N, WW)                                                                                        \
+  do {                                                                                                              \
+    WNB_CUDA(cudaFuncSetAttribute(decode_warp_kernel<N, WW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    decode_warp_kernel<N, WW><<<grid, WW * 32 + 32, smem, st>>>(p);                                                 \
   } while (0)
-  if (NU == 4) WNB_LAUNCH_DW(4);
-  else if (NU == 2) WNB_LAUNCH_DW(2);
-  else WNB_LAUNCH_DW(1);
+  if (NU == 4) WNB_LAUNCH_DW(4, 8);
+  else if (NU == 2) WNB_LAUNCH_DW(2, 16);
+  else WNB_LAUNCH_DW(1, 16);
 #undef WNB_LAUNCH_DW
   WNB_CHECK_LAUNCH("decode_warp");
   return WNB_OK;
@@ -567,11 +640,19 @@ WNB_API int wnb_decode_warp_supported(int Q, int Ap, int R, int S, int ks, int L
   return (Q == dw::kQ && Ap == dw::kAp && R == dw::kR && S == dw::kS && ks == 2 && L >= 1 && L <= dw::kMaxL) ? 1 : 0;
 }
 
+// consumer warps (8 or 16) the launcher will use for B utterances: the stream must be packed accordingly
+WNB_API int wnb_decode_warp_plan(int B) {
+  int NU, W;
+  decode_warp_plan(B, &NU, &W);
+  return W;
+}
+
 WNB_API int wnb_decode_warp(int32_t* xs, const float* h, const float* up_w, const float* up_b, const float* wf,
                             const float* bf, const float* stream, const float* b1, const float* b2, const float* bp1,
                             const float* bp2, const int32_t* host_dilations, int L, void* queues,
                             const int32_t* n_samples, const float* uniforms, float* logits_out, int B, int P,
-                            int max_n, int n_pad, int Th, int A, int U, int mode, uint64_t seed, void* stream_handle) {
+                            int max_n, int n_pad, int Th, int A, int U, int mode, uint64_t seed, int W,
+                            void* stream_handle) {
   WNB_REQUIRE(B > 0 && P >= 1 && max_n >= 1 && Th >= 1 && A > 0 && A <= dw::kAp && U >= 0 && L >= 1 && L <= dw::kMaxL,
               "decode_warp: bad shape");
   WNB_REQUIRE(xs && h && wf && bf && stream && b1 && b2 && bp1 && bp2 && n_samples && queues,
@@ -592,7 +673,7 @@ WNB_API int wnb_decode_warp(int32_t* xs, const float* h, const float* up_w, cons
     off += (long long)host_dilations[l] * dw::kR;
   }
   p.q_per_utt = off;
-  int rc = decode_warp_launch(p, (cudaStream_t)stream_handle);
+  int rc = decode_warp_launch(p, W, (cudaStream_t)stream_handle);
   if (rc == WNB_ERR_UNSUPPORTED) set_error("decode_warp: not enough shared memory for this depth");
   return rc;
 }

@@ -497,19 +497,20 @@ class WaveNet(nn.Module):
         parts += [w["wp1d"].reshape(-1), w["wp2d"].reshape(-1)]
         return torch.cat(parts).contiguous()
 
-    def _decode_warp_pack(self):
-        """Warp-tile ordered stream for wnb_decode_warp (layout: csrc/decode_warp.cu)."""
+    def _decode_warp_pack(self, W):
+        """Warp-tile ordered stream for wnb_decode_warp with W consumer warps (layout: csrc/decode_warp.cu)."""
         with torch.no_grad():
             wf, bf, W1, b1, W2, b2, Wp1, bp1, Wp2, bp2 = [t.detach().float() for t in self._pack()]
             L = W1.size(0)
-            # W1 (L,128,160)[o][k] -> [j][w][g][lane][4]: k = 32j+lane; the lane's 16 values (index 4g+e) are
-            # (sigmoid rows 8w..8w+7, tanh rows 8w..8w+7); consecutive lanes are 16 B apart (conflict-free LDS.128)
-            t1 = W1.reshape(L, 2, 8, 8, 5, 32).permute(0, 4, 2, 1, 3, 5)          # [L][j][w][br][cc][lane]
-            t1 = t1.reshape(L, 5, 8, 4, 4, 32).permute(0, 1, 2, 3, 5, 4).reshape(L, -1)   # [j][w][g][lane][e]
-            # W2 res rows (L,64,64)[o][k] -> [j][w][g][lane][4]: k = 32j+lane, o = 8w + 4g + e
-            tr = W2[:, :64, :].reshape(L, 8, 8, 2, 32).permute(0, 3, 1, 2, 4)     # [L][j][w][cc][lane]
-            tr = tr.reshape(L, 2, 8, 2, 4, 32).permute(0, 1, 2, 3, 5, 4).reshape(L, -1)
-            # W2 skip rows (L,512,64)[o][k] -> [k][w][64]
+            CH = 64 // W                     # gate / residual channels per warp
+            # W1 (L,128,160)[o][k] -> [j][w][g][lane][4]: k = 32j+lane; a lane's 2*CH values (index 4g+e) are
+            # (sigmoid rows CH*w.., tanh rows CH*w..); consecutive lanes are 16 B apart (conflict-free LDS.128)
+            t1 = W1.reshape(L, 2, W, CH, 5, 32).permute(0, 4, 2, 1, 3, 5)          # [L][j][w][br][cc][lane]
+            t1 = t1.reshape(L, 5, W, 2 * CH // 4, 4, 32).permute(0, 1, 2, 3, 5, 4).reshape(L, -1)
+            # W2 res rows (L,64,64)[o][k] -> [j][w][g][lane][4]: k = 32j+lane, o = CH*w + 4g + e
+            tr = W2[:, :64, :].reshape(L, W, CH, 2, 32).permute(0, 3, 1, 2, 4)     # [L][j][w][cc][lane]
+            tr = tr.reshape(L, 2, W, CH // 4, 4, 32).permute(0, 1, 2, 3, 5, 4).reshape(L, -1)
+            # W2 skip rows (L,512,64)[o][k] -> [k][512]
             ts = W2[:, 64:, :].transpose(1, 2).reshape(L, -1)
             per_layer = torch.cat([t1, tr, ts], 1).reshape(-1)
             return torch.cat([per_layer, Wp1.t().reshape(-1), Wp2.t().reshape(-1)]).contiguous()
@@ -552,11 +553,13 @@ class WaveNet(nn.Module):
         rc = -3
         self.last_decode_kernel = None
         if kernel in ("auto", "warp") and lib.wnb_decode_warp_supported(Q, Ap, R, S, ks, L):
-            wstream = self._decode_warp_pack()
+            Wc = lib.wnb_decode_warp_plan(B)
+            wstream = self._decode_warp_pack(Wc)
             assert wstream.numel() == lib.wnb_decode_warp_floats(L)
             rc = lib.wnb_decode_warp(ptr(xs), ptr(h), ptr(upw), ptr(upb), ptr(w["wf"]), ptr(w["bf"]), ptr(wstream),
                                      ptr(w["b1"]), ptr(w["b2"]), ptr(w["bp1"]), ptr(w["bp2"]), dil, L, ptr(queues),
-                                     ptr(nsm), ptr(uni), ptr(lg), B, P, max_n, n_pad, Th, A, U, cmode, cseed, stream())
+                                     ptr(nsm), ptr(uni), ptr(lg), B, P, max_n, n_pad, Th, A, U, cmode, cseed, Wc,
+                                     stream())
             if rc != -3 or kernel == "warp":
                 check(rc, "decode_warp")
             if rc == 0:

@@ -270,12 +270,14 @@ def test_decode_arctic_shape_all_kernels():
         for i, b in enumerate(order):
             assert np.array_equal(gen[b, :nl[b]], outs[i]), (kern, b)
             np.testing.assert_allclose(lg[b, :nl[b]], olg[b, :nl[b]], atol=1e-4, rtol=0, err_msg=kern)
-    # many utterances per CTA (NU = 2 / 4 paths): 300 utterances, identical inputs -> identical outputs
-    Bm = 300
-    xm = np.full((Bm, 1), 128, np.int64)
-    hm = np.repeat(h[:1], Bm, axis=0)
-    with torch.no_grad():
-        gm = net._decode(torch.from_numpy(xm).cuda(), torch.from_numpy(hm).cuda(), [6] * Bm, "argmax", kernel="warp")
-    gm = gm.cpu().numpy()
-    assert np.array_equal(gm, np.repeat(gm[:1], Bm, axis=0))
-    assert np.array_equal(gm[0, :6], outs[order.index(0)][:6])
+    # several utterances per CTA: 200 -> NU = 2 (16 consumer warps), 300 -> NU = 4 (8 consumer warps);
+    # identical inputs must give identical outputs, equal to the oracle's
+    for Bm in (200, 300):
+        xm = np.full((Bm, 1), 128, np.int64)
+        hm = np.repeat(h[:1], Bm, axis=0)
+        with torch.no_grad():
+            gm = net._decode(torch.from_numpy(xm).cuda(), torch.from_numpy(hm).cuda(), [6] * Bm, "argmax",
+                             kernel="warp")
+        gm = gm.cpu().numpy()
+        assert np.array_equal(gm, np.repeat(gm[:1], Bm, axis=0)), Bm
+        assert np.array_equal(gm[0, :6], outs[order.index(0)][:6]), Bm

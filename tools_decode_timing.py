@@ -19,5 +19,6 @@ t = t[t.sum(1) > 0]
 names = ['prologue', 'sync0', 'gateGEMV', 'reduce+gate', 'sync1', 'resGEMV', 'skipGEMV', 'sync2', 'post1', 'post2', 'pick']
 per = t.mean(0)[:11] / n
 print('kernel:', net.last_decode_kernel, ' CTAs', len(t), ' cycles/step total %.0f' % per.sum())
+print('  blocked in acquire() (warp 0): %.0f cyc/step' % (t.mean(0)[12] / n))
 for k, v in zip(names, per):
     print('  %-12s %9.0f cyc/step  %5.1f%%' % (k, v, 100 * v / per.sum()))
