@@ -33,12 +33,19 @@ constexpr int kMaxL = 64;
 // stream layout per layer (floats), G = 32 / W groups of 4 gate values, H = 16 / W groups of 4 res values:
 //   W1 [5 j][W warp][G g][32 lane][4] | W2res [2 j][W warp][H g][32 lane][4] | W2skip [64 k][512]
 // (value index of a lane = 4 g + e; skip / post matrices are plain K-major, warp w owns columns 512/W * w ...)
-constexpr int kW1Floats = 5 * 8 * 32 * 16;       // 20480 (80 KB) -> chunks 32K,32K,16K bytes
-constexpr int kWresFloats = 2 * 8 * 32 * 8;      // 4096  (16 KB) -> 1 chunk
+// The biases travel INSIDE the stream, right behind the matrix they belong to, so they land in shared memory
+// with the weights (a per-layer __ldg of a bias misses L1 every time: ~700 cycles on the critical path).
+constexpr int kW1Floats = 5 * 8 * 32 * 16;       // 20480 (80 KB) -> chunks 32K, 32K, 16K + b1
+constexpr int kB1Floats = 128;                   // gate bias, appended to the last W1 chunk
+constexpr int kWresFloats = 2 * 8 * 32 * 8;      // 4096  (16 KB) -> 1 chunk (+ b2)
+constexpr int kB2Floats = kR + kS;               // res + skip bias, appended to the W2res chunk
 constexpr int kWskipFloats = 64 * 8 * 64;        // 32768 (128 KB) -> 4 chunks
-constexpr int kLayerFloats = kW1Floats + kWresFloats + kWskipFloats;
-constexpr int kP1Floats = 512 * 8 * 64;          // post1 [512][8][64]  (1 MB)  -> 32 chunks
-constexpr int kP2Floats = 512 * 8 * 32;          // post2 [512][8][32]  (512 KB)-> 16 chunks
+constexpr int kOffB1 = kW1Floats, kOffWres = kOffB1 + kB1Floats, kOffB2 = kOffWres + kWresFloats,
+              kOffWskip = kOffB2 + kB2Floats;
+constexpr int kLayerFloats = kOffWskip + kWskipFloats;
+constexpr int kPBiasFloats = kS + kQ;            // post biases: one small chunk ahead of the post matrices
+constexpr int kP1Floats = 512 * 8 * 64;          // post1 [512][512]  (1 MB)  -> 32 chunks
+constexpr int kP2Floats = 512 * 8 * 32;          // post2 [512][256]  (512 KB)-> 16 chunks
 
 struct Params {
   int32_t* xs; const float* h; const float* up_w; const float* up_b;
@@ -75,11 +82,9 @@ struct Ring {
   long long waited;                                      // debug: cycles spent blocked in acquire()
   __device__ __forceinline__ const float* acquire() {   // consumer: wait for the current chunk
     const int slot = idx % nslot;
-    if (!ptx::mbar_try_wait(&full[slot], (idx / nslot) & 1)) {
-      const long long t0 = clock64();
-      ptx::mbar_wait(&full[slot], (idx / nslot) & 1);
-      waited += clock64() - t0;
-    }
+    const long long t0 = clock64();   // (try_wait itself may suspend the warp until the phase flips)
+    ptx::mbar_wait(&full[slot], (idx / nslot) & 1);
+    waited += clock64() - t0;
     return reinterpret_cast<const float*>(base + (size_t)slot * kSlot);
   }
   __device__ __forceinline__ void release() {           // consumer: whole warp done with the current chunk
@@ -201,15 +206,17 @@ __global__ void __launch_bounds__(W * 32 + 32, 1) decode_warp_kernel(const Param
         const bool want = pos >= p.P - 1;
         for (int l = 0; l < L; l++) {
           const float* base = p.stream + (size_t)l * kLayerFloats;
-          ring.push(base, 32768);                       // W1 j = 0,1
-          ring.push(base + 8192, 32768);                // W1 j = 2,3
-          ring.push(base + 16384, 16384);               // W1 j = 4
-          ring.push(base + kW1Floats, 16384);           // W2res
+          ring.push(base, 32768);                                          // W1 j = 0,1
+          ring.push(base + 8192, 32768);                                   // W1 j = 2,3
+          ring.push(base + 16384, 16384 + kB1Floats * 4);                  // W1 j = 4, then b1
+          ring.push(base + kOffWres, (kWresFloats + kB2Floats) * 4);       // W2res, then b2
           if (want)
-            for (int c = 0; c < 4; c++) ring.push(base + kW1Floats + kWresFloats + c * 8192, 32768);
+            for (int c = 0; c < 4; c++) ring.push(base + kOffWskip + c * 8192, 32768);
         }
         if (want) {
-          const float* p1 = p.stream + (size_t)L * kLayerFloats;
+          const float* pb = p.stream + (size_t)L * kLayerFloats;
+          ring.push(pb, kPBiasFloats * 4);                                 // bp1 | bp2
+          const float* p1 = pb + kPBiasFloats;
           for (int c = 0; c < 32; c++) ring.push(p1 + (size_t)c * 8192, 32768);
           const float* p2 = p1 + kP1Floats;
           for (int c = 0; c < 16; c++) ring.push(p2 + (size_t)c * 8192, 32768);
@@ -263,8 +270,9 @@ __global__ void __launch_bounds__(W * 32 + 32, 1) decode_warp_kernel(const Param
     }
     for (int e = tid; e < NU * L * kR; e += kCons) {
       const int r = e & 63;
-      const int l = (e >> 6) % L;
-      const int u = e / (L * kR);
+      const int ul = e >> 6;                                 // u * L + l  (no runtime division: NU <= 4)
+      const int u = (ul >= L) + (ul >= 2 * L) + (ul >= 3 * L);
+      const int l = ul - u * L;
       const int ug = min(u0 + u, p.B - 1);
       const int d = p.dil[l];
       float v = 0.f;
@@ -272,7 +280,7 @@ __global__ void __launch_bounds__(W * 32 + 32, 1) decode_warp_kernel(const Param
       // overwritten with the time-`pos` input later in THIS step -> all reads happen here, before the barrier
       if (pos - d >= 0) {
         const float* q = p.queues + (size_t)ug * p.q_per_utt + p.qoff[l];
-        v = __ldcg(q + (size_t)(pos % d) * kR + r);
+        v = __ldcg(q + (size_t)(pos & (d - 1)) * kR + r);
       }
       qtap[e] = v;
     }
@@ -284,7 +292,7 @@ __global__ void __launch_bounds__(W * 32 + 32, 1) decode_warp_kernel(const Param
       const int u = e >> 6, r = e & 63;
       if (u0 + u < p.B) {
         float* q0 = p.queues + (size_t)(u0 + u) * p.q_per_utt + p.qoff[0];
-        __stcg(q0 + (size_t)(pos % p.dil[0]) * kR + r, cur[e]);
+        __stcg(q0 + (size_t)(pos & (p.dil[0] - 1)) * kR + r, cur[e]);
       }
     }
 
@@ -300,6 +308,7 @@ __global__ void __launch_bounds__(W * 32 + 32, 1) decode_warp_kernel(const Param
 #pragma unroll
       for (int i = 0; i < NU * GV; i++) acc[i] = 0.f;
       const float* chunk = nullptr;
+      float gate_bs = 0.f, gate_bt = 0.f;
 #pragma unroll
       for (int j = 0; j < 5; j++) {
         if (j == 0 || j == 2 || j == 4) chunk = ring.acquire();
@@ -319,6 +328,11 @@ __global__ void __launch_bounds__(W * 32 + 32, 1) decode_warp_kernel(const Param
             a[4 * g + 2] = fmaf(wv[g].z, x, a[4 * g + 2]); a[4 * g + 3] = fmaf(wv[g].w, x, a[4 * g + 3]);
           }
         }
+        if (j == 4) {   // b1 sits right behind the j = 4 weights in this chunk
+          const int c = warp * CH + (lane % CH);
+          gate_bs = chunk[4096 + c];
+          gate_bt = chunk[4096 + 64 + c];
+        }
         if (j == 1 || j == 3 || j == 4) ring.release();
       }
       WNB_T(2);
@@ -326,14 +340,15 @@ __global__ void __launch_bounds__(W * 32 + 32, 1) decode_warp_kernel(const Param
       __syncwarp();
       if (lane < CH * NU) {
         const int u = lane / CH, cc = lane % CH, c = warp * CH + cc;
-        const float a = my_pre[u * GV + cc] + __ldg(p.b1 + (size_t)l * 128 + c);
-        const float g = my_pre[u * GV + CH + cc] + __ldg(p.b1 + (size_t)l * 128 + 64 + c);
+        const float a = my_pre[u * GV + cc] + gate_bs;
+        const float g = my_pre[u * GV + CH + cc] + gate_bt;
         zs[u * kR + c] = sigmoidf_(a) * tanhf(g);
       }
       WNB_T(3);
       cons_sync_w<W>();
       WNB_T(4);
       // ---------------- phase B: residual 1x1 (split K) ----------------
+      float skip_b[SL];
       {
         float racc[NU * CH];
 #pragma unroll
@@ -356,16 +371,20 @@ __global__ void __launch_bounds__(W * 32 + 32, 1) decode_warp_kernel(const Param
             }
           }
         }
+        // b2 = [res 64 | skip 512] sits right behind the res weights in this chunk
+        const float res_b = rc[kWresFloats + warp * CH + (lane % CH)];
+#pragma unroll
+        for (int e = 0; e < SL; e++) skip_b[e] = rc[kWresFloats + kR + warp * SV + lane * SL + e];
         ring.release();
         warp_reduce_scatter<NU * CH>(racc, my_pre, lane);
         __syncwarp();
         if (lane < CH * NU) {
           const int u = lane / CH, cc = lane % CH, c = warp * CH + cc;
-          const float v = my_pre[u * CH + cc] + __ldg(p.b2 + (size_t)l * (kR + kS) + c) + cur[u * kR + c];
+          const float v = my_pre[u * CH + cc] + res_b + cur[u * kR + c];
           cur[u * kR + c] = v;
           if (l + 1 < L && u0 + u < p.B) {   // input of layer l+1 at time `pos` -> its dilation queue
             float* q = p.queues + (size_t)(u0 + u) * p.q_per_utt + p.qoff[l + 1];
-            __stcg(q + (size_t)(pos % p.dil[l + 1]) * kR + c, v);
+            __stcg(q + (size_t)(pos & (p.dil[l + 1] - 1)) * kR + c, v);   // dilations are powers of two
           }
         }
       }
@@ -406,7 +425,7 @@ __global__ void __launch_bounds__(W * 32 + 32, 1) decode_warp_kernel(const Param
         }
 #pragma unroll
         for (int e = 0; e < SL; e++) {
-          const float bv = __ldg(p.b2 + (size_t)l * (kR + kS) + kR + warp * SV + lane * SL + e);
+          const float bv = skip_b[e];
 #pragma unroll
           for (int u = 0; u < NU; u++) {
             const float sv = s[u][e] + bv;
@@ -425,6 +444,14 @@ __global__ void __launch_bounds__(W * 32 + 32, 1) decode_warp_kernel(const Param
       for (int u = 0; u < NU; u++)
 #pragma unroll
         for (int e = 0; e < SL; e++) skipx[u * kS + warp * SV + lane * SL + e] = fmaxf(skip_tot[u][e], 0.f);
+      float post_b1[SL], post_b2;
+      {
+        const float* pbias = ring.acquire();   // [bp1 512 | bp2 256]
+#pragma unroll
+        for (int e = 0; e < SL; e++) post_b1[e] = pbias[warp * SV + lane * SL + e];
+        post_b2 = pbias[kS + warp * QV + (lane % QV)];
+        ring.release();
+      }
       cons_sync_w<W>();
       {
         float s[NU][SL];
@@ -461,7 +488,7 @@ __global__ void __launch_bounds__(W * 32 + 32, 1) decode_warp_kernel(const Param
         }
 #pragma unroll
         for (int e = 0; e < SL; e++) {
-          const float bv = __ldg(p.bp1 + warp * SV + lane * SL + e);
+          const float bv = post_b1[e];
 #pragma unroll
           for (int u = 0; u < NU; u++) h1[u * kS + warp * SV + lane * SL + e] = fmaxf(s[u][e] + bv, 0.f);
         }
@@ -497,7 +524,7 @@ __global__ void __launch_bounds__(W * 32 + 32, 1) decode_warp_kernel(const Param
           }
           ring.release();
         }
-        const float bv = __ldg(p.bp2 + warp * QV + lo);
+        const float bv = post_b2;
 #pragma unroll
         for (int u = 0; u < NU; u++) {
           float v = s[u];
@@ -626,7 +653,7 @@ extern "C" {
 
 // floats of the warp-tiled decode stream (layout: csrc/decode_warp.cu header) for L layers
 WNB_API size_t wnb_decode_warp_floats(int L) {
-  return (size_t)L * dw::kLayerFloats + dw::kP1Floats + dw::kP2Floats;
+  return (size_t)L * dw::kLayerFloats + dw::kPBiasFloats + dw::kP1Floats + dw::kP2Floats;
 }
 
 // debug: device buffer (16 int64 per CTA) that the next wnb_decode_warp launches fill with per-phase cycle
@@ -668,6 +695,8 @@ WNB_API int wnb_decode_warp(int32_t* xs, const float* h, const float* up_w, cons
   p.timing = g_decode_timing;
   long long off = 0;
   for (int l = 0; l < L; l++) {
+    WNB_REQUIRE(host_dilations[l] >= 1 && (host_dilations[l] & (host_dilations[l] - 1)) == 0,
+                "decode_warp: dilations must be powers of two");
     p.dil[l] = host_dilations[l];
     p.qoff[l] = off;
     off += (long long)host_dilations[l] * dw::kR;

@@ -512,8 +512,10 @@ class WaveNet(nn.Module):
             tr = tr.reshape(L, 2, W, CH // 4, 4, 32).permute(0, 1, 2, 3, 5, 4).reshape(L, -1)
             # W2 skip rows (L,512,64)[o][k] -> [k][512]
             ts = W2[:, 64:, :].transpose(1, 2).reshape(L, -1)
-            per_layer = torch.cat([t1, tr, ts], 1).reshape(-1)
-            return torch.cat([per_layer, Wp1.t().reshape(-1), Wp2.t().reshape(-1)]).contiguous()
+            # biases ride in the stream right behind their matrices: [W1 | b1 | W2res | b2 | W2skip] per layer,
+            # then [bp1 | bp2 | Wp1^T | Wp2^T]
+            per_layer = torch.cat([t1, b1, tr, b2, ts], 1).reshape(-1)
+            return torch.cat([per_layer, bp1, bp2, Wp1.t().reshape(-1), Wp2.t().reshape(-1)]).contiguous()
 
     def _decode(self, x, h, n_samples_list, mode, uniforms=None, return_logits=False, seed=None, kernel="auto"):
         lib = _lib.load()
