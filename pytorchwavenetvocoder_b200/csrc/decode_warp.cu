@@ -28,7 +28,7 @@ namespace dw {
 constexpr int kR = 64, kS = 512, kQ = 256, kAp = 32, kK1 = 160;
 // W = consumer warps (8 or 16).  More warps = more latency hiding for the dependent smem->FMA chains
 // (the kernel is issue-latency bound, the weight stream is always ahead: see profiles/r1_decode_notes.md).
-constexpr int kSlot = 32 * 1024;
+constexpr int kSlot = 32 * 1024;          // ring slot: 32 KB, or 2 * kSlot when the BIG (64 KB) schedule is used
 constexpr int kMaxL = 64;
 // stream layout per layer (floats), G = 32 / W groups of 4 gate values, H = 16 / W groups of 4 res values:
 //   W1 [5 j][W warp][G g][32 lane][4] | W2res [2 j][W warp][H g][32 lane][4] | W2skip [64 k][512]
@@ -52,7 +52,7 @@ struct Params {
   const float *wf, *bf, *b1, *b2, *bp1, *bp2;
   const float* stream;
   float* queues; const int32_t* n_samples; const float* uniforms; float* logits_out;
-  int B, P, max_n, n_pad, Th, A, U, mode, L, nslot, split;
+  int B, P, max_n, n_pad, Th, A, U, mode, L, nslot, split, big;
   unsigned long long seed;
   int dil[kMaxL];
   long long qoff[kMaxL];
@@ -78,31 +78,32 @@ template <int W>
 __device__ __forceinline__ void cons_sync_w() { asm volatile("bar.sync 1, %0;" ::"n"(W * 32) : "memory"); }
 
 struct Ring {
-  unsigned char* base; uint64_t* full; uint64_t* empty; int nslot; uint32_t idx; int split;
-  long long waited;                                      // debug: cycles spent blocked in acquire()
+  unsigned char* base; uint64_t* full; uint64_t* empty; int nslot; int split; int slot_bytes;
+  int slot; uint32_t phase;   // current chunk's slot and phase parity, advanced incrementally (no runtime division)
+  long long waited;           // debug: cycles spent inside acquire()
+  __device__ __forceinline__ void advance() {
+    if (++slot == nslot) { slot = 0; phase ^= 1u; }
+  }
   __device__ __forceinline__ const float* acquire() {   // consumer: wait for the current chunk
-    const int slot = idx % nslot;
     const long long t0 = clock64();   // (try_wait itself may suspend the warp until the phase flips)
-    ptx::mbar_wait(&full[slot], (idx / nslot) & 1);
+    ptx::mbar_wait(&full[slot], phase);
     waited += clock64() - t0;
-    return reinterpret_cast<const float*>(base + (size_t)slot * kSlot);
+    return reinterpret_cast<const float*>(base + (size_t)slot * slot_bytes);
   }
   __device__ __forceinline__ void release() {           // consumer: whole warp done with the current chunk
-    const int slot = idx % nslot;
     __syncwarp();
     if ((threadIdx.x & 31) == 0) ptx::mbar_arrive(&empty[slot]);
-    idx++;
+    advance();
   }
   __device__ __forceinline__ void push(const float* src, uint32_t bytes) {  // producer
-    const int slot = idx % nslot;
-    ptx::mbar_wait(&empty[slot], ((idx / nslot) & 1) ^ 1);
+    ptx::mbar_wait(&empty[slot], phase ^ 1u);
     ptx::mbar_arrive_expect_tx(&full[slot], bytes);
     // several smaller bulk copies per chunk keep more L2 requests in flight than one large copy
     const uint32_t part = bytes / split;
     for (int i = 0; i < split; i++)
-      bulk_g2s(base + (size_t)slot * kSlot + (size_t)i * part, reinterpret_cast<const unsigned char*>(src) + (size_t)i * part,
+      bulk_g2s(base + (size_t)slot * slot_bytes + (size_t)i * part, reinterpret_cast<const unsigned char*>(src) + (size_t)i * part,
                part, &full[slot]);
-    idx++;
+    advance();
   }
 };
 
@@ -154,9 +155,11 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
   out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
-template <int NU, int W>
+template <int NU, int W, bool BIG>
 __global__ void __launch_bounds__(W * 32 + 32, 1) decode_warp_kernel(const Params p) {
   constexpr int kCons = W * 32;          // consumer threads
+  constexpr int kSlotB = BIG ? 2 * kSlot : kSlot;   // bytes per ring slot
+  constexpr int KPC = BIG ? 32 : 16;     // skip / post-1 rows (k) per chunk; post-2 has 2 * KPC
   constexpr int CH = kR / W;             // gate / residual channels owned by a warp (8 or 4)
   constexpr int GV = 2 * CH;             // gate values per lane: [sigmoid CH | tanh CH]
   constexpr int SV = kS / W;             // skip / post-1 outputs per warp (64 or 32)
@@ -166,7 +169,7 @@ __global__ void __launch_bounds__(W * 32 + 32, 1) decode_warp_kernel(const Param
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int L = p.L;
   unsigned char* ring_base = smem_raw;
-  uint64_t* full = reinterpret_cast<uint64_t*>(ring_base + (size_t)p.nslot * kSlot);
+  uint64_t* full = reinterpret_cast<uint64_t*>(ring_base + (size_t)p.nslot * kSlotB);
   uint64_t* empty = full + p.nslot;
   float* fw = reinterpret_cast<float*>(empty + p.nslot);
   float* cur = fw;                          // [NU][64]
@@ -197,7 +200,7 @@ __global__ void __launch_bounds__(W * 32 + 32, 1) decode_warp_kernel(const Param
   for (int u = 0; u < NU; u++) nmax = max(nmax, s_n[u]);
   if (nmax == 0) return;
   const int last_pos = p.P - 1 + nmax - 1;
-  Ring ring{ring_base, full, empty, p.nslot, 0u, p.split, 0ll};
+  Ring ring{ring_base, full, empty, p.nslot, p.split, kSlotB, 0, 0u, 0ll};
 
   if (warp == W) {
     // ================================ producer warp ================================
@@ -206,20 +209,24 @@ __global__ void __launch_bounds__(W * 32 + 32, 1) decode_warp_kernel(const Param
         const bool want = pos >= p.P - 1;
         for (int l = 0; l < L; l++) {
           const float* base = p.stream + (size_t)l * kLayerFloats;
-          ring.push(base, 32768);                                          // W1 j = 0,1
-          ring.push(base + 8192, 32768);                                   // W1 j = 2,3
+          if (BIG) {
+            ring.push(base, 65536);                                        // W1 j = 0..3
+          } else {
+            ring.push(base, 32768);                                        // W1 j = 0,1
+            ring.push(base + 8192, 32768);                                 // W1 j = 2,3
+          }
           ring.push(base + 16384, 16384 + kB1Floats * 4);                  // W1 j = 4, then b1
           ring.push(base + kOffWres, (kWresFloats + kB2Floats) * 4);       // W2res, then b2
           if (want)
-            for (int c = 0; c < 4; c++) ring.push(base + kOffWskip + c * 8192, 32768);
+            for (int c = 0; c < 64 / KPC; c++) ring.push(base + kOffWskip + c * (KPC * kS), KPC * kS * 4);
         }
         if (want) {
           const float* pb = p.stream + (size_t)L * kLayerFloats;
           ring.push(pb, kPBiasFloats * 4);                                 // bp1 | bp2
           const float* p1 = pb + kPBiasFloats;
-          for (int c = 0; c < 32; c++) ring.push(p1 + (size_t)c * 8192, 32768);
+          for (int c = 0; c < kS / KPC; c++) ring.push(p1 + (size_t)c * (KPC * kS), KPC * kS * 4);
           const float* p2 = p1 + kP1Floats;
-          for (int c = 0; c < 16; c++) ring.push(p2 + (size_t)c * 8192, 32768);
+          for (int c = 0; c < kS / (2 * KPC); c++) ring.push(p2 + (size_t)c * (2 * KPC * kQ), 2 * KPC * kQ * 4);
         }
       }
     }
@@ -311,9 +318,10 @@ __global__ void __launch_bounds__(W * 32 + 32, 1) decode_warp_kernel(const Param
       float gate_bs = 0.f, gate_bt = 0.f;
 #pragma unroll
       for (int j = 0; j < 5; j++) {
-        if (j == 0 || j == 2 || j == 4) chunk = ring.acquire();
+        if (j == 0 || (!BIG && j == 2) || j == 4) chunk = ring.acquire();
         // [j][warp][group g][lane][4]: consecutive lanes read consecutive 16 B -> conflict-free LDS.128
-        const float4* wp = reinterpret_cast<const float4*>(chunk + (size_t)((j & 1) * W + warp) * (GV * 32)) + lane;
+        const int jj = (j == 4) ? 0 : (BIG ? j : (j & 1));   // index of this j inside its chunk
+        const float4* wp = reinterpret_cast<const float4*>(chunk + (size_t)(jj * W + warp) * (GV * 32)) + lane;
         float4 wv[GV / 4];
 #pragma unroll
         for (int g = 0; g < GV / 4; g++) wv[g] = wp[g * 32];
@@ -333,7 +341,7 @@ __global__ void __launch_bounds__(W * 32 + 32, 1) decode_warp_kernel(const Param
           gate_bs = chunk[4096 + c];
           gate_bt = chunk[4096 + 64 + c];
         }
-        if (j == 1 || j == 3 || j == 4) ring.release();
+        if ((!BIG && j == 1) || j == 3 || j == 4) ring.release();
       }
       WNB_T(2);
       warp_reduce_scatter<NU * GV>(acc, my_pre, lane);
@@ -397,13 +405,13 @@ __global__ void __launch_bounds__(W * 32 + 32, 1) decode_warp_kernel(const Param
 #pragma unroll
           for (int e = 0; e < SL; e++) s[u][e] = 0.f;
 #pragma unroll 1
-        for (int c4 = 0; c4 < 4; c4++) {
+        for (int c4 = 0; c4 < 64 / KPC; c4++) {
           const float* sc = ring.acquire() + warp * SV + lane * SL;
 #pragma unroll
-          for (int k4 = 0; k4 < 16; k4 += 4) {
+          for (int k4 = 0; k4 < KPC; k4 += 4) {
             float4 zv[NU];
 #pragma unroll
-            for (int u = 0; u < NU; u++) zv[u] = *reinterpret_cast<const float4*>(zs + u * kR + c4 * 16 + k4);
+            for (int u = 0; u < NU; u++) zv[u] = *reinterpret_cast<const float4*>(zs + u * kR + c4 * KPC + k4);
 #pragma unroll
             for (int kk = 0; kk < 4; kk++) {
               float wv[SL];
@@ -460,13 +468,13 @@ __global__ void __launch_bounds__(W * 32 + 32, 1) decode_warp_kernel(const Param
 #pragma unroll
           for (int e = 0; e < SL; e++) s[u][e] = 0.f;
 #pragma unroll 1
-        for (int c = 0; c < 32; c++) {
+        for (int c = 0; c < kS / KPC; c++) {
           const float* pc = ring.acquire() + warp * SV + lane * SL;
 #pragma unroll
-          for (int k4 = 0; k4 < 16; k4 += 4) {
+          for (int k4 = 0; k4 < KPC; k4 += 4) {
             float4 xv[NU];
 #pragma unroll
-            for (int u = 0; u < NU; u++) xv[u] = *reinterpret_cast<const float4*>(skipx + u * kS + c * 16 + k4);
+            for (int u = 0; u < NU; u++) xv[u] = *reinterpret_cast<const float4*>(skipx + u * kS + c * KPC + k4);
 #pragma unroll
             for (int kk = 0; kk < 4; kk++) {
               float wv[SL];
@@ -503,13 +511,13 @@ __global__ void __launch_bounds__(W * 32 + 32, 1) decode_warp_kernel(const Param
 #pragma unroll
         for (int u = 0; u < NU; u++) s[u] = 0.f;
 #pragma unroll 1
-        for (int c = 0; c < 16; c++) {
+        for (int c = 0; c < kS / (2 * KPC); c++) {
           const float* pc = ring.acquire() + warp * QV + lo;
 #pragma unroll
-          for (int k4 = 0; k4 < 32; k4 += 4) {
+          for (int k4 = 0; k4 < 2 * KPC; k4 += 4) {
             float4 xv[NU];
 #pragma unroll
-            for (int u = 0; u < NU; u++) xv[u] = *reinterpret_cast<const float4*>(h1 + u * kS + c * 32 + k4);
+            for (int u = 0; u < NU; u++) xv[u] = *reinterpret_cast<const float4*>(h1 + u * kS + c * (2 * KPC) + k4);
 #pragma unroll
             for (int kk = 0; kk < 4; kk++) {
               if (KS == 1 || (kk & 1) == ksel) {
@@ -620,22 +628,31 @@ int decode_warp_launch(dw::Params& p, int W_packed, cudaStream_t st) {
   }
   const size_t work = ((size_t)NU * (kR * 2 + kAp + 2 * kS + kQ + (size_t)p.L * kR) + 128 * NU) * sizeof(float);
   const long avail = 227L * 1024 - 256 - (long)work - 16 * 16;
-  int nslot = (int)(avail / kSlot);
+  // three 64 KB slots (half as many mbarrier round trips per step) when they fit, else up to six 32 KB slots
+  const char* eb = getenv("WNB_DECODE_BIG");
+  const bool big = avail >= 3L * 2 * kSlot && !(eb && atoi(eb) == 0);
+  int nslot = big ? 3 : (int)(avail / kSlot);
   if (nslot > 6) nslot = 6;
   if (nslot < 3) return WNB_ERR_UNSUPPORTED;
   p.nslot = nslot;
+  p.big = big ? 1 : 0;
   {
     const char* e = getenv("WNB_DECODE_SPLIT");
     int sp = e ? atoi(e) : 1;
     if (sp != 1 && sp != 2 && sp != 4 && sp != 8) sp = 1;
     p.split = sp;
   }
-  const size_t smem = (size_t)nslot * kSlot + 2 * nslot * sizeof(uint64_t) + work;
+  const size_t smem = (size_t)nslot * (big ? 2 * kSlot : kSlot) + 2 * nslot * sizeof(uint64_t) + work;
   const int grid = cdiv(p.B, NU);
-#define WNB_LAUNCH_DW(N, WW)                                                                                        \
-  do {                                                                                                              \
-    WNB_CUDA(cudaFuncSetAttribute(decode_warp_kernel<N, WW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    decode_warp_kernel<N, WW><<<grid, WW * 32 + 32, smem, st>>>(p);                                                 \
+#define WNB_LAUNCH_DW(N, WW)                                                                                             \
+  do {                                                                                                                   \
+    if (big) {                                                                                                           \
+      WNB_CUDA(cudaFuncSetAttribute(decode_warp_kernel<N, WW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      decode_warp_kernel<N, WW, true><<<grid, WW * 32 + 32, smem, st>>>(p);                                              \
+    } else {                                                                                                             \
+      WNB_CUDA(cudaFuncSetAttribute(decode_warp_kernel<N, WW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      decode_warp_kernel<N, WW, false><<<grid, WW * 32 + 32, smem, st>>>(p);                                             \
+    }                                                                                                                    \
   } while (0)
   if (NU == 4) WNB_LAUNCH_DW(4, 8);
   else if (NU == 2) WNB_LAUNCH_DW(2, 16);
