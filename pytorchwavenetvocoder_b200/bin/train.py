@@ -83,12 +83,15 @@ def train_generator(wav_list, feat_list, receptive_field,
                     shuffle=True,
                     upsampling_factor=80,
                     use_upsampling_layer=True,
-                    use_speaker_code=False):
+                    use_speaker_code=False,
+                    device=None):
     """GENERATE TRAINING BATCH (reference train.py:67-312; the four batching modes, same arithmetic).
 
     Yields ``((x, h), t)``: x (B, T) long inputs, h (B, D, T or T/upsampling_factor) float aux, t (B, T)
     next-sample targets.  Windows are ``receptive_field + batch_length`` long and hop by ``batch_length``.
     """
+    if device is not None and torch.cuda.is_available():
+        torch.cuda.set_device(device)   # this body runs in the prefetch thread: bind it to the rank's GPU
     if shuffle:
         idx = np.random.permutation(len(wav_list))
         wav_list = [wav_list[i] for i in idx]
@@ -302,7 +305,8 @@ def main():
         shuffle=True,
         upsampling_factor=args.upsampling_factor,
         use_upsampling_layer=args.use_upsampling_layer,
-        use_speaker_code=args.use_speaker_code)
+        use_speaker_code=args.use_speaker_code,
+        device=local)
 
     if args.resume is not None and len(args.resume) != 0:
         checkpoint = torch.load(args.resume, map_location=lambda storage, loc: storage, weights_only=False)
