@@ -16,8 +16,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libwnb200.so")
 SOURCES = ["elementwise.cu", "resblock_simt.cu", "resblock_tc.cu", "decode.cu", "decode_stream.cu", "wgrad_tc.cu", "decode_warp.cu", "gemm_nt_tc.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-              "--use_fast_math=false" if False else "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
-              "--fmad=true", "-cudart", "static"]
+              "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--fmad=true", "-cudart", "static"]
 
 
 def _nvcc():

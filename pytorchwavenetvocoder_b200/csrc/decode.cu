@@ -147,7 +147,6 @@ __global__ void __launch_bounds__(kDecThreads) decode_kernel(const DecodeParams 
   float* qtap = hcol + NU * Ap;                // [NU][ntap][R]
   float* partial = qtap + (size_t)NU * ntap * R;  // [parts][NU][O]  (>= NU*max(1024, Omax))
   __shared__ int s_n[NU];
-  __shared__ int s_pick[NU];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int u0 = blockIdx.x * NU;

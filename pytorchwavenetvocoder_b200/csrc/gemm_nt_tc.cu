@@ -36,7 +36,7 @@ struct alignas(64) Params {
   int out2_col0;
 };
 
-enum { BAR_FULL0 = 0 };  // layout: full[nstages] empty[nstages] dfull[2] dempty[2]
+// barrier layout in smem: full[nstages] empty[nstages] dfull[2] dempty[2]
 
 __global__ void __launch_bounds__(kThreadsN, 1) gemm_nt_tc_kernel(const __grid_constant__ Params p) {
   extern __shared__ unsigned char smem_raw[];

@@ -1,6 +1,6 @@
 """Debug helper: per-phase cycle breakdown of the warp-tiled decode kernel (run on the GPU box)."""
 import sys, ctypes, torch, numpy as np
-sys.path.insert(0, '.')
+sys.path.insert(0, '.'); sys.path.insert(0, '..')
 from bench import make_model
 from pytorchwavenetvocoder_b200 import _lib
 lib = _lib.load()
