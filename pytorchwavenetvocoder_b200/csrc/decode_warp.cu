@@ -81,18 +81,37 @@ struct Ring {
   unsigned char* base; uint64_t* full; uint64_t* empty; int nslot; int split; int slot_bytes;
   int slot; uint32_t phase;   // current chunk's slot and phase parity, advanced incrementally (no runtime division)
   long long waited;           // debug: cycles spent inside acquire()
+  uint32_t* ready;            // number of chunks the gatekeeper warp has seen complete (monotonic)
+  uint32_t cidx;              // chunks this thread has consumed / published so far
   __device__ __forceinline__ void advance() {
     if (++slot == nslot) { slot = 0; phase ^= 1u; }
   }
-  __device__ __forceinline__ const float* acquire() {   // consumer: wait for the current chunk
-    const long long t0 = clock64();   // (try_wait itself may suspend the warp until the phase flips)
-    ptx::mbar_wait(&full[slot], phase);
+  // consumer: wait until the gatekeeper has published chunk `cidx`.  A plain acquire-load poll of a shared
+  // counter (~30 cycles when the data is already there) instead of an mbarrier try_wait (~170 cycles): the
+  // gatekeeper warp is the only one that touches the TMA `full` barriers.
+  __device__ __forceinline__ const float* acquire() {
+    const long long t0 = clock64();
+    uint32_t seen;
+    uint32_t spins = 0;
+    for (;;) {
+      asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(seen) : "r"(ptx::smem_u32(ready)) : "memory");
+      if ((int32_t)(seen - cidx) > 0) break;
+      if (++spins > (1u << 26)) { printf("wnb200: decode ring wait timed out\n"); __trap(); }
+    }
     waited += clock64() - t0;
     return reinterpret_cast<const float*>(base + (size_t)slot * slot_bytes);
   }
   __device__ __forceinline__ void release() {           // consumer: whole warp done with the current chunk
     __syncwarp();
     if ((threadIdx.x & 31) == 0) ptx::mbar_arrive(&empty[slot]);
+    advance();
+    cidx++;
+  }
+  // gatekeeper: observe the TMA completion of the current chunk, then publish it to the consumers
+  __device__ __forceinline__ void gate() {
+    ptx::mbar_wait(&full[slot], phase);
+    cidx++;
+    asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(ptx::smem_u32(ready)), "r"(cidx) : "memory");
     advance();
   }
   __device__ __forceinline__ void push(const float* src, uint32_t bytes) {  // producer
@@ -156,7 +175,7 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
 }
 
 template <int NU, int W, bool BIG>
-__global__ void __launch_bounds__(W * 32 + 32, 1) decode_warp_kernel(const Params p) {
+__global__ void __launch_bounds__(W * 32 + 64, 1) decode_warp_kernel(const Params p) {
   constexpr int kCons = W * 32;          // consumer threads
   constexpr int kSlotB = BIG ? 2 * kSlot : kSlot;   // bytes per ring slot
   constexpr int KPC = BIG ? 32 : 16;     // skip / post-1 rows (k) per chunk; post-2 has 2 * KPC
@@ -171,7 +190,8 @@ __global__ void __launch_bounds__(W * 32 + 32, 1) decode_warp_kernel(const Param
   unsigned char* ring_base = smem_raw;
   uint64_t* full = reinterpret_cast<uint64_t*>(ring_base + (size_t)p.nslot * kSlotB);
   uint64_t* empty = full + p.nslot;
-  float* fw = reinterpret_cast<float*>(empty + p.nslot);
+  uint32_t* ready = reinterpret_cast<uint32_t*>(empty + p.nslot);   // + 3 pad words (keeps 16 B alignment)
+  float* fw = reinterpret_cast<float*>(ready + 4);
   float* cur = fw;                          // [NU][64]
   float* zs = cur + NU * kR;                // [NU][64]
   float* hcol = zs + NU * kR;               // [NU][32]
@@ -191,6 +211,7 @@ __global__ void __launch_bounds__(W * 32 + 32, 1) decode_warp_kernel(const Param
       ptx::mbar_init(&full[i], 1);
       ptx::mbar_init(&empty[i], W);
     }
+    *ready = 0u;
     ptx::fence_barrier_init();
   }
   if (tid < NU) s_n[tid] = (u0 + tid < p.B) ? p.n_samples[u0 + tid] : 0;
@@ -200,7 +221,7 @@ __global__ void __launch_bounds__(W * 32 + 32, 1) decode_warp_kernel(const Param
   for (int u = 0; u < NU; u++) nmax = max(nmax, s_n[u]);
   if (nmax == 0) return;
   const int last_pos = p.P - 1 + nmax - 1;
-  Ring ring{ring_base, full, empty, p.nslot, p.split, kSlotB, 0, 0u, 0ll};
+  Ring ring{ring_base, full, empty, p.nslot, p.split, kSlotB, 0, 0u, 0ll, ready, 0u};
 
   if (warp == W) {
     // ================================ producer warp ================================
@@ -228,6 +249,19 @@ __global__ void __launch_bounds__(W * 32 + 32, 1) decode_warp_kernel(const Param
           const float* p2 = p1 + kP1Floats;
           for (int c = 0; c < kS / (2 * KPC); c++) ring.push(p2 + (size_t)c * (2 * KPC * kQ), 2 * KPC * kQ * 4);
         }
+      }
+    }
+    return;
+  }
+  if (warp == W + 1) {
+    // ================================ gatekeeper warp ================================
+    if (lane == 0) {
+      const int per_layer_warm = (BIG ? 2 : 3) + 1, per_layer_skip = 64 / KPC;
+      const int post_chunks = 1 + kS / KPC + kS / (2 * KPC);
+      for (int pos = 0; pos <= last_pos; pos++) {
+        const bool want = pos >= p.P - 1;
+        const int n = L * (per_layer_warm + (want ? per_layer_skip : 0)) + (want ? post_chunks : 0);
+        for (int i = 0; i < n; i++) ring.gate();
       }
     }
     return;
@@ -642,16 +676,16 @@ int decode_warp_launch(dw::Params& p, int W_packed, cudaStream_t st) {
     if (sp != 1 && sp != 2 && sp != 4 && sp != 8) sp = 1;
     p.split = sp;
   }
-  const size_t smem = (size_t)nslot * (big ? 2 * kSlot : kSlot) + 2 * nslot * sizeof(uint64_t) + work;
+  const size_t smem = (size_t)nslot * (big ? 2 * kSlot : kSlot) + 2 * nslot * sizeof(uint64_t) + 16 + work;
   const int grid = cdiv(p.B, NU);
 #define WNB_LAUNCH_DW(N, WW)                                                                                             \
   do {                                                                                                                   \
     if (big) {                                                                                                           \
       WNB_CUDA(cudaFuncSetAttribute(decode_warp_kernel<N, WW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-      decode_warp_kernel<N, WW, true><<<grid, WW * 32 + 32, smem, st>>>(p);                                              \
+      decode_warp_kernel<N, WW, true><<<grid, WW * 32 + 64, smem, st>>>(p);                                              \
     } else {                                                                                                             \
       WNB_CUDA(cudaFuncSetAttribute(decode_warp_kernel<N, WW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-      decode_warp_kernel<N, WW, false><<<grid, WW * 32 + 32, smem, st>>>(p);                                             \
+      decode_warp_kernel<N, WW, false><<<grid, WW * 32 + 64, smem, st>>>(p);                                             \
     }                                                                                                                    \
   } while (0)
   if (NU == 4) WNB_LAUNCH_DW(4, 8);
