@@ -8,6 +8,7 @@
 // Used for: the post network forward (wavenet.py:518-523) and backward, the residual-stream data
 // gradient dX (two time-shifted segments) and the aux gradient dhaux (reduce-add).
 #include <cuda.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -20,18 +21,22 @@ constexpr int kTM = 128;
 constexpr int kASub = kTM * 32 * 4;      // 16 KB
 constexpr int kStg = 32 * 32 * 4;        // 4 KB
 constexpr int kThreadsN = 192;
-constexpr int kMaxSeg = 3;
+constexpr int kMaxSeg = 4;
 
-struct Seg { int amap; int shift; int K; int bmap; int b_k0; int b_n0; };
+struct Seg { int amap; int shift; int K; int bmap; int b_k0; int b_n0; int b_n1; };  // b_n1 >= 0: rows of the 2nd half of N
 struct alignas(64) Params {
-  CUtensorMap maps[8];    // [0..2] A tensors, [3..5] weight matrices, [6] output, [7] second output (gate mode)
+  CUtensorMap maps[10];   // [0..3] A tensors, [4..7] weight matrices, [8] output, [9] second output
   Seg seg[kMaxSeg];
   int nseg, N, T, B, nstages, nacc;
   const float* bias; const float* mask; int ldmask; const float* add; int ldadd;
   int relu_out, accumulate;
-  // gate-backward epilogue (N == 128 = [sigmoid pre | tanh pre], R = 64): dz (B,T,64) in, z -> maps[6], dpre -> maps[7]
-  const float* gate_dz;
-  // split output: columns >= out2_col0 (> 0) are reduce-added into maps[7] at column c - out2_col0; bias / add /
+  // gate epilogues (N == 128 = [64 sigmoid pre | 64 tanh pre] of gate channels gate_c0 .. gate_c0+63 of gate_R):
+  //   forward  (gate_mode 1): z -> maps[8] at column gate_c0 + c
+  //   backward (gate_mode 2): dz (B,T,gate_R) in;  z -> maps[8];  dpre -> maps[9] at columns gate_c0+c / gate_R+gate_c0+c
+  // bias = sigmoid-branch bias, bias2 = tanh-branch bias (already offset by gate_c0)
+  const float* gate_dz; const float* bias2;
+  int gate_mode, gate_c0, gate_R;
+  // split output: columns >= out2_col0 (> 0) are reduce-added into maps[9] at column c - out2_col0; bias / add /
   // mask / ReLU apply to the primary columns only
   int out2_col0;
 };
@@ -75,7 +80,7 @@ __global__ void __launch_bounds__(kThreadsN, 1) gemm_nt_tc_kernel(const __grid_c
 
   if (warp == 0) {
     if (lane == 0) {
-      for (int i = 0; i < 8; i++) ptx::prefetch_tmap(&p.maps[i]);
+      for (int i = 0; i < 10; i++) ptx::prefetch_tmap(&p.maps[i]);
       uint32_t g = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int b = tile / tiles_per_b, t0 = (tile - b * tiles_per_b) * kTM;
@@ -87,8 +92,13 @@ __global__ void __launch_bounds__(kThreadsN, 1) gemm_nt_tc_kernel(const __grid_c
             ptx::mbar_arrive_expect_tx(&full[st], stage_bytes);
             unsigned char* dst = smem + (size_t)st * stage_bytes;
             ptx::tma_load_3d(dst, &p.maps[sg.amap], &full[st], kc * 32, t0 + sg.shift, b);
-            for (int n0 = 0; n0 < N; n0 += 256)
-              ptx::tma_load_2d(dst + kASub + n0 * 128, &p.maps[sg.bmap], &full[st], sg.b_k0 + kc * 32, sg.b_n0 + n0);
+            if (sg.b_n1 >= 0) {   // N = two row ranges of N/2 each (sigmoid rows, tanh rows)
+              ptx::tma_load_2d(dst + kASub, &p.maps[sg.bmap], &full[st], sg.b_k0 + kc * 32, sg.b_n0);
+              ptx::tma_load_2d(dst + kASub + (N / 2) * 128, &p.maps[sg.bmap], &full[st], sg.b_k0 + kc * 32, sg.b_n1);
+            } else {
+              for (int n0 = 0; n0 < N; n0 += 256)
+                ptx::tma_load_2d(dst + kASub + n0 * 128, &p.maps[sg.bmap], &full[st], sg.b_k0 + kc * 32, sg.b_n0 + n0);
+            }
           }
         }
       }
@@ -135,8 +145,8 @@ __global__ void __launch_bounds__(kThreadsN, 1) gemm_nt_tc_kernel(const __grid_c
       const uint32_t use = (p.nacc == 2) ? (it >> 1) : it;
       ptx::mbar_wait(&dfull[buf], use & 1);
       ptx::tc_fence_after();
-      if (p.gate_dz) {
-        // ---- gate backward: pair sigmoid column c with tanh column 64 + c ----
+      if (p.gate_mode) {
+        // ---- gate epilogues: pair sigmoid column c with tanh column 64 + c ----
         for (int c0 = 0; c0 < 64; c0 += 32) {
           float a[32], g[32];
           {
@@ -157,8 +167,31 @@ __global__ void __launch_bounds__(kThreadsN, 1) gemm_nt_tc_kernel(const __grid_c
             ptx::mbar_arrive(&dempty[buf]);
           }
           float dzv[32];
+          if (p.gate_mode == 1) {
+            // forward: z only
+#pragma unroll
+            for (int i = 0; i < 32; i++) {
+              const float sg = 0.5f * ptx::tanh_approx(0.5f * (a[i] + __ldg(p.bias + c0 + i))) + 0.5f;
+              dzv[i] = sg * ptx::tanh_approx(g[i] + __ldg(p.bias2 + c0 + i));
+            }
+            unsigned char* sb = stg + (nstore & 1) * kStg;
+            if (lane == 0) ptx::bulk_wait_read<1>();
+            __syncwarp();
+            float4* dstrow = reinterpret_cast<float4*>(sb + lane * 128);
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+              dstrow[j ^ (lane & 7)] = make_float4(dzv[4 * j], dzv[4 * j + 1], dzv[4 * j + 2], dzv[4 * j + 3]);
+            ptx::fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              ptx::tma_store_3d(&p.maps[8], sb, p.gate_c0 + c0, t0 + q * 32, b);
+              ptx::bulk_commit();
+            }
+            nstore++;
+            continue;
+          }
           if (row_ok) {
-            const float4* dr = reinterpret_cast<const float4*>(p.gate_dz + grow * 64 + c0);
+            const float4* dr = reinterpret_cast<const float4*>(p.gate_dz + grow * p.gate_R + p.gate_c0 + c0);
 #pragma unroll
             for (int j = 0; j < 8; j++) {
               const float4 d4 = __ldg(dr + j);
@@ -171,7 +204,7 @@ __global__ void __launch_bounds__(kThreadsN, 1) gemm_nt_tc_kernel(const __grid_c
 #pragma unroll
           for (int i = 0; i < 32; i++) {
             const float sg = 0.5f * ptx::tanh_approx(0.5f * (a[i] + __ldg(p.bias + c0 + i))) + 0.5f;
-            const float th = ptx::tanh_approx(g[i] + __ldg(p.bias + 64 + c0 + i));
+            const float th = ptx::tanh_approx(g[i] + __ldg(p.bias2 + c0 + i));
             const float dz = dzv[i];
             a[i] = dz * th * sg * (1.f - sg);      // d pre-sigmoid
             g[i] = dz * sg * (1.f - th * th);      // d pre-tanh
@@ -190,8 +223,8 @@ __global__ void __launch_bounds__(kThreadsN, 1) gemm_nt_tc_kernel(const __grid_c
             ptx::fence_proxy_async();
             __syncwarp();
             if (lane == 0) {
-              if (which == 0) ptx::tma_store_3d(&p.maps[6], sb, c0, t0 + q * 32, b);
-              else ptx::tma_store_3d(&p.maps[7], sb, (which == 1 ? 0 : 64) + c0, t0 + q * 32, b);
+              if (which == 0) ptx::tma_store_3d(&p.maps[8], sb, p.gate_c0 + c0, t0 + q * 32, b);
+              else ptx::tma_store_3d(&p.maps[9], sb, (which == 1 ? 0 : p.gate_R) + p.gate_c0 + c0, t0 + q * 32, b);
               ptx::bulk_commit();
             }
             nstore++;
@@ -249,9 +282,9 @@ __global__ void __launch_bounds__(kThreadsN, 1) gemm_nt_tc_kernel(const __grid_c
         ptx::fence_proxy_async();
         __syncwarp();
         if (lane == 0) {
-          if (second) ptx::tma_reduce_add_3d(&p.maps[7], sb, c0 - p.out2_col0, t0 + q * 32, b);
-          else if (p.accumulate) ptx::tma_reduce_add_3d(&p.maps[6], sb, c0, t0 + q * 32, b);
-          else ptx::tma_store_3d(&p.maps[6], sb, c0, t0 + q * 32, b);
+          if (second) ptx::tma_reduce_add_3d(&p.maps[9], sb, c0 - p.out2_col0, t0 + q * 32, b);
+          else if (p.accumulate) ptx::tma_reduce_add_3d(&p.maps[8], sb, c0, t0 + q * 32, b);
+          else ptx::tma_store_3d(&p.maps[8], sb, c0, t0 + q * 32, b);
           ptx::bulk_commit();
         }
         nstore++;
@@ -304,11 +337,13 @@ static bool map2(CUtensorMap* m, const float* base, int K, int Nrows, int box_ro
 // One segment: activation tensor (B,T,CA) read at rows t+shift, channels [0,K); weight matrix w (rows x ldw,
 // K-contiguous) rows [n0, n0+N), columns [k0, k0+K).
 struct NtTcSeg { const float* a; int CA; int shift; int K; const float* w; int w_rows; int w_cols; int k0; int n0; };
+// gate epilogue request: mode 1 = forward (z out), 2 = backward (dz in, z + dpre out); channels c0..c0+63 of R
+struct NtTcGate { int mode; int c0; int R; const float* bias_sig; const float* bias_tanh; const float* dz; float* dpre; };
 
 int gemm_nt_tc(const NtTcSeg* segs, int nseg, int N, float* out, int ld_out, const float* bias, const float* mask,
                int ldmask, const float* add, int ldadd, int relu_out, int accumulate, int B, int T, cudaStream_t st,
                const float* gate_dz = nullptr, float* gate_dpre = nullptr, float* out2 = nullptr, int ld_out2 = 0,
-               int out2_col0 = 0) {
+               int out2_col0 = 0, const NtTcGate* gate = nullptr) {
   using namespace nt;
   if (nseg < 1 || nseg > kMaxSeg || N % 32 != 0 || N < 32 || N > 512 || (N > 256 && N != 512) || ld_out % 4 != 0) {
     set_error("gemm_nt_tc: unsupported shape (nseg=%d N=%d)", nseg, N);
@@ -316,28 +351,42 @@ int gemm_nt_tc(const NtTcSeg* segs, int nseg, int N, float* out, int ld_out, con
   }
   Params p;
   memset(&p, 0, sizeof(p));
-  const int nbox = N > 256 ? 256 : N;
+  const int nbox = gate ? 64 : (N > 256 ? 256 : N);
   for (int s = 0; s < nseg; s++) {
     if (segs[s].K % 32 != 0) { set_error("gemm_nt_tc: K must be a multiple of 32"); return WNB_ERR_INVALID; }
     if (!map3(&p.maps[s], segs[s].a, segs[s].CA, T, B, kTM) ||
-        !map2(&p.maps[3 + s], segs[s].w, segs[s].w_cols, segs[s].w_rows, nbox)) {
+        !map2(&p.maps[4 + s], segs[s].w, segs[s].w_cols, segs[s].w_rows, nbox)) {
       set_error("gemm_nt_tc: tensor map creation failed");
       return WNB_ERR_CUDA;
     }
-    p.seg[s] = Seg{s, segs[s].shift, segs[s].K, 3 + s, segs[s].k0, segs[s].n0};
+    p.seg[s] = Seg{s, segs[s].shift, segs[s].K, 4 + s, segs[s].k0, segs[s].n0, -1};
   }
-  for (int s = nseg; s < 3; s++) { p.maps[s] = p.maps[0]; p.maps[3 + s] = p.maps[3]; }
-  if (!map3(&p.maps[6], out, ld_out, T, B, 32)) { set_error("gemm_nt_tc: output map failed"); return WNB_ERR_CUDA; }
-  p.maps[7] = p.maps[6];
-  if (gate_dz) {
-    if (N != 128 || !gate_dpre || !bias || !map3(&p.maps[7], gate_dpre, 128, T, B, 32)) {
+  for (int s = nseg; s < 4; s++) { p.maps[s] = p.maps[0]; p.maps[4 + s] = p.maps[4]; }
+  if (!map3(&p.maps[8], out, ld_out, T, B, 32)) { set_error("gemm_nt_tc: output map failed"); return WNB_ERR_CUDA; }
+  p.maps[9] = p.maps[8];
+  if (gate_dz) {   // R = 64 shorthand used by the fused-shape backward: whole gate in one launch
+    if (N != 128 || !gate_dpre || !bias || !map3(&p.maps[9], gate_dpre, 128, T, B, 32)) {
       set_error("gemm_nt_tc: bad gate-backward configuration");
       return WNB_ERR_INVALID;
     }
-    p.gate_dz = gate_dz;
+    p.gate_dz = gate_dz; p.bias2 = bias + 64; p.gate_mode = 2; p.gate_c0 = 0; p.gate_R = 64;
+  }
+  if (gate) {      // general form: 64 gate channels [c0, c0+64) of R; W rows c0.. (sigmoid) and R+c0.. (tanh)
+    if (N != 128 || gate->R % 64 != 0 || gate->c0 % 64 != 0 || gate->c0 + 64 > gate->R || !gate->bias_sig ||
+        !gate->bias_tanh || (gate->mode != 1 && gate->mode != 2) || (gate->mode == 2 && (!gate->dz || !gate->dpre))) {
+      set_error("gemm_nt_tc: bad gate configuration");
+      return WNB_ERR_INVALID;
+    }
+    if (gate->mode == 2 && !map3(&p.maps[9], gate->dpre, 2 * gate->R, T, B, 32)) {
+      set_error("gemm_nt_tc: dpre map failed");
+      return WNB_ERR_CUDA;
+    }
+    for (int s = 0; s < nseg; s++) { p.seg[s].b_n0 = gate->c0; p.seg[s].b_n1 = gate->R + gate->c0; }
+    p.bias = gate->bias_sig; p.bias2 = gate->bias_tanh; p.gate_dz = gate->dz;
+    p.gate_mode = gate->mode; p.gate_c0 = gate->c0; p.gate_R = gate->R;
   }
   if (out2) {
-    if (gate_dz || out2_col0 <= 0 || out2_col0 % 32 != 0 || out2_col0 >= N || !map3(&p.maps[7], out2, ld_out2, T, B, 32)) {
+    if (gate_dz || out2_col0 <= 0 || out2_col0 % 32 != 0 || out2_col0 >= N || !map3(&p.maps[9], out2, ld_out2, T, B, 32)) {
       set_error("gemm_nt_tc: bad split-output configuration");
       return WNB_ERR_INVALID;
     }
@@ -349,7 +398,9 @@ int gemm_nt_tc(const NtTcSeg* segs, int nseg, int N, float* out, int ld_out, con
   p.nacc = N <= 256 ? 2 : 1;
   const int stage_bytes = kASub + N * 128;
   int nst = (int)((227 * 1024 - 1024 - 512 - 4 * 2 * kStg) / stage_bytes);
-  if (nst > 4) nst = 4;
+  static int max_stages = 0;
+  if (!max_stages) { const char* e = getenv("WNB_NT_MAXSTAGES"); max_stages = e ? atoi(e) : 4; if (max_stages < 2) max_stages = 2; }
+  if (nst > max_stages) nst = max_stages;
   if (nst < 2) { set_error("gemm_nt_tc: N too large"); return WNB_ERR_INVALID; }
   p.nstages = nst;
   const size_t smem = (size_t)nst * stage_bytes + 4 * 2 * kStg + 512 + 1024;

@@ -358,10 +358,11 @@ int wgrad_tc(const WgOperand* a_ops, int na_ops, const WgOperand* b_ops, int nb_
 
 // implemented in gemm_nt_tc.cu
 struct NtTcSeg { const float* a; int CA; int shift; int K; const float* w; int w_rows; int w_cols; int k0; int n0; };
+struct NtTcGate { int mode; int c0; int R; const float* bias_sig; const float* bias_tanh; const float* dz; float* dpre; };
 int gemm_nt_tc(const NtTcSeg* segs, int nseg, int N, float* out, int ld_out, const float* bias, const float* mask,
                int ldmask, const float* add, int ldadd, int relu_out, int accumulate, int B, int T, cudaStream_t st,
                const float* gate_dz = nullptr, float* gate_dpre = nullptr, float* out2 = nullptr, int ld_out2 = 0,
-               int out2_col0 = 0);
+               int out2_col0 = 0, const NtTcGate* gate = nullptr);
 
 static bool nt_tc_n_ok(int N) { return N % 32 == 0 && N >= 32 && (N <= 256 || N == 512); }
 
@@ -392,9 +393,78 @@ static int wgrad_tc_full(const float* a, int CA, int M, const float* b, int CB, 
   return WNB_OK;
 }
 
+// Weight gradient with A = the channel concatenation [a0 (C0) | a1 (C1)] (a1 may be null), M = rows used,
+// B = channels [0, N) of tensor b (CB channels) read at time t + shift:  C (M x N, ldc) += A^T B, db (M) += colsum A.
+// M-blocks of 128 rows are batched per launch as far as TMEM allows; N goes in chunks of <= 224 columns.
+static int wgrad_tc_concat(const float* a0, int C0, const float* a1, int C1, int M, const float* b, int CB, int N,
+                           int shift, float* c, int ldc, float* db, int B, int T, cudaStream_t st) {
+  int rc;
+  for (int n0 = 0; n0 < N; n0 += 224) {
+    const int ncols = (N - n0) < 224 ? (N - n0) : 224;
+    const bool with_db = db && n0 == 0;
+    int per_launch = 512 / (ncols + (with_db ? 32 : 0));
+    if (per_launch > 5) per_launch = 5;
+    const WgOperand bo[1] = {{b, CB, n0, ncols / 32, shift}};
+    WgBlock blk[5];
+    int nblk = 0;
+    for (int m0 = 0; m0 < M; m0 += 128) {
+      WgBlock& bk = blk[nblk];
+      bk.m_valid = (M - m0) < 128 ? (M - m0) : 128;
+      bk.c = c + (size_t)m0 * ldc + n0;
+      bk.db = with_db ? db + m0 : nullptr;
+      // rows m0..m0+127 of the concatenation, in groups of 32 channels
+      if (m0 + 128 <= C0 || !a1) {
+        bk.nops = 1;
+        bk.ops[0] = WgOperand{a0, C0, m0, 4, 0};            // (groups past C0 are TMA zero fill)
+      } else if (m0 >= C0) {
+        bk.nops = 1;
+        bk.ops[0] = WgOperand{a1, C1, m0 - C0, 4, 0};
+      } else {
+        const int g0 = (C0 - m0) / 32;                       // groups still inside a0
+        bk.nops = 2;
+        bk.ops[0] = WgOperand{a0, C0, m0, g0, 0};
+        bk.ops[1] = WgOperand{a1, C1, 0, 4 - g0, 0};
+      }
+      if (++nblk == per_launch || m0 + 128 >= M) {
+        if ((rc = wgrad_tc_blocks(blk, nblk, bo, 1, ldc, B, T, st)) != WNB_OK) return rc;
+        nblk = 0;
+      }
+    }
+  }
+  return WNB_OK;
+}
+
+// shapes the composed tensor-core path covers (generic tcgen05 GEMMs + gate epilogues per 64-channel chunk)
+static bool composed_tc_supported(int R, int S, int Ap, int ks) {
+  return R % 64 == 0 && nt_tc_n_ok(R) && nt_tc_n_ok(S) && Ap % 32 == 0 && Ap <= 256 && ks >= 1 && ks <= 3;
+}
+
 // implemented in resblock_tc.cu
 int resblock_fwd_tc(const FwdParams& p, cudaStream_t st);
 bool resblock_fwd_tc_supported(int R, int S, int Ap, int ks);
+
+// Forward of one residual block for shapes outside the fused kernel: R/64 gate GEMMs (N = 128: 64 sigmoid + 64
+// tanh rows of W1, K = ks*R + Ap streamed) with the gate epilogue writing z, then the res GEMM (+bias, +x) and the
+// skip GEMM (+bias, store or reduce-add).  z (B,T,R) goes through p.zsave.
+static int resblock_fwd_composed(const FwdParams& p, cudaStream_t st) {
+  const int R = p.R, S = p.S, Ap = p.Ap, ks = p.ks, K1 = ks * R + Ap;
+  NtTcSeg segs[4];
+  int ns = 0, rc;
+  for (int j = 0; j < ks; j++) segs[ns++] = NtTcSeg{p.xin, R, -(ks - 1 - j) * p.d, R, p.w1, 2 * R, K1, j * R, 0};
+  segs[ns++] = NtTcSeg{p.haux, Ap, 0, Ap, p.w1, 2 * R, K1, ks * R, 0};
+  for (int c0 = 0; c0 < R; c0 += 64) {
+    const NtTcGate g{1, c0, R, p.b1 + c0, p.b1 + R + c0, nullptr, nullptr};
+    if ((rc = gemm_nt_tc(segs, ns, 128, p.zsave, R, nullptr, nullptr, 0, nullptr, 0, 0, 0, p.B, p.T, st, nullptr, nullptr,
+                         nullptr, 0, 0, &g)) != WNB_OK)
+      return rc;
+  }
+  if (p.xout) {
+    const NtTcSeg sr[1] = {{p.zsave, R, 0, R, p.w2, R + S, R, 0, 0}};
+    if ((rc = gemm_nt_tc(sr, 1, R, p.xout, R, p.b2, nullptr, 0, p.xin, R, 0, 0, p.B, p.T, st)) != WNB_OK) return rc;
+  }
+  const NtTcSeg ss[1] = {{p.zsave, R, 0, R, p.w2, R + S, R, 0, R}};
+  return gemm_nt_tc(ss, 1, S, p.skip, S, p.b2 + R, nullptr, 0, nullptr, 0, 0, p.skip_init ? 0 : 1, p.B, p.T, st);
+}
 
 }  // namespace wnb
 
@@ -409,9 +479,11 @@ WNB_API int wnb_resblock_fwd(const float* xin, const float* haux, const float* w
   WNB_REQUIRE(xin && haux && w1 && b1 && w2 && b2 && skip, "resblock_fwd: null pointer");
   FwdParams p{xin, haux, w1, b1, w2, b2, xout, skip, zsave, B, T, R, S, Ap, ks, dilation, skip_init};
   if (math_mode == WNB_MATH_TF32) {
-    WNB_REQUIRE(resblock_fwd_tc_supported(R, S, Ap, ks), "resblock_fwd: shape R=%d S=%d Ap=%d ks=%d not supported by the "
-                "tcgen05 path (use WNB_MATH_FP32)", R, S, Ap, ks);
-    return resblock_fwd_tc(p, (cudaStream_t)stream);
+    if (resblock_fwd_tc_supported(R, S, Ap, ks)) return resblock_fwd_tc(p, (cudaStream_t)stream);
+    WNB_REQUIRE(composed_tc_supported(R, S, Ap, ks), "resblock_fwd: shape R=%d S=%d Ap=%d ks=%d not supported by the "
+                "tcgen05 paths (use WNB_MATH_FP32)", R, S, Ap, ks);
+    WNB_REQUIRE(zsave, "resblock_fwd: the composed tcgen05 path needs the zsave (B,T,R) scratch buffer");
+    return resblock_fwd_composed(p, (cudaStream_t)stream);
   }
   WNB_REQUIRE(math_mode == WNB_MATH_FP32, "resblock_fwd: unknown math_mode %d", math_mode);
   const size_t smem = sizeof(TileSmem<8>) + (size_t)R * kBsLd * sizeof(float);
@@ -429,7 +501,8 @@ WNB_API int wnb_resblock_fwd(const float* xin, const float* haux, const float* w
 
 WNB_API int wnb_resblock_fwd_supported(int R, int S, int Ap, int ks, int math_mode) {
   if (R <= 0 || S <= 0 || Ap <= 0 || ks < 1) return 0;
-  if (math_mode == WNB_MATH_TF32) return resblock_fwd_tc_supported(R, S, Ap, ks) ? 1 : 0;
+  if (math_mode == WNB_MATH_TF32)   // 1 = fused kernel, 2 = composed tcgen05 path (needs the zsave scratch)
+    return resblock_fwd_tc_supported(R, S, Ap, ks) ? 1 : (composed_tc_supported(R, S, Ap, ks) ? 2 : 0);
   return (sizeof(TileSmem<8>) + (size_t)R * kBsLd * sizeof(float)) <= 227 * 1024 ? 1 : 0;
 }
 
@@ -451,7 +524,47 @@ WNB_API int wnb_resblock_bwd(const float* xin, const float* haux, const float* d
   float* dpre = z + (size_t)B * T * R;
   const int K1 = ks * R + Ap, M2 = R + S;
   int rc;
-  const bool tc_bwd = math_mode == WNB_MATH_TF32 && R == 64 && ks == 2 && Ap == 32 && S % 32 == 0;
+  const bool tc_fused_shape = math_mode == WNB_MATH_TF32 && R == 64 && ks == 2 && Ap == 32 && S % 32 == 0;
+  if (math_mode == WNB_MATH_TF32 && !tc_fused_shape && composed_tc_supported(R, S, Ap, ks)) {
+    // ---------------- composed tensor-core backward for general shapes ----------------
+    float* dz = dxin;   // (B,T,R) scratch until the dX GEMM overwrites it
+    if (dout) {
+      const NtTcSeg sz[2] = {{dout, R, 0, R, w2t, R, R + S, 0, 0}, {dskip, S, 0, S, w2t, R, R + S, R, 0}};
+      if ((rc = gemm_nt_tc(sz, 2, R, dz, R, nullptr, nullptr, 0, nullptr, 0, 0, 0, B, T, st)) != WNB_OK) return rc;
+    } else {
+      const NtTcSeg sz[1] = {{dskip, S, 0, S, w2t, R, R + S, R, 0}};
+      if ((rc = gemm_nt_tc(sz, 1, R, dz, R, nullptr, nullptr, 0, nullptr, 0, 0, 0, B, T, st)) != WNB_OK) return rc;
+    }
+    NtTcSeg sg[4];
+    int ns = 0;
+    for (int j = 0; j < ks; j++) sg[ns++] = NtTcSeg{xin, R, -(ks - 1 - j) * dilation, R, w1, 2 * R, K1, j * R, 0};
+    sg[ns++] = NtTcSeg{haux, Ap, 0, Ap, w1, 2 * R, K1, ks * R, 0};
+    for (int c0 = 0; c0 < R; c0 += 64) {   // gate recompute + z + dpre, 64 gate channels per launch
+      const NtTcGate g{2, c0, R, b1 + c0, b1 + R + c0, dz, dpre};
+      if ((rc = gemm_nt_tc(sg, ns, 128, z, R, nullptr, nullptr, 0, nullptr, 0, 0, 0, B, T, st, nullptr, nullptr, nullptr, 0,
+                           0, &g)) != WNB_OK)
+        return rc;
+    }
+    {  // dxin = dout + sum_j dpre(t + (ks-1-j)d) W1[:, tap j]
+      NtTcSeg sx[3];
+      for (int j = 0; j < ks; j++) sx[j] = NtTcSeg{dpre, 2 * R, (ks - 1 - j) * dilation, 2 * R, w1t, K1, 2 * R, 0, j * R};
+      if ((rc = gemm_nt_tc(sx, ks, R, dxin, R, nullptr, nullptr, 0, dout, R, 0, 0, B, T, st)) != WNB_OK) return rc;
+    }
+    if (dhaux) {
+      const NtTcSeg sh[1] = {{dpre, 2 * R, 0, 2 * R, w1t, K1, 2 * R, 0, ks * R}};
+      if ((rc = gemm_nt_tc(sh, 1, Ap, dhaux, Ap, nullptr, nullptr, 0, nullptr, 0, 0, 1, B, T, st)) != WNB_OK) return rc;
+    }
+    // dW1 = dpre^T [x taps | aux]  (+ db1), dW2 = [dout | dskip]^T z  (+ db2)
+    for (int j = 0; j < ks; j++)
+      if ((rc = wgrad_tc_concat(dpre, 2 * R, nullptr, 0, 2 * R, xin, R, R, -(ks - 1 - j) * dilation, dw1 + j * R, K1,
+                                j == 0 ? db1 : nullptr, B, T, st)) != WNB_OK)
+        return rc;
+    if ((rc = wgrad_tc_concat(dpre, 2 * R, nullptr, 0, 2 * R, haux, Ap, Ap, 0, dw1 + ks * R, K1, nullptr, B, T, st)) != WNB_OK)
+      return rc;
+    if (dout) return wgrad_tc_concat(dout, R, dskip, S, R + S, z, R, R, 0, dw2, R, db2, B, T, st);
+    return wgrad_tc_concat(dskip, S, nullptr, 0, S, z, R, R, 0, dw2 + (size_t)R * R, R, db2 + R, B, T, st);
+  }
+  const bool tc_bwd = tc_fused_shape;
   if (tc_bwd) {
     // dz[t][c] = sum_r w2[r][c] dout[t][r] + sum_s w2[R+s][c] dskip[t][s]   (w2t: rows c, cols o)
     float* dz = dxin;   // dxin is not produced until the dX GEMM below: use it as the (B,T,64) scratch for dz

@@ -13,6 +13,7 @@
 // out of range by TMA.  An optional extra all-ones B group turns column 0 of that group into the bias
 // gradient sum_t A[t][m] (replaces colsum_kernel).
 #include <cuda.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -35,7 +36,7 @@ struct alignas(64) Params {
   int m_valid[kMaxMB];           // rows >= m_valid are padding (not written)
   float* db[kMaxMB];             // per block (128) or null
   int T, B, tiles_per_b, ntiles, nstages;
-  int tk;                        // time rows per stage (K of one stage): 64 or 32
+  int tk;                        // time rows per stage (K of one stage): 64, 32 or 16
 };
 
 __device__ __forceinline__ uint64_t smem_desc_mn_sw128(uint32_t saddr, uint32_t lbo_bytes) {
@@ -210,13 +211,17 @@ int wgrad_tc_blocks(const WgBlock* blocks, int nblocks, const WgOperand* b_ops, 
   if (p.nB < 1 || p.nB > kMaxB - 1) { set_error("wgrad_tc: 1..7 B groups"); return WNB_ERR_INVALID; }
   const int N = 32 * (p.nB + p.use_ones);
   if (N * nblocks > 512) { set_error("wgrad_tc: accumulators exceed TMEM (%d x %d columns)", nblocks, N); return WNB_ERR_INVALID; }
-  // rows per stage: the largest of {64, 32} that leaves at least 2 stages
+  // rows per stage: HBM needs several stages of loads in flight per SM (ncu: 2 stages of 64 rows ran at 40 % of
+  // peak), so take the largest of {64, 32, 16} that still leaves at least 4 stages
+  const int groups = 4 * nblocks + p.nB + p.use_ones;
   int tk = 64;
-  if ((220 * 1024) / ((4 * nblocks + p.nB + p.use_ones) * 64 * 128) < 2) tk = 32;
+  static int min_stages = 0;
+  if (!min_stages) { const char* e = getenv("WNB_WG_MINSTAGES"); min_stages = e ? atoi(e) : 2; if (min_stages < 2) min_stages = 2; }
+  while (tk > 16 && (220 * 1024) / (groups * tk * 128) < min_stages) tk >>= 1;
   const int sub = tk * 128;
-  const int stage_bytes = (4 * nblocks + p.nB + p.use_ones) * sub;
+  const int stage_bytes = groups * sub;
   int nst = (220 * 1024) / stage_bytes;
-  if (nst > 6) nst = 6;
+  if (nst > 8) nst = 8;
   if (nst < 2) { set_error("wgrad_tc: stage too large"); return WNB_ERR_INVALID; }
   p.tk = tk;
   p.nstages = nst;

@@ -177,6 +177,10 @@ class _WaveNetFn(torch.autograd.Function):
         xs = torch.empty(nbuf, B, T, R, device=dev, dtype=torch.float32)
         check(lib.wnb_front_embed_fwd(ptr(x), ptr(wf), ptr(bf), ptr(xs[0]), B, T, Q, R, ks, st), "front_embed_fwd")
         skip = torch.empty(B, T, S, device=dev, dtype=torch.float32)
+        # shapes outside the fused tcgen05 kernel run the composed tcgen05 path, which needs a z scratch
+        zbuf = None
+        if math_mode == MATH_TF32 and lib.wnb_resblock_fwd_supported(R, S, Ap, ks, MATH_TF32) == 2:
+            zbuf = torch.empty(B, T, R, device=dev, dtype=torch.float32)
         prof = PROFILE_EVENTS
         for l, d in enumerate(dilations):
             xin = xs[l % nbuf]
@@ -185,7 +189,7 @@ class _WaveNetFn(torch.autograd.Function):
                 ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
                 ev[0].record()
             check(lib.wnb_resblock_fwd(ptr(xin), ptr(haux), ptr(W1[l]), ptr(b1[l]), ptr(W2[l]), ptr(b2[l]),
-                                       ptr(xout), ptr(skip), None, B, T, R, S, Ap, ks, int(d),
+                                       ptr(xout), ptr(skip), ptr(zbuf), B, T, R, S, Ap, ks, int(d),
                                        1 if l == 0 else 0, math_mode, st), "resblock_fwd")
             if prof is not None:
                 ev[1].record()

@@ -165,3 +165,92 @@ def test_tf32_training_learns():
         losses.append(loss.item())
     assert np.isfinite(losses).all()
     assert losses[0] > 5.0 and losses[-1] < 0.6 * losses[0], (losses[0], losses[-1])
+
+
+# ------------------------------------------------------------------------------------------------------------
+# composed tensor-core path: shapes outside the fused kernel (e.g. the recipes' 512 res / 256 skip, kernel_size 3)
+# ------------------------------------------------------------------------------------------------------------
+def _block_general(mode, R, S, Ap, ks, d, B, T, last, init, seed):
+    from pytorchwavenetvocoder_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    rn = lambda *sh: torch.randn(*sh, device="cuda", generator=g)  # noqa: E731
+    K1 = ks * R + Ap
+    xin, haux = rn(B, T, R), rn(B, T, Ap)
+    W1 = (rn(2 * R, K1) / np.sqrt(K1)).contiguous()
+    W2 = (rn(R + S, R) / np.sqrt(R)).contiguous()
+    b1, b2 = 0.1 * rn(2 * R), 0.1 * rn(R + S)
+    skip = torch.zeros(B, T, S, device="cuda") if init else rn(B, T, S)
+    xout = None if last else torch.full((B, T, R), float("nan"), device="cuda")
+    zbuf = torch.empty(B, T, R, device="cuda") if lib.wnb_resblock_fwd_supported(R, S, Ap, ks, mode) == 2 else None
+    _lib.check(lib.wnb_resblock_fwd(_lib.ptr(xin), _lib.ptr(haux), _lib.ptr(W1), _lib.ptr(b1), _lib.ptr(W2),
+                                    _lib.ptr(b2), _lib.ptr(xout), _lib.ptr(skip), _lib.ptr(zbuf), B, T, R, S, Ap, ks, d,
+                                    1 if init else 0, mode, _lib.stream()), "resblock_fwd")
+    # backward with the same operands
+    dout = None if last else rn(B, T, R)
+    dskip = rn(B, T, S)
+    w1t, w2t = W1.t().contiguous(), W2.t().contiguous()
+    ws = torch.empty(lib.wnb_resblock_bwd_workspace(B, T, R, S, Ap, ks) // 4, device="cuda")
+    dx = torch.empty(B, T, R, device="cuda")
+    dh = torch.zeros(B, T, Ap, device="cuda")
+    dw1, db1 = torch.zeros(2 * R, K1, device="cuda"), torch.zeros(2 * R, device="cuda")
+    dw2, db2 = torch.zeros(R + S, R, device="cuda"), torch.zeros(R + S, device="cuda")
+    _lib.check(lib.wnb_resblock_bwd(_lib.ptr(xin), _lib.ptr(haux), _lib.ptr(dout), _lib.ptr(dskip), _lib.ptr(W1),
+                                    _lib.ptr(b1), _lib.ptr(w1t), _lib.ptr(w2t), _lib.ptr(dx), _lib.ptr(dh),
+                                    _lib.ptr(dw1), _lib.ptr(db1), _lib.ptr(dw2), _lib.ptr(db2), _lib.ptr(ws),
+                                    B, T, R, S, Ap, ks, d, mode, _lib.stream()), "resblock_bwd")
+    torch.cuda.synchronize()
+    return dict(xout=xout, skip=skip, dx=dx, dh=dh, dw1=dw1, db1=db1, dw2=dw2, db2=db2)
+
+
+@pytest.mark.parametrize("R,S,Ap,ks,d,T,last,init", [
+    (128, 256, 32, 2, 4, 300, False, True),      # mixed [dout | dskip] wgrad block is not needed (R % 128 == 0)
+    (512, 256, 32, 2, 16, 520, False, False),    # the recipes' shape (egs/arctic/sd/run.sh:48-49)
+    (128, 64, 96, 3, 2, 260, False, False),      # kernel_size 3, 80-dim aux padded to 96 (ljspeech-like)
+    (192, 512, 32, 2, 1, 256, True, False),      # R % 128 != 0: mixed wgrad block, last layer (no dout)
+    (192, 96, 32, 3, 8, 200, False, True),
+])
+def test_composed_block_fwd_bwd_tf32_vs_fp32(R, S, Ap, ks, d, T, last, init):
+    from pytorchwavenetvocoder_b200 import _lib
+    lib = _lib.load()
+    assert lib.wnb_resblock_fwd_supported(R, S, Ap, ks, _lib.MATH_TF32) == 2
+    ref = _block_general(_lib.MATH_FP32, R, S, Ap, ks, d, 2, T, last, init, seed=R + S + T)
+    got = _block_general(_lib.MATH_TF32, R, S, Ap, ks, d, 2, T, last, init, seed=R + S + T)
+    for k, r in ref.items():
+        if r is None:
+            continue
+        g = got[k]
+        assert torch.isfinite(g).all(), k
+        rel = (g - r).norm().item() / max(r.norm().item(), 1e-12)
+        assert rel < 6e-3, (k, rel)
+
+
+def test_composed_full_model_step_tf32_vs_fp32():
+    """ljspeech-like small model (80-dim aux, kernel_size 3, R=128/S=64): tf32 (composed tcgen05 path) vs fp32."""
+    from pytorchwavenetvocoder_b200.nets import cross_entropy
+    from pytorchwavenetvocoder_b200.nets.wavenet import tc_supported
+    cfg_t = (256, 80, 128, 64, 4, 2, 3, 8)
+    assert tc_supported(cfg_t)
+    cfg = O.Config(*cfg_t)
+    p = O.make_params(cfg, 9)
+    rng = np.random.RandomState(3)
+    B, T = 2, 384
+    x = torch.from_numpy(rng.randint(0, 256, size=(B, T)).astype(np.int64)).cuda()
+    t = torch.from_numpy(rng.randint(0, 256, size=(B, T)).astype(np.int64)).cuda()
+    h = torch.from_numpy(rng.standard_normal((B, 80, T // 8)).astype(np.float32)).cuda()
+    res = {}
+    for mode in ("fp32", "tf32"):
+        net = our_model(cfg, p, math_mode=mode).train()
+        y = net(x, h)
+        loss = cross_entropy(y, t, cfg.receptive_field)
+        loss.backward()
+        res[mode] = (loss.item(), y.detach(), {k: v.grad.clone() for k, v in net.named_parameters() if v.grad is not None})
+    assert abs(res["fp32"][0] - res["tf32"][0]) < 2e-3
+    assert (res["fp32"][1] - res["tf32"][1]).abs().max().item() < 5e-2
+    for k, g in res["fp32"][2].items():
+        g2 = res["tf32"][2][k]
+        if g.numel() == 1:
+            assert (g - g2).abs().item() <= 3e-3, k
+        else:
+            tol = 0.10 if g.dim() == 1 else 0.05
+            assert (g - g2).norm().item() <= tol * g.norm().item() + 1e-7, k
