@@ -369,7 +369,7 @@ int gemm_nt_tc(const NtTcSeg* segs, int nseg, int N, float* out, int ld_out, con
       set_error("gemm_nt_tc: bad gate-backward configuration");
       return WNB_ERR_INVALID;
     }
-    p.gate_dz = gate_dz; p.bias2 = bias + 64; p.gate_mode = 2; p.gate_c0 = 0; p.gate_R = 64;
+    p.gate_dz = gate_dz; p.bias = bias; p.bias2 = bias + 64; p.gate_mode = 2; p.gate_c0 = 0; p.gate_R = 64;
   }
   if (gate) {      // general form: 64 gate channels [c0, c0+64) of R; W rows c0.. (sigmoid) and R+c0.. (tanh)
     if (N != 128 || gate->R % 64 != 0 || gate->c0 % 64 != 0 || gate->c0 + 64 > gate->R || !gate->bias_sig ||
@@ -393,7 +393,8 @@ int gemm_nt_tc(const NtTcSeg* segs, int nseg, int N, float* out, int ld_out, con
     p.out2_col0 = out2_col0;
   }
   p.nseg = nseg; p.N = N; p.T = T; p.B = B;
-  p.bias = bias; p.mask = mask; p.ldmask = ldmask; p.add = add; p.ldadd = ldadd;
+  if (!p.gate_mode) p.bias = bias;   // (the gate modes have already installed their own bias pointers)
+  p.mask = mask; p.ldmask = ldmask; p.add = add; p.ldadd = ldadd;
   p.relu_out = relu_out; p.accumulate = accumulate;
   p.nacc = N <= 256 ? 2 : 1;
   const int stage_bytes = kASub + N * 128;
