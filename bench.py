@@ -202,8 +202,9 @@ def run_ours(args):
             "value": samples / (per_step * 1e-3), "unit": "samples/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "tf32" if args.math == "tf32" else "f32", "data": "synthetic",
-            "config": {"workload": "configs[1]: arctic/sd 16kHz WaveNet(256,28,64,512,10,3,2,80) batch 8 x 23040 "
-                                   "(20000 + rf window) per GPU, Adam, loss on [rf:]",
+            "config": {"workload": ("configs[1]: arctic/sd 16kHz " if CFG == (256, 28, 64, 512, 10, 3, 2, 80) else "custom: ") +
+                                   "WaveNet%s batch %d x %d (20000 + rf window) per GPU, Adam, loss on [rf:]"
+                                   % (str(CFG).replace(" ", ""), BATCH, int(T)),
                        "global_batch": world * BATCH, "seq_len": int(T), "parallelism": "dp%d" % world,
                        "math": args.math, "storage": "fp32 channels-last",
                        "l2": "per-step working set ~10 GB >> 126 MB L2 (no explicit flush needed)"},
@@ -382,9 +383,17 @@ def main():
     ap.add_argument("--math", default=None, choices=["fp32", "tf32"])
     ap.add_argument("--with-decode", type=int, default=1, help="also report the decode workload (extra object)")
     ap.add_argument("--cpu-baseline", type=int, default=1)
+    ap.add_argument("--cfg", default=None, help="override the WaveNet ctor tuple, e.g. 256,28,512,256,10,3,2,80 "
+                                                "(recipe shape); the default is BASELINE.json configs[1]")
+    ap.add_argument("--batch", type=int, default=None, help="override the per-GPU batch (default 8)")
     ap.add_argument("--decode-utts", type=int, default=64)
     ap.add_argument("--decode-samples", type=int, default=32000)
     args = ap.parse_args()
+    global CFG, BATCH
+    if args.cfg:
+        CFG = tuple(int(v) for v in args.cfg.split(","))
+    if args.batch:
+        BATCH = args.batch
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         return run_reference(args)

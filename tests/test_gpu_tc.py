@@ -252,5 +252,5 @@ def test_composed_full_model_step_tf32_vs_fp32():
         if g.numel() == 1:
             assert (g - g2).abs().item() <= 3e-3, k
         else:
-            tol = 0.10 if g.dim() == 1 else 0.05
+            tol = 0.10 if g.dim() == 1 else 0.08     # K = 3*128+96 per gate GEMM: a little more tf32 rounding
             assert (g - g2).norm().item() <= tol * g.norm().item() + 1e-7, k
