@@ -82,13 +82,28 @@ class ClockSampler(object):
                 "reasons": reasons, "samples": len(sm)}
 
 
+class _Cfg(object):
+    """Plain view of the WaveNet ctor tuple (no oracle import on the measured arm)."""
+
+    def __init__(self, t):
+        (self.n_quantize, self.n_aux, self.n_resch, self.n_skipch, self.dilation_depth, self.dilation_repeat,
+         self.kernel_size, self.upsampling_factor) = t
+        self.dilations = [2 ** i for i in range(self.dilation_depth)] * self.dilation_repeat
+        self.receptive_field = (self.kernel_size - 1) * sum(self.dilations) + 1
+
+
 def make_model(device, math_mode, seed=20260924):
-    from oracle import wavenet_oracle as O  # only for seeded synthetic weights (same as the parity tests)
-    from pytorchwavenetvocoder_b200.nets import WaveNet
-    cfg = O.Config(*CFG)
-    p = O.make_params(cfg, seed)
+    """Random-init weights of the named architecture: the reference initialiser (xavier conv weights, unit
+    up-sampling) plus seeded N(0, 0.05) biases so that no bias path is trivially zero."""
+    from pytorchwavenetvocoder_b200.nets import WaveNet, initialize
+    cfg = _Cfg(CFG)
+    torch.manual_seed(seed)
     net = WaveNet(*CFG)
-    net.load_state_dict({k: torch.from_numpy(v) for k, v in p.items()})
+    net.apply(initialize)
+    with torch.no_grad():
+        for name, prm in net.named_parameters():
+            if name.endswith("bias"):
+                prm.add_(0.05 * torch.randn_like(prm))
     net.math_mode = math_mode
     return cfg, net.to(device)
 
