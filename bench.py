@@ -129,8 +129,19 @@ def run_ours(args):
     dist = None
     if world > 1:
         import torch.distributed as dist
-        os.environ["NCCL_DEBUG"] = os.environ.get("WNB_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL prints its version banner on stdout while the communicator is created: send fd 1 to stderr for
+        # that moment so that stdout carries nothing but the one JSON line
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     from pytorchwavenetvocoder_b200 import _lib
     from pytorchwavenetvocoder_b200.nets import cross_entropy
     from pytorchwavenetvocoder_b200.nets import wavenet as wn
