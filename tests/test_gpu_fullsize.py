@@ -39,13 +39,16 @@ def test_train_forward_causality_and_batch_independence(net):
         # batch independence: a row computed alone equals the same row inside the batch (same tiles, same order)
         y1 = model(x[3:4], h[3:4])
         assert torch.equal(y1[0], y[3])
-        # receptive field: logits at t >= rf - 1 + t1 do not depend on samples before t1
+        # receptive field: the residual stack sees receptive_field samples of the front conv's output, and the front
+        # conv (kernel_size taps) adds kernel_size - 1 more: logits at t >= t1 + rf - 1 + (ks - 1) cannot depend on
+        # samples before t1, earlier ones do
         t1 = 4096
         x3 = x.clone()
         x3[:, :t1] = 128
         y3 = model(x3, h)
-        lim = t1 + cfg.receptive_field - 1
+        lim = t1 + cfg.receptive_field - 1 + (cfg.kernel_size - 1)
         assert torch.equal(y[:, lim:], y3[:, lim:])
+        assert not torch.equal(y[:, t1:lim], y3[:, t1:lim])
 
 
 def test_train_step_full_size_decreases_loss(net):
