@@ -91,8 +91,13 @@ WNB_API int wnb_resblock_fwd(const float* xin, const float* haux, const float* w
                      int B, int T, int R, int S, int Ap, int ks, int dilation, int skip_init,
                      int math_mode, void* stream);
 
-/* 1 if (R,S,Ap,ks) is covered by the kernel family selected by math_mode, else 0 */
+/* 1 = fused kernel, 2 = composed tcgen05 path (pass the zsave scratch), 0 = not covered by math_mode */
 WNB_API int wnb_resblock_fwd_supported(int R, int S, int Ap, int ks, int math_mode);
+
+/* ---- a5 standalone: CausalConv1d.forward (wavenet.py:95-121), channels-last, fp32 FFMA, forward only.
+ * x (B,T,Cin), w (Cout, ks*Cin) with w[o][j*Cin+c] = conv.weight[o][c][j], bias (Cout) or NULL, out (B,T,Cout). */
+WNB_API int wnb_causal_conv1d_fwd(const float* x, const float* w, const float* bias, float* out, int B, int T,
+                                  int Cin, int Cout, int ks, int dilation, void* stream);
 
 /* ---- a10 backward --------------------------------------------------------------------------
  * Recomputes the gate from xin/haux, then produces dxin and accumulates weight gradients.

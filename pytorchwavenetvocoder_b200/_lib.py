@@ -37,6 +37,7 @@ SIGNATURES = {
     "wnb_aux_upsample_bwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "wnb_resblock_fwd": (_I, [_P] * 9 + [_I] * 9 + [_P]),
     "wnb_resblock_fwd_supported": (_I, [_I] * 5),
+    "wnb_causal_conv1d_fwd": (_I, [_P] * 4 + [_I] * 6 + [_P]),
     "wnb_resblock_bwd_workspace": (_c.c_size_t, [_I] * 6),
     "wnb_resblock_bwd": (_I, [_P] * 15 + [_I] * 8 + [_P]),
     "wnb_post_fwd": (_I, [_P] * 7 + [_I] * 5 + [_P]),

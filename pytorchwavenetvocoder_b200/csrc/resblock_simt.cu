@@ -499,6 +499,19 @@ WNB_API int wnb_resblock_fwd(const float* xin, const float* haux, const float* w
   return WNB_OK;
 }
 
+// standalone CausalConv1d forward (wavenet.py:95-121) on channels-last tensors, fp32 FFMA:
+//   out[b][t][o] = bias[o] + sum_j sum_c w[o][j*Cin + c] * x[b][t - (ks-1-j)*dilation][c]   (zero for t < 0)
+WNB_API int wnb_causal_conv1d_fwd(const float* x, const float* w, const float* bias, float* out, int B, int T, int Cin,
+                                  int Cout, int ks, int dilation, void* stream) {
+  WNB_REQUIRE(B > 0 && T > 0 && Cin > 0 && Cout > 0 && ks >= 1 && ks <= 4 && dilation >= 1, "causal_conv1d_fwd: bad shape");
+  WNB_REQUIRE(x && w && out, "causal_conv1d_fwd: null pointer");
+  NtParams p{};
+  p.nseg = ks;
+  for (int j = 0; j < ks; j++) p.seg[j] = NtSeg{w + (size_t)j * Cin, ks * Cin, x, Cin, -(ks - 1 - j) * dilation, Cin};
+  p.M = Cout; p.T = T; p.B = B; p.bias = bias; p.c = out; p.ldc = Cout;
+  return launch_nt(p, (cudaStream_t)stream);
+}
+
 WNB_API int wnb_resblock_fwd_supported(int R, int S, int Ap, int ks, int math_mode) {
   if (R <= 0 || S <= 0 || Ap <= 0 || ks < 1) return 0;
   if (math_mode == WNB_MATH_TF32)   // 1 = fused kernel, 2 = composed tcgen05 path (needs the zsave scratch)

@@ -281,9 +281,23 @@ class CausalConv1d(nn.Module):
                               padding=padding, dilation=dilation, bias=bias)
 
     def forward(self, x):
-        raise NotImplementedError(
-            "CausalConv1d is a parameter container in the B200 build; the convolution runs inside "
-            "WaveNet's fused residual-block kernel")
+        """FORWARD CALCULATION (reference wavenet.py:108-121): x (B, C, T) -> (B, C_out, T), inference only.
+
+        Inside ``WaveNet`` the convolution runs in the fused block kernels; this standalone form exists for API
+        compatibility and goes through ``wnb_causal_conv1d_fwd`` (no autograd)."""
+        if torch.is_grad_enabled() and (x.requires_grad or self.conv.weight.requires_grad):
+            x = x.detach()   # forward only: gradients flow through WaveNet.forward, not through this helper
+        lib = _lib.load()
+        if not x.is_cuda:
+            raise _lib.WnbError("CausalConv1d.forward needs CUDA tensors: the B200 build has no CPU fallback")
+        B, C, T = x.shape
+        xl = x.detach().float().transpose(1, 2).contiguous()                                   # (B, T, C)
+        w = self.conv.weight.detach().float().permute(0, 2, 1).reshape(self.out_channels, -1).contiguous()  # [o][j*C+c]
+        b = None if self.conv.bias is None else self.conv.bias.detach().float().contiguous()
+        out = torch.empty(B, T, self.out_channels, device=x.device, dtype=torch.float32)
+        check(lib.wnb_causal_conv1d_fwd(ptr(xl), ptr(w), ptr(b), ptr(out), B, T, C, self.out_channels,
+                                        self.kernel_size, self.dilation, stream()), "causal_conv1d_fwd")
+        return out.transpose(1, 2)
 
 
 class UpSampling(nn.Module):

@@ -281,3 +281,17 @@ def test_decode_arctic_shape_all_kernels():
         gm = gm.cpu().numpy()
         assert np.array_equal(gm, np.repeat(gm[:1], Bm, axis=0)), Bm
         assert np.array_equal(gm[0, :6], outs[order.index(0)][:6]), Bm
+
+
+def test_causal_conv1d_standalone():
+    """CausalConv1d.forward (reference wavenet.py:95-121) vs the oracle's causal_conv."""
+    from pytorchwavenetvocoder_b200.nets import CausalConv1d
+    torch.manual_seed(0)
+    for cin, cout, ks, d in ((5, 7, 2, 1), (32, 16, 3, 4), (64, 64, 2, 16)):
+        m = CausalConv1d(cin, cout, ks, d).cuda()
+        x = torch.randn(2, cin, 70).cuda()
+        y = m(x)
+        assert tuple(y.shape) == (2, cout, 70)
+        ref = O.causal_conv(x.cpu().numpy().astype(np.float64), m.conv.weight.detach().cpu().numpy().astype(np.float64),
+                            m.conv.bias.detach().cpu().numpy().astype(np.float64), d)
+        np.testing.assert_allclose(y.cpu().numpy(), ref, atol=1e-5, rtol=0)
