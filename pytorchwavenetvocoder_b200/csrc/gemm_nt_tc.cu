@@ -8,6 +8,7 @@
 // Used for: the post network forward (wavenet.py:518-523) and backward, the residual-stream data
 // gradient dX (two time-shifted segments) and the aux gradient dhaux (reduce-add).
 #include <cuda.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -20,7 +21,8 @@ namespace nt {
 constexpr int kTM = 128;
 constexpr int kASub = kTM * 32 * 4;      // 16 KB
 constexpr int kStg = 32 * 32 * 4;        // 4 KB
-constexpr int kThreadsN = 192;
+constexpr int kEpiWarpsN = 8;            // two per SM sub-partition: (TMEM lane quarter) x (alternate 32-column chunks)
+constexpr int kThreadsN = 32 * (2 + kEpiWarpsN);
 constexpr int kMaxSeg = 4;
 
 struct Seg { int amap; int shift; int K; int bmap; int b_k0; int b_n0; int b_n1; };  // b_n1 >= 0: rows of the 2nd half of N
@@ -43,13 +45,29 @@ struct alignas(64) Params {
 
 // barrier layout in smem: full[nstages] empty[nstages] dfull[2] dempty[2]
 
+// Tuning aid (WNB_PROF=1): cycles each role spends blocked, summed over CTAs.
+enum { NP_P_EMPTY = 0, NP_M_DEMPTY, NP_M_FULL, NP_M_TOTAL, NP_E_DFULL, NP_E_BULK, NP_E_TOTAL, NP_MIN, NP_MAX, NP_COUNT };
+__device__ unsigned long long g_nt_prof[NP_COUNT];
+
+template <bool PROF>
 __global__ void __launch_bounds__(kThreadsN, 1) gemm_nt_tc_kernel(const __grid_constant__ Params p) {
+  long long acc[NP_COUNT] = {};
+  auto wait = [&](uint64_t* bar, uint32_t parity, int k) {
+    if constexpr (PROF) {
+      const long long t = clock64();
+      ptx::mbar_wait(bar, parity);
+      acc[k] += clock64() - t;
+    } else {
+      ptx::mbar_wait(bar, parity);
+    }
+  };
+  const long long t_begin = PROF ? clock64() : 0;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int N = p.N;
   const int stage_bytes = kASub + N * 128;
   unsigned char* stg_base = smem + (size_t)p.nstages * stage_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(stg_base + 4 * 2 * kStg);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stg_base + kEpiWarpsN * 2 * kStg);
   uint64_t* full = bars;
   uint64_t* empty = bars + p.nstages;
   uint64_t* dfull = bars + 2 * p.nstages;
@@ -68,7 +86,7 @@ __global__ void __launch_bounds__(kThreadsN, 1) gemm_nt_tc_kernel(const __grid_c
     }
     for (int i = 0; i < 2; i++) {
       ptx::mbar_init(&dfull[i], 1);
-      ptx::mbar_init(&dempty[i], 128);
+      ptx::mbar_init(&dempty[i], 32 * kEpiWarpsN);
     }
     ptx::fence_barrier_init();
   }
@@ -76,19 +94,21 @@ __global__ void __launch_bounds__(kThreadsN, 1) gemm_nt_tc_kernel(const __grid_c
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
+  ptx::tmem_base_must_be_zero(*tmem_slot);
+  constexpr uint32_t tmem = 0;
 
+  // single-thread roles are entered through elect.sync (not `lane == 0`): the compiler then knows exactly one
+  // thread is active and issues the uniform-datapath TMA / tcgen05 instructions without a per-thread ELECT loop
   if (warp == 0) {
-    if (lane == 0) {
+    if (ptx::elect_one()) {
       for (int i = 0; i < 10; i++) ptx::prefetch_tmap(&p.maps[i]);
-      uint32_t g = 0;
+      uint32_t st = 0, ph = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int b = tile / tiles_per_b, t0 = (tile - b * tiles_per_b) * kTM;
         for (int s = 0; s < p.nseg; s++) {
           const Seg sg = p.seg[s];
-          for (int kc = 0; kc < sg.K / 32; kc++, g++) {
-            const int st = g % p.nstages;
-            ptx::mbar_wait(&empty[st], ((g / p.nstages) & 1) ^ 1);
+          for (int kc = 0; kc < sg.K / 32; kc++) {
+            wait(&empty[st], ph ^ 1, NP_P_EMPTY);
             ptx::mbar_arrive_expect_tx(&full[st], stage_bytes);
             unsigned char* dst = smem + (size_t)st * stage_bytes;
             ptx::tma_load_3d(dst, &p.maps[sg.amap], &full[st], kc * 32, t0 + sg.shift, b);
@@ -99,40 +119,47 @@ __global__ void __launch_bounds__(kThreadsN, 1) gemm_nt_tc_kernel(const __grid_c
               for (int n0 = 0; n0 < N; n0 += 256)
                 ptx::tma_load_2d(dst + kASub + n0 * 128, &p.maps[sg.bmap], &full[st], sg.b_k0 + kc * 32, sg.b_n0 + n0);
             }
+            if (++st == (uint32_t)p.nstages) { st = 0; ph ^= 1; }
           }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (ptx::elect_one()) {
       const int nmma = N > 256 ? 256 : N;
       const uint32_t idesc = ptx::idesc_tf32(128, nmma);
-      uint32_t g = 0, it = 0;
+      const uint32_t s_lo0 = ptx::desc_lo(ptx::smem_u32(smem), 16);
+      constexpr uint32_t hi = ptx::kDescHiKSw128;
+      const uint32_t stage_step = (uint32_t)stage_bytes >> 4;
+      uint32_t st = 0, ph = 0, it = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
         const uint32_t buf = (p.nacc == 2) ? (it & 1) : 0;
         const uint32_t use = (p.nacc == 2) ? (it >> 1) : it;
-        ptx::mbar_wait(&dempty[buf], (use & 1) ^ 1);
+        wait(&dempty[buf], (use & 1) ^ 1, NP_M_DEMPTY);
         ptx::tc_fence_after();
         const uint32_t dcol = buf * N;
-        for (int kc = 0; kc < kchunks; kc++, g++) {
-          const int st = g % p.nstages;
-          ptx::mbar_wait(&full[st], (g / p.nstages) & 1);
+        for (int kc = 0; kc < kchunks; kc++) {
+          wait(&full[st], ph, NP_M_FULL);
           ptx::tc_fence_after();
-          const uint32_t sa = ptx::smem_u32(smem + (size_t)st * stage_bytes);
-          const uint32_t sb = sa + kASub;
+          const uint32_t a_lo = s_lo0 + st * stage_step, b_lo = a_lo + (kASub >> 4);
 #pragma unroll
           for (int k = 0; k < 4; k++) {
-            for (int n0 = 0; n0 < N; n0 += 256)
-              ptx::mma_tf32_ss(tmem + dcol + n0, ptx::smem_desc_k_sw128(sa + k * 32),
-                               ptx::smem_desc_k_sw128(sb + n0 * 128 + k * 32), idesc, (kc | k) != 0);
+            ptx::mma_tf32_ss(tmem + dcol, ptx::desc64(a_lo + 2 * k, hi), ptx::desc64(b_lo + 2 * k, hi), idesc,
+                             (kc | k) != 0);
+            if (N > 256)
+              ptx::mma_tf32_ss(tmem + dcol + 256, ptx::desc64(a_lo + 2 * k, hi),
+                               ptx::desc64(b_lo + (256 * 128 >> 4) + 2 * k, hi), idesc, (kc | k) != 0);
           }
           ptx::tc_commit(&empty[st]);
+          if (++st == (uint32_t)p.nstages) { st = 0; ph ^= 1; }
         }
         ptx::tc_commit(&dfull[buf]);
       }
+      if constexpr (PROF) acc[NP_M_TOTAL] = clock64() - t_begin;
     }
   } else {
-    const int q = warp & 3;
+    const int q = warp & 3;                 // TMEM lane quarter (hardware restriction: warp id % 4)
+    const int hf = (warp - 2) >> 2;         // 0 / 1: this warp takes 32-column chunks hf, hf + 2, ...
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     unsigned char* stg = stg_base + (warp - 2) * 2 * kStg;
     uint32_t it = 0, nstore = 0;
@@ -143,11 +170,11 @@ __global__ void __launch_bounds__(kThreadsN, 1) gemm_nt_tc_kernel(const __grid_c
       const size_t grow = (size_t)b * p.T + (row_ok ? t : 0);
       const uint32_t buf = (p.nacc == 2) ? (it & 1) : 0;
       const uint32_t use = (p.nacc == 2) ? (it >> 1) : it;
-      ptx::mbar_wait(&dfull[buf], use & 1);
+      wait(&dfull[buf], use & 1, NP_E_DFULL);
       ptx::tc_fence_after();
       if (p.gate_mode) {
         // ---- gate epilogues: pair sigmoid column c with tanh column 64 + c ----
-        for (int c0 = 0; c0 < 64; c0 += 32) {
+        for (int c0 = hf * 32; c0 < 64; c0 += 64) {
           float a[32], g[32];
           {
             float lo[16], hi[16];
@@ -162,10 +189,8 @@ __global__ void __launch_bounds__(kThreadsN, 1) gemm_nt_tc_kernel(const __grid_c
 #pragma unroll
             for (int i = 0; i < 16; i++) { g[i] = lo[i]; g[16 + i] = hi[i]; }
           }
-          if (c0 == 32) {
-            ptx::tc_fence_before();
-            ptx::mbar_arrive(&dempty[buf]);
-          }
+          ptx::tc_fence_before();
+          ptx::mbar_arrive(&dempty[buf]);   // this warp's share of the accumulator is in registers
           float dzv[32];
           if (p.gate_mode == 1) {
             // forward: z only
@@ -175,8 +200,12 @@ __global__ void __launch_bounds__(kThreadsN, 1) gemm_nt_tc_kernel(const __grid_c
               dzv[i] = sg * ptx::tanh_approx(g[i] + __ldg(p.bias2 + c0 + i));
             }
             unsigned char* sb = stg + (nstore & 1) * kStg;
-            if (lane == 0) ptx::bulk_wait_read<1>();
-            __syncwarp();
+            {
+              const long long tb = PROF ? clock64() : 0;
+              if (lane == 0) ptx::bulk_wait_read<1>();
+              __syncwarp();
+              if constexpr (PROF) acc[NP_E_BULK] += clock64() - tb;
+            }
             float4* dstrow = reinterpret_cast<float4*>(sb + lane * 128);
 #pragma unroll
             for (int j = 0; j < 8; j++)
@@ -214,8 +243,12 @@ __global__ void __launch_bounds__(kThreadsN, 1) gemm_nt_tc_kernel(const __grid_c
           for (int which = 0; which < 3; which++) {
             const float* src = which == 0 ? dzv : (which == 1 ? a : g);
             unsigned char* sb = stg + (nstore & 1) * kStg;
-            if (lane == 0) ptx::bulk_wait_read<1>();
-            __syncwarp();
+            {
+              const long long tb = PROF ? clock64() : 0;
+              if (lane == 0) ptx::bulk_wait_read<1>();
+              __syncwarp();
+              if constexpr (PROF) acc[NP_E_BULK] += clock64() - tb;
+            }
             float4* dstrow = reinterpret_cast<float4*>(sb + lane * 128);
 #pragma unroll
             for (int j = 0; j < 8; j++)
@@ -232,7 +265,11 @@ __global__ void __launch_bounds__(kThreadsN, 1) gemm_nt_tc_kernel(const __grid_c
         }
         continue;
       }
-      for (int c0 = 0; c0 < N; c0 += 32) {
+      if (hf * 32 >= N) {  // N == 32: the second warp of the pair has no chunk
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(&dempty[buf]);
+      }
+      for (int c0 = hf * 32; c0 < N; c0 += 64) {
         float v[32];
         {
           float lo[16], hi[16];
@@ -242,7 +279,7 @@ __global__ void __launch_bounds__(kThreadsN, 1) gemm_nt_tc_kernel(const __grid_c
 #pragma unroll
           for (int i = 0; i < 16; i++) { v[i] = lo[i]; v[16 + i] = hi[i]; }
         }
-        if (c0 + 32 >= N) {  // last chunk in registers: the accumulator can be overwritten
+        if (c0 + 64 >= N) {  // this warp's last chunk is in registers: the accumulator can be overwritten
           ptx::tc_fence_before();
           ptx::mbar_arrive(&dempty[buf]);
         }
@@ -273,8 +310,12 @@ __global__ void __launch_bounds__(kThreadsN, 1) gemm_nt_tc_kernel(const __grid_c
           }
         }
         unsigned char* sb = stg + (nstore & 1) * kStg;
-        if (lane == 0) ptx::bulk_wait_read<1>();
-        __syncwarp();
+        {
+          const long long tb = PROF ? clock64() : 0;
+          if (lane == 0) ptx::bulk_wait_read<1>();
+          __syncwarp();
+          if constexpr (PROF) acc[NP_E_BULK] += clock64() - tb;
+        }
         float4* dstrow = reinterpret_cast<float4*>(sb + lane * 128);
 #pragma unroll
         for (int j = 0; j < 8; j++)
@@ -291,6 +332,18 @@ __global__ void __launch_bounds__(kThreadsN, 1) gemm_nt_tc_kernel(const __grid_c
       }
     }
     if (lane == 0) ptx::bulk_wait<0>();
+    if constexpr (PROF) {
+      if (warp == 2 && lane == 0) {
+        acc[NP_E_TOTAL] = clock64() - t_begin;
+        atomicMin(&g_nt_prof[NP_MIN], (unsigned long long)acc[NP_E_TOTAL]);
+        atomicMax(&g_nt_prof[NP_MAX], (unsigned long long)acc[NP_E_TOTAL]);
+      }
+    }
+  }
+  if constexpr (PROF) {
+    if (warp <= 1 || (warp == 2 && lane == 0))   // single-thread roles: only the elected lane has counts
+      for (int k = 0; k < NP_MIN; k++)
+        if (acc[k]) atomicAdd(&g_nt_prof[k], (unsigned long long)acc[k]);
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -398,16 +451,17 @@ int gemm_nt_tc(const NtTcSeg* segs, int nseg, int N, float* out, int ld_out, con
   p.relu_out = relu_out; p.accumulate = accumulate;
   p.nacc = N <= 256 ? 2 : 1;
   const int stage_bytes = kASub + N * 128;
-  int nst = (int)((227 * 1024 - 1024 - 512 - 4 * 2 * kStg) / stage_bytes);
+  int nst = (int)((227 * 1024 - 1024 - 512 - kEpiWarpsN * 2 * kStg) / stage_bytes);
   static int max_stages = 0;
   if (!max_stages) { const char* e = getenv("WNB_NT_MAXSTAGES"); max_stages = e ? atoi(e) : 4; if (max_stages < 2) max_stages = 2; }
   if (nst > max_stages) nst = max_stages;
   if (nst < 2) { set_error("gemm_nt_tc: N too large"); return WNB_ERR_INVALID; }
   p.nstages = nst;
-  const size_t smem = (size_t)nst * stage_bytes + 4 * 2 * kStg + 512 + 1024;
+  const size_t smem = (size_t)nst * stage_bytes + kEpiWarpsN * 2 * kStg + 512 + 1024;
   static size_t configured = 0;
   if (smem > configured) {
-    WNB_CUDA(cudaFuncSetAttribute(gemm_nt_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    WNB_CUDA(cudaFuncSetAttribute(gemm_nt_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    WNB_CUDA(cudaFuncSetAttribute(gemm_nt_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
   static int sms = 0;
@@ -418,7 +472,25 @@ int gemm_nt_tc(const NtTcSeg* segs, int nseg, int N, float* out, int ld_out, con
   }
   const int ntiles = B * ((T + kTM - 1) / kTM);
   const int grid = ntiles < sms ? ntiles : sms;
-  gemm_nt_tc_kernel<<<grid, kThreadsN, smem, st>>>(p);
+  static int prof = -1;
+  if (prof < 0) { const char* e = getenv("WNB_PROF"); prof = (e && e[0] == '1') ? 1 : 0; }
+  if (prof) {
+    unsigned long long zero[NP_COUNT] = {}, h[NP_COUNT];
+    zero[NP_MIN] = ~0ull;
+    WNB_CUDA(cudaMemcpyToSymbol(g_nt_prof, zero, sizeof(zero)));
+    gemm_nt_tc_kernel<true><<<grid, kThreadsN, smem, st>>>(p);
+    WNB_CHECK_LAUNCH("gemm_nt_tc");
+    WNB_CUDA(cudaStreamSynchronize(st));
+    WNB_CUDA(cudaMemcpyFromSymbol(h, g_nt_prof, sizeof(h)));
+    int kc = 0;
+    for (int i = 0; i < nseg; i++) kc += segs[i].K / 32;
+    fprintf(stderr, "wnb200 nt prof N=%d kchunks=%d gate=%d stages=%d (kcycles/CTA): P:empty=%.1f M:dempty=%.1f M:full=%.1f "
+            "M:total=%.1f E:dfull=%.1f E:bulk=%.1f E:total=%.1f cta min=%.1f max=%.1f\n", N, kc, p.gate_mode, nst,
+            h[0] / 1e3 / grid, h[1] / 1e3 / grid, h[2] / 1e3 / grid, h[3] / 1e3 / grid, h[4] / 1e3 / grid,
+            h[5] / 1e3 / grid, h[6] / 1e3 / grid, h[7] / 1e3, h[8] / 1e3);
+    return WNB_OK;
+  }
+  gemm_nt_tc_kernel<false><<<grid, kThreadsN, smem, st>>>(p);
   WNB_CHECK_LAUNCH("gemm_nt_tc");
   return WNB_OK;
 }

@@ -4,21 +4,27 @@
 //
 // Per 128-sample time tile (M = 128 rows = time, channels-last activations are K-major operands):
 //   GEMM-1  D1[128 x 128] = [x(t-d) | x(t) | aux(t)] [128 x 160] * W1^T          (tcgen05.mma kind::tf32, SS)
-//           A tiles arrive by TMA (zero fill for t-d < 0 = the causal left padding), W1 stays resident.
+//           A tiles arrive by TMA (zero fill for t-d < 0 = the causal left padding); W1 k-chunks and
+//           W2 row-chunks stream from L2 through one 7-deep TMA ring (prefetched across tile boundaries).
 //   gate    z = sigmoid(D1[:, :64] + b) * tanh(D1[:, 64:] + b)   TMEM -> registers -> TMEM (never smem/HBM)
 //   GEMM-2  D2[128 x 64] = z[128 x 64] * W2_chunk^T for the res chunk and S/64 skip chunks
-//           (A operand straight from TMEM, W2 chunks streamed through a 2-deep TMA ring from L2)
+//           (A operand straight from TMEM, B operand = the ring slot)
 //   out     xout = D2 + b2 + x(t) (x re-used from the A stage in smem) -> swizzled staging -> TMA store
 //           skip += D2 + b2                                            -> staging -> TMA reduce-add (.add.f32)
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane), warps 2-5 =
-// epilogue (each owns the 32 TMEM lanes / time rows of its quarter and its own staging + bulk groups, so
-// the epilogue warps never synchronise with each other).  All hand-offs are mbarriers; every wait is
+// Warp roles (352 threads): warp 0 = TMA producer for the activation tiles, warp 2 = TMA producer for the
+// weights (two independent producers: the next tile's A stage is requested as soon as the epilogue frees it,
+// not after the current tile's W2 chunks), warp 1 = MMA issuer (one elected lane), warps 3-10 =
+// epilogue: two per SM sub-partition, each owning (32 TMEM lanes / time rows) x (32 of the 64 columns of a
+// chunk) with its own staging box + bulk group, so the epilogue warps never synchronise with each other.  All hand-offs are mbarriers; every wait is
 // bounded (trap instead of hang).  fp32 storage in HBM, tf32 multiplies, fp32 accumulate.
 //
-// Shared memory (1 CTA / SM): W1 80 KB | A stage 80 KB | W2 ring 2 x 16 KB | staging 4 x 2 x 4 KB.
-// TMEM: D1 128 cols | z 64 | D2 ping-pong 2 x 64  (512 allocated).
+// Shared memory (1 CTA / SM): weight ring 7 x 16 KB | A stage 80 KB | staging 8 x 4 KB.
+// TMEM: D1 128 cols | z 64 | D2 4 x 64  (512 allocated).
 #include <cuda.h>
+
+#include <cstdio>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "tc_ptx.cuh"
@@ -42,22 +48,41 @@ constexpr int kNSubA = kK1 / 32;         // 5
 constexpr int kW2SubBytes = 64 * 32 * 4;
 constexpr int kW2StageBytes = 2 * kW2SubBytes;
 constexpr int kStgBytes = 32 * 32 * 4;   // one [32 rows x 32 fp32] staging box
-constexpr int kOffW1 = 0;
-constexpr int kOffA = kOffW1 + kNSubA * kSubBytes;
-constexpr int kOffW2 = kOffA + kNSubA * kSubBytes;
-constexpr int kOffStg = kOffW2 + 2 * kW2StageBytes;
-constexpr int kOffBar = kOffStg + 4 * 2 * kStgBytes;
+constexpr int kEpiWarps = 8;     // two per SM sub-partition: (TMEM lane quarter) x (column half)
+constexpr int kEpiThreads = 32 * kEpiWarps;
+constexpr int kNSlot = 7;                // weight ring depth: W1 k-chunks and W2 row-chunks, 16 KB each
+constexpr int kSlotBytes = kSubBytes;
+static_assert(kW2StageBytes == kSlotBytes, "W1 and W2 chunks share the ring slots");
+constexpr int kND2 = 4;                  // D2 accumulator buffers in TMEM
+constexpr int kOffRing = 0;
+constexpr int kOffA = kOffRing + kNSlot * kSlotBytes;
+constexpr int kOffStg = kOffA + kNSubA * kSubBytes;
+constexpr int kOffBar = kOffStg + kEpiWarps * kStgBytes;
 constexpr int kSmemBytes = kOffBar + 256 + 1024;  // + alignment slack
-constexpr int kThreadsTc = 192;
+constexpr int kThreadsTc = 32 * (3 + kEpiWarps);  // warp 0 A-tile producer, 1 MMA issuer, 2 weight producer, 3.. epilogue
 constexpr uint32_t kColD1 = 0, kColZ = 128, kColD2 = 192;
 
 struct alignas(64) Maps {
   CUtensorMap x, haux, w1, w2, xout, skip;
 };
 
-enum { B_W1 = 0, B_AFULL, B_AEMPTY, B_W2F0, B_W2F1, B_W2E0, B_W2E1, B_D1F, B_D1E, B_ZF, B_D2F0, B_D2F1, B_D2E0,
-       B_D2E1, B_COUNT };
+enum { B_AFULL = 0, B_AEMPTY, B_D1F, B_D1E, B_ZF, B_WF0, B_WE0 = B_WF0 + kNSlot, B_D2F0 = B_WE0 + kNSlot,
+       B_D2E0 = B_D2F0 + kND2, B_TILE0 = B_D2E0 + kND2, B_COUNT = B_TILE0 + 2 };
+static_assert(8 * B_COUNT + 16 <= 256, "barrier block");
+static_assert(kColD2 + kND2 * 64 <= 512, "TMEM columns");
 
+// Tuning aid (WNB_FWD_PROF=1): cycles each role spends blocked on each hand-off, summed over CTAs.
+enum { P_A_AEMPTY = 0, P_W_W2E, P_M_AFULL, P_M_D1E, P_M_ZF, P_M_W2F, P_M_D2E, P_M_TOTAL, P_E_D1F, P_E_D2F, P_E_BULK,
+       P_E_GATE, P_E_TOTAL, P_E_MIN, P_E_MAX, P_COUNT };
+__device__ unsigned long long g_fwd_prof[P_COUNT];
+
+// Dynamic tile scheduler: CTA c starts on tile c and then takes tiles from this counter, so SMs that get a
+// smaller share of the memory system simply process fewer tiles (with a static stride the slowest SM set the
+// kernel time: ncu showed SMs active for only 80 % of the elapsed cycles).  The last CTA to finish resets both
+// counters; launches of this kernel must therefore be stream-ordered (they are: one stream per process).
+__device__ unsigned int g_tile_next, g_cta_done;
+
+template <bool PROF>
 __global__ void __launch_bounds__(kThreadsTc, 1)
 resblock_fwd_tc_kernel(const __grid_constant__ Maps maps, const float* __restrict__ b1, const float* __restrict__ b2,
                        int B, int T, int S, int d, int has_xout, int skip_init) {
@@ -65,43 +90,58 @@ resblock_fwd_tc_kernel(const __grid_constant__ Maps maps, const float* __restric
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffBar + 8 * B_COUNT);
+  volatile int* tile_ring = reinterpret_cast<volatile int*>(smem + kOffBar + 8 * B_COUNT + 8);  // 2 entries
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_per_b = (T + kTM - 1) / kTM;
   const int ntiles = B * tiles_per_b;
   const int nchunks = (has_xout ? 1 : 0) + S / 64;
   const int row0 = has_xout ? 0 : kR;  // first W2 row of chunk 0
+  long long acc[P_COUNT] = {};
+  auto wait = [&](uint64_t* bar, uint32_t parity, int k) {
+    if constexpr (PROF) {
+      const long long t = clock64();
+      ptx::mbar_wait(bar, parity);
+      acc[k] += clock64() - t;
+    } else {
+      ptx::mbar_wait(bar, parity);
+    }
+  };
+  const long long t_begin = PROF ? clock64() : 0;
 
   if (threadIdx.x == 0) {
-    ptx::mbar_init(&bars[B_W1], 1);
     ptx::mbar_init(&bars[B_AFULL], 1);
-    ptx::mbar_init(&bars[B_AEMPTY], 128);
-    ptx::mbar_init(&bars[B_W2F0], 1); ptx::mbar_init(&bars[B_W2F1], 1);
-    ptx::mbar_init(&bars[B_W2E0], 1); ptx::mbar_init(&bars[B_W2E1], 1);
+    ptx::mbar_init(&bars[B_AEMPTY], kEpiThreads);
+    for (int i = 0; i < kNSlot; i++) { ptx::mbar_init(&bars[B_WF0 + i], 1); ptx::mbar_init(&bars[B_WE0 + i], 1); }
     ptx::mbar_init(&bars[B_D1F], 1);
-    ptx::mbar_init(&bars[B_D1E], 128);
-    ptx::mbar_init(&bars[B_ZF], 128);
-    ptx::mbar_init(&bars[B_D2F0], 1); ptx::mbar_init(&bars[B_D2F1], 1);
-    ptx::mbar_init(&bars[B_D2E0], 128); ptx::mbar_init(&bars[B_D2E1], 128);
+    ptx::mbar_init(&bars[B_D1E], kEpiThreads);
+    ptx::mbar_init(&bars[B_ZF], kEpiThreads);
+    for (int i = 0; i < kND2; i++) { ptx::mbar_init(&bars[B_D2F0 + i], 1); ptx::mbar_init(&bars[B_D2E0 + i], kEpiThreads); }
+    ptx::mbar_init(&bars[B_TILE0], 1); ptx::mbar_init(&bars[B_TILE0 + 1], 1);
     ptx::fence_barrier_init();
   }
   if (warp == 1) ptx::tmem_alloc<512>(tmem_slot);
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
+  ptx::tmem_base_must_be_zero(*tmem_slot);
+  constexpr uint32_t tmem = 0;
 
+  // (single-thread roles are entered through elect.sync, not `lane == 0`: the compiler then knows exactly one thread
+  //  is active and issues the uniform-datapath TMA / tcgen05 instructions without a per-thread ELECT loop)
   if (warp == 0) {
-    // =============================== TMA producer ===============================
-    if (lane == 0) {
-      ptx::prefetch_tmap(&maps.x); ptx::prefetch_tmap(&maps.haux); ptx::prefetch_tmap(&maps.w1);
-      ptx::prefetch_tmap(&maps.w2);
-      ptx::mbar_arrive_expect_tx(&bars[B_W1], kNSubA * kSubBytes);
-      for (int j = 0; j < kNSubA; j++) ptx::tma_load_2d(smem + kOffW1 + j * kSubBytes, &maps.w1, &bars[B_W1], j * 32, 0);
-      uint32_t it = 0, gchunk = 0;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
+    // =============================== TMA producer: activation tiles ===============================
+    // (its own warp, so that the next tile's A stage is requested the moment the epilogue releases it instead of
+    //  queueing behind the W2 chunk stream of the current tile)
+    if (ptx::elect_one()) {
+      ptx::prefetch_tmap(&maps.x); ptx::prefetch_tmap(&maps.haux);
+      int tile = blockIdx.x;
+      for (uint32_t it = 0;; it++) {
+        tile_ring[it & 1] = tile;                  // publish the tile (or the stop mark) to the other roles
+        ptx::mbar_arrive(&bars[B_TILE0 + (it & 1)]);
+        if (tile < 0) break;
         const int b = tile / tiles_per_b, t0 = (tile - b * tiles_per_b) * kTM;
-        ptx::mbar_wait(&bars[B_AEMPTY], (it & 1) ^ 1);
+        wait(&bars[B_AEMPTY], (it & 1) ^ 1, P_A_AEMPTY);
         ptx::mbar_arrive_expect_tx(&bars[B_AFULL], kNSubA * kSubBytes);
         unsigned char* sA = smem + kOffA;
         ptx::tma_load_3d(sA + 0 * kSubBytes, &maps.x, &bars[B_AFULL], 0, t0 - d, b);
@@ -109,78 +149,126 @@ resblock_fwd_tc_kernel(const __grid_constant__ Maps maps, const float* __restric
         ptx::tma_load_3d(sA + 2 * kSubBytes, &maps.x, &bars[B_AFULL], 0, t0, b);
         ptx::tma_load_3d(sA + 3 * kSubBytes, &maps.x, &bars[B_AFULL], 32, t0, b);
         ptx::tma_load_3d(sA + 4 * kSubBytes, &maps.haux, &bars[B_AFULL], 0, t0, b);
-        for (int c = 0; c < nchunks; c++, gchunk++) {
-          const uint32_t s = gchunk & 1;
-          ptx::mbar_wait(&bars[B_W2E0 + s], ((gchunk >> 1) & 1) ^ 1);
-          ptx::mbar_arrive_expect_tx(&bars[B_W2F0 + s], kW2StageBytes);
-          unsigned char* dst = smem + kOffW2 + s * kW2StageBytes;
-          ptx::tma_load_2d(dst, &maps.w2, &bars[B_W2F0 + s], 0, row0 + c * 64);
-          ptx::tma_load_2d(dst + kW2SubBytes, &maps.w2, &bars[B_W2F0 + s], 32, row0 + c * 64);
+        tile = (int)(atomicAdd(&g_tile_next, 1u) + gridDim.x);
+        if (tile >= ntiles) tile = -1;
+      }
+    }
+  } else if (warp == 2) {
+    // =============================== TMA producer: weight ring ===============================
+    // Every tile streams W1 (5 k-chunks of [128 x 32]) and then W2 (row chunks of [64 x 64]) from L2 through one
+    // kNSlot-deep ring, so up to 112 KB of weights are in flight / prefetched across tile boundaries and the
+    // MMA warp does not see the L2 latency (it did with W1 resident and only a 2-deep W2 ring).
+    if (ptx::elect_one()) {
+      ptx::prefetch_tmap(&maps.w1); ptx::prefetch_tmap(&maps.w2);
+      uint32_t slot = 0, ph = 0;
+      for (uint32_t it = 0;; it++) {
+        ptx::mbar_wait(&bars[B_TILE0 + (it & 1)], (it >> 1) & 1);
+        if (tile_ring[it & 1] < 0) break;
+        for (int c = 0; c < kNSubA + nchunks; c++) {
+          wait(&bars[B_WE0 + slot], ph ^ 1, P_W_W2E);
+          ptx::mbar_arrive_expect_tx(&bars[B_WF0 + slot], kSlotBytes);
+          unsigned char* dst = smem + kOffRing + slot * kSlotBytes;
+          if (c < kNSubA) {
+            ptx::tma_load_2d(dst, &maps.w1, &bars[B_WF0 + slot], c * 32, 0);
+          } else {
+            const int r = row0 + (c - kNSubA) * 64;
+            ptx::tma_load_2d(dst, &maps.w2, &bars[B_WF0 + slot], 0, r);
+            ptx::tma_load_2d(dst + kW2SubBytes, &maps.w2, &bars[B_WF0 + slot], 32, r);
+          }
+          if (++slot == kNSlot) { slot = 0; ph ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // =============================== MMA issuer ===============================
-    if (lane == 0) {
+    if (ptx::elect_one()) {
       constexpr uint32_t idesc1 = ptx::idesc_tf32(128, 128);
       constexpr uint32_t idesc2 = ptx::idesc_tf32(128, 64);
-      const uint32_t sA = ptx::smem_u32(smem + kOffA), sW1 = ptx::smem_u32(smem + kOffW1),
-                     sW2 = ptx::smem_u32(smem + kOffW2);
-      ptx::mbar_wait(&bars[B_W1], 0);
-      uint32_t it = 0, gchunk = 0;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
-        ptx::mbar_wait(&bars[B_AFULL], it & 1);
-        ptx::mbar_wait(&bars[B_D1E], (it & 1) ^ 1);
+      const uint32_t a_lo0 = ptx::desc_lo(ptx::smem_u32(smem + kOffA), 16);
+      const uint32_t w_lo0 = ptx::desc_lo(ptx::smem_u32(smem + kOffRing), 16);
+      constexpr uint32_t hi = ptx::kDescHiKSw128;
+      uint32_t gchunk = 0, slot = 0, wph = 0;
+      for (uint32_t it = 0;; it++) {
+        ptx::mbar_wait(&bars[B_TILE0 + (it & 1)], (it >> 1) & 1);
+        if (tile_ring[it & 1] < 0) break;
+        wait(&bars[B_AFULL], it & 1, P_M_AFULL);
+        wait(&bars[B_D1E], (it & 1) ^ 1, P_M_D1E);
         ptx::tc_fence_after();
-#pragma unroll
-        for (int j = 0; j < kNSubA; j++)
+#pragma unroll 1
+        for (int j = 0; j < kNSubA; j++) {
+          wait(&bars[B_WF0 + slot], wph, P_M_W2F);
+          ptx::tc_fence_after();
+          const uint32_t w_lo = w_lo0 + slot * (kSlotBytes >> 4), a_lo = a_lo0 + j * (kSubBytes >> 4);
 #pragma unroll
           for (int k = 0; k < 4; k++)
-            ptx::mma_tf32_ss(tmem + kColD1, ptx::smem_desc_k_sw128(sA + j * kSubBytes + k * 32),
-                             ptx::smem_desc_k_sw128(sW1 + j * kSubBytes + k * 32), idesc1, (j | k) != 0);
+            ptx::mma_tf32_ss(tmem + kColD1, ptx::desc64(a_lo + 2 * k, hi), ptx::desc64(w_lo + 2 * k, hi), idesc1,
+                             (j | k) != 0);
+          ptx::tc_commit(&bars[B_WE0 + slot]);
+          if (++slot == kNSlot) { slot = 0; wph ^= 1; }
+        }
         ptx::tc_commit(&bars[B_D1F]);
-        ptx::mbar_wait(&bars[B_ZF], it & 1);
+        wait(&bars[B_ZF], it & 1, P_M_ZF);
         ptx::tc_fence_after();
         for (int c = 0; c < nchunks; c++, gchunk++) {
-          const uint32_t s = gchunk & 1, ph = (gchunk >> 1) & 1;
-          ptx::mbar_wait(&bars[B_W2F0 + s], ph);
-          ptx::mbar_wait(&bars[B_D2E0 + s], ph ^ 1);
+          const uint32_t s = gchunk % kND2, ph = (gchunk / kND2) & 1;
+          wait(&bars[B_WF0 + slot], wph, P_M_W2F);
+          wait(&bars[B_D2E0 + s], ph ^ 1, P_M_D2E);
           ptx::tc_fence_after();
+          const uint32_t w_lo = w_lo0 + slot * (kSlotBytes >> 4);
 #pragma unroll
           for (int kk = 0; kk < 2; kk++)
 #pragma unroll
             for (int k = 0; k < 4; k++)
               ptx::mma_tf32_ts(tmem + kColD2 + s * 64, tmem + kColZ + kk * 32 + k * 8,
-                               ptx::smem_desc_k_sw128(sW2 + s * kW2StageBytes + kk * kW2SubBytes + k * 32), idesc2,
-                               (kk | k) != 0);
-          ptx::tc_commit(&bars[B_W2E0 + s]);
+                               ptx::desc64(w_lo + kk * (kW2SubBytes >> 4) + 2 * k, hi), idesc2, (kk | k) != 0);
+          ptx::tc_commit(&bars[B_WE0 + slot]);
           ptx::tc_commit(&bars[B_D2F0 + s]);
+          if (++slot == kNSlot) { slot = 0; wph ^= 1; }
         }
       }
+      if constexpr (PROF) acc[P_M_TOTAL] = clock64() - t_begin;
     }
   } else {
-    // =============================== epilogue warps ===============================
+    // =============================== epilogue warps (3..10) ===============================
+    // Warp e = warp - 3 owns TMEM lane quarter (warp & 3) -- the hardware restriction -- and column half (e >> 2):
+    // two epilogue warps per SM sub-partition, so TMEM-load / bias / fence / bulk-wait latencies of one overlap
+    // the arithmetic of the other.  Each warp has one 4 KB staging box and its own bulk-async group.
     const int q = warp & 3;                         // TMEM lane quarter this warp may access
+    const int hf = (warp - 3) >> 2;                 // which 32 of the 64 columns of every chunk
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     const int row = q * 32 + lane;                  // time row inside the tile
-    unsigned char* stg = smem + kOffStg + (warp - 2) * 2 * kStgBytes;
-    const unsigned char* sX = smem + kOffA + 2 * kSubBytes;  // x(t) sub-tiles (channels 0-31, 32-63)
-    uint32_t it = 0, gchunk = 0, nstore = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
+    unsigned char* sb = smem + kOffStg + (warp - 3) * kStgBytes;
+    const uint32_t sb_row = ptx::smem_u32(sb + lane * 128);
+    const unsigned char* sX = smem + kOffA + (2 + hf) * kSubBytes;  // x(t) sub-tile holding this warp's channels
+    const float4* b1v = reinterpret_cast<const float4*>(b1);
+    uint32_t gchunk = 0;
+    for (uint32_t it = 0;; it++) {
+      ptx::mbar_wait(&bars[B_TILE0 + (it & 1)], (it >> 1) & 1);
+      const int tile = tile_ring[it & 1];
+      if (tile < 0) break;
       const int b = tile / tiles_per_b, t0 = (tile - b * tiles_per_b) * kTM;
-      ptx::mbar_wait(&bars[B_D1F], it & 1);
+      wait(&bars[B_D1F], it & 1, P_E_D1F);
+      const long long t_gate = PROF ? clock64() : 0;
       ptx::tc_fence_after();
       // ---- gate: z = sigmoid(a) * tanh(g), 16 channels at a time, TMEM -> regs -> TMEM ----
 #pragma unroll
-      for (int g = 0; g < 4; g++) {
+      for (int gg = 0; gg < 2; gg++) {
+        const int g = hf * 2 + gg;
         float a[16], t[16], z[16];
         ptx::tmem_ld16(tmem + lane_base + kColD1 + g * 16, a);
         ptx::tmem_ld16(tmem + lane_base + kColD1 + 64 + g * 16, t);
+        float4 ba[4], bt[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) { ba[i] = __ldg(b1v + g * 4 + i); bt[i] = __ldg(b1v + 16 + g * 4 + i); }
         ptx::tc_wait_ld();
 #pragma unroll
-        for (int i = 0; i < 16; i++) {
-          const float av = a[i] + __ldg(b1 + g * 16 + i), tv = t[i] + __ldg(b1 + 64 + g * 16 + i);
-          z[i] = (0.5f * ptx::tanh_approx(0.5f * av) + 0.5f) * ptx::tanh_approx(tv);
+        for (int i = 0; i < 4; i++) {
+          const float bav[4] = {ba[i].x, ba[i].y, ba[i].z, ba[i].w}, btv[4] = {bt[i].x, bt[i].y, bt[i].z, bt[i].w};
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            const float av = a[4 * i + k] + bav[k], tv = t[4 * i + k] + btv[k];
+            z[4 * i + k] = (0.5f * ptx::tanh_approx(0.5f * av) + 0.5f) * ptx::tanh_approx(tv);
+          }
         }
         ptx::tmem_st16(tmem + lane_base + kColZ + g * 16, z);
       }
@@ -188,66 +276,86 @@ resblock_fwd_tc_kernel(const __grid_constant__ Maps maps, const float* __restric
       ptx::tc_fence_before();
       ptx::mbar_arrive(&bars[B_ZF]);
       ptx::mbar_arrive(&bars[B_D1E]);
+      if constexpr (PROF) acc[P_E_GATE] += clock64() - t_gate;
       if (!has_xout) ptx::mbar_arrive(&bars[B_AEMPTY]);  // last block: nothing else reads the A stage
       // ---- res / skip chunks ----
       for (int c = 0; c < nchunks; c++, gchunk++) {
-        const uint32_t s = gchunk & 1, ph = (gchunk >> 1) & 1;
+        const uint32_t s = gchunk % kND2, ph = (gchunk / kND2) & 1;
         const bool is_res = has_xout && c == 0;
         const int col0 = is_res ? 0 : (c - (has_xout ? 1 : 0)) * 64;  // channel offset inside xout / skip
-        const float* bias = b2 + (is_res ? 0 : kR + col0);
-        ptx::mbar_wait(&bars[B_D2F0 + s], ph);
+        const float4* bias = reinterpret_cast<const float4*>(b2 + (is_res ? 0 : kR + col0) + hf * 32);
+        float4 bv[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) bv[j] = __ldg(bias + j);
+        wait(&bars[B_D2F0 + s], ph, P_E_D2F);
         ptx::tc_fence_after();
+        float v[32];
+        {
+          float lo[16], hi[16];
+          ptx::tmem_ld16(tmem + lane_base + kColD2 + s * 64 + hf * 32, lo);
+          ptx::tmem_ld16(tmem + lane_base + kColD2 + s * 64 + hf * 32 + 16, hi);
+          ptx::tc_wait_ld();
 #pragma unroll
-        for (int half = 0; half < 2; half++) {
-          float v[32];
-          {
-            float lo[16], hi[16];
-            ptx::tmem_ld16(tmem + lane_base + kColD2 + s * 64 + half * 32, lo);
-            ptx::tmem_ld16(tmem + lane_base + kColD2 + s * 64 + half * 32 + 16, hi);
-            ptx::tc_wait_ld();
+          for (int i = 0; i < 16; i++) { v[i] = lo[i]; v[16 + i] = hi[i]; }
+        }
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(&bars[B_D2E0 + s]);   // this warp's part of the D2 buffer is in registers
 #pragma unroll
-            for (int i = 0; i < 16; i++) { v[i] = lo[i]; v[16 + i] = hi[i]; }
+        for (int j = 0; j < 8; j++) {
+          v[4 * j] += bv[j].x; v[4 * j + 1] += bv[j].y; v[4 * j + 2] += bv[j].z; v[4 * j + 3] += bv[j].w;
+        }
+        if (is_res) {
+          const float4* xr = reinterpret_cast<const float4*>(sX + row * 128);
+#pragma unroll
+          for (int j = 0; j < 8; j++) {
+            const float4 xv = xr[j ^ (row & 7)];
+            v[4 * j] += xv.x; v[4 * j + 1] += xv.y; v[4 * j + 2] += xv.z; v[4 * j + 3] += xv.w;
           }
-          if (half == 1) {  // both halves of this D2 buffer are in registers: hand it back to the MMA warp
-            ptx::tc_fence_before();
-            ptx::mbar_arrive(&bars[B_D2E0 + s]);
-          }
-#pragma unroll
-          for (int i = 0; i < 32; i++) v[i] += __ldg(bias + half * 32 + i);
-          if (is_res) {
-            const float4* xr = reinterpret_cast<const float4*>(sX + half * kSubBytes + row * 128);
-#pragma unroll
-            for (int j = 0; j < 8; j++) {
-              const float4 xv = xr[j ^ (row & 7)];
-              v[4 * j] += xv.x; v[4 * j + 1] += xv.y; v[4 * j + 2] += xv.z; v[4 * j + 3] += xv.w;
-            }
-            if (half == 1) ptx::mbar_arrive(&bars[B_AEMPTY]);  // x(t) consumed: the A stage may be refilled
-          }
-          unsigned char* sb = stg + (nstore & 1) * kStgBytes;
-          if (lane == 0) ptx::bulk_wait_read<1>();  // the store that used this staging buffer has drained
+          ptx::mbar_arrive(&bars[B_AEMPTY]);  // x(t) consumed: the A stage may be refilled
+        }
+        {
+          const long long t = PROF ? clock64() : 0;
+          if (lane == 0) ptx::bulk_wait_read<0>();  // the previous store out of this staging box has drained
           __syncwarp();
-          float4* dstrow = reinterpret_cast<float4*>(sb + lane * 128);
+          if constexpr (PROF) acc[P_E_BULK] += clock64() - t;
+        }
 #pragma unroll
-          for (int j = 0; j < 8; j++)
-            dstrow[j ^ (lane & 7)] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-          ptx::fence_proxy_async();
-          __syncwarp();
-          if (lane == 0) {
-            const int tc = t0 + q * 32;
-            if (is_res) ptx::tma_store_3d(&maps.xout, sb, half * 32, tc, b);
-            else if (skip_init) ptx::tma_store_3d(&maps.skip, sb, col0 + half * 32, tc, b);
-            else ptx::tma_reduce_add_3d(&maps.skip, sb, col0 + half * 32, tc, b);
-            ptx::bulk_commit();
-          }
-          nstore++;
+        for (int j = 0; j < 8; j++)
+          ptx::st_shared_v4(sb_row + ((j ^ (lane & 7)) << 4), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        ptx::fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          const int tc = t0 + q * 32;
+          if (is_res) ptx::tma_store_3d(&maps.xout, sb, hf * 32, tc, b);
+          else if (skip_init) ptx::tma_store_3d(&maps.skip, sb, col0 + hf * 32, tc, b);
+          else ptx::tma_reduce_add_3d(&maps.skip, sb, col0 + hf * 32, tc, b);
+          ptx::bulk_commit();
         }
       }
     }
     if (lane == 0) ptx::bulk_wait<0>();
   }
+  if constexpr (PROF) {
+    if (warp <= 2 || (warp == 3 && lane == 0)) {   // single-thread roles: only the elected lane has counts
+      if (warp == 3) {
+        acc[P_E_TOTAL] = clock64() - t_begin;
+        atomicMin(&g_fwd_prof[P_E_MIN], (unsigned long long)acc[P_E_TOTAL]);
+        atomicMax(&g_fwd_prof[P_E_MAX], (unsigned long long)acc[P_E_TOTAL]);
+      }
+      for (int k = 0; k < P_E_MIN; k++)
+        if (acc[k]) atomicAdd(&g_fwd_prof[k], (unsigned long long)acc[k]);
+    }
+  }
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 1) ptx::tmem_dealloc<512>(tmem);
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(&g_cta_done, 1u) == gridDim.x - 1) {  // last CTA out: re-arm the scheduler for the next launch
+      g_tile_next = 0;
+      g_cta_done = 0;
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -298,6 +406,10 @@ int resblock_fwd_tc(const FwdParams& p, cudaStream_t st) {
     set_error("resblock_fwd_tc: zsave is not supported on the tcgen05 path");
     return WNB_ERR_UNSUPPORTED;
   }
+  if ((reinterpret_cast<uintptr_t>(p.b1) | reinterpret_cast<uintptr_t>(p.b2)) & 15) {
+    set_error("resblock_fwd_tc: b1 / b2 must be 16-byte aligned");
+    return WNB_ERR_INVALID;
+  }
   Maps maps;
   const uint64_t dx[3] = {(uint64_t)kR, (uint64_t)p.T, (uint64_t)p.B};
   const uint64_t dh[3] = {(uint64_t)kAp, (uint64_t)p.T, (uint64_t)p.B};
@@ -313,8 +425,14 @@ int resblock_fwd_tc(const FwdParams& p, cudaStream_t st) {
     return WNB_ERR_CUDA;
   }
   static bool configured = false;
+  static bool prof = false;
   if (!configured) {
-    WNB_CUDA(cudaFuncSetAttribute(resblock_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    const char* e = getenv("WNB_FWD_PROF");
+    prof = e && e[0] == '1';
+    WNB_CUDA(cudaFuncSetAttribute(resblock_fwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  kSmemBytes));
+    WNB_CUDA(cudaFuncSetAttribute(resblock_fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  kSmemBytes));
     configured = true;
   }
   static int sms = 0;
@@ -325,8 +443,24 @@ int resblock_fwd_tc(const FwdParams& p, cudaStream_t st) {
   }
   const int ntiles = p.B * ((p.T + kTM - 1) / kTM);
   const int grid = ntiles < sms ? ntiles : sms;
-  resblock_fwd_tc_kernel<<<grid, kThreadsTc, kSmemBytes, st>>>(maps, p.b1, p.b2, p.B, p.T, p.S, p.d, p.xout ? 1 : 0,
-                                                             p.skip_init);
+  if (prof) {  // tuning aid: synchronous, prints where each role of the pipeline waited
+    unsigned long long zero[P_COUNT] = {}, h[P_COUNT];
+    zero[P_E_MIN] = ~0ull;
+    WNB_CUDA(cudaMemcpyToSymbol(g_fwd_prof, zero, sizeof(zero)));
+    resblock_fwd_tc_kernel<true><<<grid, kThreadsTc, kSmemBytes, st>>>(maps, p.b1, p.b2, p.B, p.T, p.S, p.d,
+                                                                     p.xout ? 1 : 0, p.skip_init);
+    WNB_CHECK_LAUNCH("resblock_fwd_tc");
+    WNB_CUDA(cudaStreamSynchronize(st));
+    WNB_CUDA(cudaMemcpyFromSymbol(h, g_fwd_prof, sizeof(h)));
+    static const char* names[P_COUNT] = {"A:aempty", "W:w2e", "M:afull", "M:d1e", "M:zf", "M:w2f", "M:d2e", "M:total",
+                                         "E:d1f", "E:d2f", "E:bulk", "E:gate", "E:total", "E:min", "E:max"};
+    fprintf(stderr, "wnb200 fwd prof d=%d tiles/cta=%.2f (kcycles per CTA):", p.d, (double)ntiles / grid);
+    for (int k = 0; k < P_COUNT; k++) fprintf(stderr, " %s=%.1f", names[k], h[k] / 1e3 / (k >= P_E_MIN ? 1 : grid));
+    fprintf(stderr, "\n");
+    return WNB_OK;
+  }
+  resblock_fwd_tc_kernel<false><<<grid, kThreadsTc, kSmemBytes, st>>>(maps, p.b1, p.b2, p.B, p.T, p.S, p.d,
+                                                                    p.xout ? 1 : 0, p.skip_init);
   WNB_CHECK_LAUNCH("resblock_fwd_tc");
   return WNB_OK;
 }

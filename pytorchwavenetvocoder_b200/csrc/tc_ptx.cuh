@@ -86,6 +86,9 @@ __device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* m, const vo
                : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
 template <int N>
 __device__ __forceinline__ void bulk_wait_read() {
   asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
@@ -120,6 +123,26 @@ __device__ __forceinline__ void tc_commit(uint64_t* bar) {
 // K-major, 128B-swizzled operand tile: rows at 128 B pitch, 8-row groups 1024 B apart (SBO), LBO unused (=1)
 __device__ __forceinline__ uint64_t smem_desc_k_sw128(uint32_t saddr) {
   return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// Descriptor halves.  The low word carries the 16-byte-granular start address (bits 0-13) and LBO (bits 16-29), so
+// stepping through a tile is ONE integer add on the low word (no carry: shared memory addresses are < 256 KB);
+// the high word (SBO, version, swizzle mode) is a constant.  Keeping both in warp-uniform registers matters: the
+// MMA issuer is a single thread, and every extra instruction per tcgen05.mma lowers the issue rate.
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo_bytes) {
+  return ((saddr >> 4) & 0x3FFF) | ((lbo_bytes >> 4) << 16);
+}
+constexpr uint32_t kDescHiKSw128 = 64u | (1u << 14) | (2u << 29);      // SBO 1024 B, SWIZZLE_128B (K-major)
+constexpr uint32_t kDescHiMnSw128B32 = 32u | (1u << 14) | (1u << 29);  // SBO 512 B, SWIZZLE_128B_BASE32B (MN-major)
+__device__ __forceinline__ uint64_t desc64(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; }
+// Every kernel here allocates all 512 TMEM columns of its SM (1 CTA / SM), so the allocation starts at column 0,
+// lane 0.  Checking that once lets TMEM addresses be compile-time constants instead of values read back from
+// shared memory (which the compiler must treat as per-thread and move to uniform registers with an ELECT loop
+// in front of every tcgen05.mma).
+__device__ __forceinline__ void tmem_base_must_be_zero(uint32_t t) {
+  if (t != 0) {
+    printf("wnb200: unexpected TMEM base %u (block %d)\n", t, blockIdx.x);
+    __trap();
+  }
 }
 // tf32 x tf32 -> f32, both operands K-major
 __host__ __device__ constexpr uint32_t idesc_tf32(int M, int N) {

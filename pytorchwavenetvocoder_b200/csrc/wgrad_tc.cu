@@ -13,6 +13,7 @@
 // out of range by TMA.  An optional extra all-ones B group turns column 0 of that group into the bias
 // gradient sum_t A[t][m] (replaces colsum_kernel).
 #include <cuda.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -37,6 +38,7 @@ struct alignas(64) Params {
   float* db[kMaxMB];             // per block (128) or null
   int T, B, tiles_per_b, ntiles, nstages;
   int tk;                        // time rows per stage (K of one stage): 64, 32 or 16
+  int vec4;                      // C blocks are 16-byte aligned with ldc % 4 == 0: flush with red.v4
 };
 
 __device__ __forceinline__ uint64_t smem_desc_mn_sw128(uint32_t saddr, uint32_t lbo_bytes) {
@@ -52,7 +54,23 @@ __host__ __device__ constexpr uint32_t idesc_tf32_mn(int M, int N) {
          ((uint32_t)(M >> 4) << 24);
 }
 
+// Tuning aid (WNB_PROF=1): cycles each role spends blocked, summed over CTAs (see tools/fwd_prof.py).
+enum { WP_P_EMPTY = 0, WP_M_FULL, WP_M_TOTAL, WP_E_FLUSH, WP_MIN, WP_MAX, WP_COUNT };
+__device__ unsigned long long g_wg_prof[WP_COUNT];
+
+template <bool PROF>
 __global__ void __launch_bounds__(kThreadsW, 1) wgrad_tc_kernel(const __grid_constant__ Params p) {
+  long long acc[WP_COUNT] = {};
+  auto wait = [&](uint64_t* bar, uint32_t parity, int k) {
+    if constexpr (PROF) {
+      const long long t = clock64();
+      ptx::mbar_wait(bar, parity);
+      acc[k] += clock64() - t;
+    } else {
+      ptx::mbar_wait(bar, parity);
+    }
+  };
+  const long long t_begin = PROF ? clock64() : 0;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int nsubB = p.nB + (p.use_ones ? 1 : 0);
@@ -93,41 +111,52 @@ __global__ void __launch_bounds__(kThreadsW, 1) wgrad_tc_kernel(const __grid_con
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
+  ptx::tmem_base_must_be_zero(*tmem_slot);
+  constexpr uint32_t tmem = 0;
 
+  // single-thread roles are entered through elect.sync (not `lane == 0`): the compiler then knows exactly one
+  // thread is active and issues the uniform-datapath TMA / tcgen05 instructions without a per-thread ELECT loop
   if (warp == 0) {
-    if (lane == 0 && my_tiles > 0) {
+    if (my_tiles > 0 && ptx::elect_one()) {
       for (int i = 0; i < kMaxMaps; i++) ptx::prefetch_tmap(&p.maps[i]);
-      uint32_t it = 0;
-      for (int tile = tile_begin; tile < tile_end; tile++, it++) {
+      uint32_t s = 0, ph = 0;
+      for (int tile = tile_begin; tile < tile_end; tile++) {
         const int b = tile / p.tiles_per_b, t0 = (tile - b * p.tiles_per_b) * p.tk;
-        const int s = it % p.nstages;
-        ptx::mbar_wait(&empty[s], ((it / p.nstages) & 1) ^ 1);
+        wait(&empty[s], ph ^ 1, WP_P_EMPTY);
         ptx::mbar_arrive_expect_tx(&full[s], (nA + p.nB) * kSubBytes);
         unsigned char* st = smem + (size_t)s * stage_bytes;
         for (int g = 0; g < nA; g++)
           ptx::tma_load_3d(st + g * kSubBytes, &p.maps[p.a[g].map], &full[s], p.a[g].c0, t0 + p.a[g].shift, b);
         for (int g = 0; g < p.nB; g++)
           ptx::tma_load_3d(st + (nA + g) * kSubBytes, &p.maps[p.b[g].map], &full[s], p.b[g].c0, t0 + p.b[g].shift, b);
+        if (++s == (uint32_t)p.nstages) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && my_tiles > 0) {
+    if (my_tiles > 0 && ptx::elect_one()) {
       const uint32_t idesc = idesc_tf32_mn(128, N);
-      uint32_t it = 0;
+      // MN-major tf32 operands have exactly one legal swizzled layout, SWIZZLE_128B_BASE32B (see tc_ptx.cuh): MN
+      // groups are LBO = one sub-tile apart, 4-row k-groups 512 B apart, one MMA K-step (8 rows) = 1024 B.
+      const uint32_t s_lo0 = ptx::desc_lo(ptx::smem_u32(smem), kSubBytes);
+      constexpr uint32_t hi = ptx::kDescHiMnSw128B32;
+      const uint32_t stage_step = (uint32_t)stage_bytes >> 4, sub_step = (uint32_t)kSubBytes >> 4;
+      const int ksteps = p.tk / 8;
+      uint32_t s = 0, ph = 0, it = 0;
       for (int tile = tile_begin; tile < tile_end; tile++, it++) {
-        const int s = it % p.nstages;
-        ptx::mbar_wait(&full[s], (it / p.nstages) & 1);
+        wait(&full[s], ph, WP_M_FULL);
         ptx::tc_fence_after();
-        const uint32_t sa = ptx::smem_u32(smem + (size_t)s * stage_bytes);
-        const uint32_t sb = sa + nA * kSubBytes;
-        for (int mb = 0; mb < p.nMB; mb++)
-          for (int k = 0; k < p.tk / 8; k++)
-            ptx::mma_tf32_ss(tmem + mb * N, smem_desc_mn_sw128(sa + mb * 4 * kSubBytes + k * 1024, kSubBytes),
-                             smem_desc_mn_sw128(sb + k * 1024, kSubBytes), idesc, (it | k) != 0);
+        const uint32_t a_lo = s_lo0 + s * stage_step, b_lo = a_lo + nA * sub_step;
+        for (int mb = 0; mb < p.nMB; mb++) {
+          const uint32_t am_lo = a_lo + mb * 4 * sub_step;
+          for (int k = 0; k < ksteps; k++)
+            ptx::mma_tf32_ss(tmem + mb * N, ptx::desc64(am_lo + k * 64, hi), ptx::desc64(b_lo + k * 64, hi), idesc,
+                             (it | k) != 0);
+        }
         ptx::tc_commit(&empty[s]);
+        if (++s == (uint32_t)p.nstages) { s = 0; ph ^= 1; }
       }
       ptx::tc_commit(done);
+      if constexpr (PROF) acc[WP_M_TOTAL] = clock64() - t_begin;
     }
   } else if (my_tiles > 0) {
     // epilogue: flush the accumulator once
@@ -135,6 +164,7 @@ __global__ void __launch_bounds__(kThreadsW, 1) wgrad_tc_kernel(const __grid_con
     const int row = q * 32 + lane;
     ptx::mbar_wait(done, 0);
     ptx::tc_fence_after();
+    const long long t_flush = PROF ? clock64() : 0;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     const int nchunk = N / 16;
     for (int mb = 0; mb < p.nMB; mb++) {
@@ -147,14 +177,36 @@ __global__ void __launch_bounds__(kThreadsW, 1) wgrad_tc_kernel(const __grid_con
         if (row < p.m_valid[mb]) {
           if (c0 < 32 * p.nB) {
             float* dst = p.c[mb] + (size_t)row * p.ldc + c0;
+            if (p.vec4) {   // 16-byte vector reductions: a quarter of the L2 atomic operations
 #pragma unroll
-            for (int i = 0; i < 16; i++) atomicAdd(dst + i, v[i]);
+              for (int i = 0; i < 16; i += 4)
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + i), "f"(v[i]), "f"(v[i + 1]),
+                             "f"(v[i + 2]), "f"(v[i + 3])
+                             : "memory");
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; i++) atomicAdd(dst + i, v[i]);
+            }
           } else if (c0 == 32 * p.nB && p.db[mb]) {
             atomicAdd(p.db[mb] + row, v[0]);
           }
         }
       }
     }
+    if constexpr (PROF) {
+      if (warp == 2) {
+        acc[WP_E_FLUSH] = clock64() - t_flush;
+        if (lane == 0) {
+          atomicMin(&g_wg_prof[WP_MIN], (unsigned long long)(clock64() - t_begin));
+          atomicMax(&g_wg_prof[WP_MAX], (unsigned long long)(clock64() - t_begin));
+        }
+      }
+    }
+  }
+  if constexpr (PROF) {
+    if (warp <= 1 || (warp == 2 && lane == 0))   // single-thread roles: only the elected lane has counts
+      for (int k = 0; k < WP_MIN; k++)
+        if (acc[k]) atomicAdd(&g_wg_prof[k], (unsigned long long)acc[k]);
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -259,13 +311,17 @@ int wgrad_tc_blocks(const WgBlock* blocks, int nblocks, const WgOperand* b_ops, 
   }
   for (int i = nmaps; i < kMaxMaps; i++) p.maps[i] = p.maps[0];
   p.ldc = ldc;
+  p.vec4 = (ldc % 4 == 0) ? 1 : 0;
+  for (int i = 0; i < nblocks; i++)
+    if (reinterpret_cast<uintptr_t>(blocks[i].c) & 15) p.vec4 = 0;
   p.T = T; p.B = B;
   p.tiles_per_b = (T + tk - 1) / tk;
   p.ntiles = B * p.tiles_per_b;
   const size_t smem = (size_t)nst * stage_bytes + 1024 + 256;
   static size_t configured = 0;
   if (smem > configured) {
-    WNB_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    WNB_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    WNB_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
   static int sms = 0;
@@ -275,7 +331,22 @@ int wgrad_tc_blocks(const WgBlock* blocks, int nblocks, const WgOperand* b_ops, 
     WNB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   }
   const int grid = p.ntiles < sms ? p.ntiles : sms;
-  wgrad_tc_kernel<<<grid, kThreadsW, smem, st>>>(p);
+  static int prof = -1;
+  if (prof < 0) { const char* e = getenv("WNB_PROF"); prof = (e && e[0] == '1') ? 1 : 0; }
+  if (prof) {
+    unsigned long long zero[WP_COUNT] = {}, h[WP_COUNT];
+    zero[WP_MIN] = ~0ull;
+    WNB_CUDA(cudaMemcpyToSymbol(g_wg_prof, zero, sizeof(zero)));
+    wgrad_tc_kernel<true><<<grid, kThreadsW, smem, st>>>(p);
+    WNB_CHECK_LAUNCH("wgrad_tc");
+    WNB_CUDA(cudaStreamSynchronize(st));
+    WNB_CUDA(cudaMemcpyFromSymbol(h, g_wg_prof, sizeof(h)));
+    fprintf(stderr, "wnb200 wgrad prof nMB=%d nB=%d tk=%d stages=%d stage=%dKB (kcycles/CTA): P:empty=%.1f M:full=%.1f "
+            "M:total=%.1f E:flush=%.1f cta min=%.1f max=%.1f\n", p.nMB, p.nB, p.tk, p.nstages, stage_bytes / 1024,
+            h[0] / 1e3 / grid, h[1] / 1e3 / grid, h[2] / 1e3 / grid, h[3] / 1e3 / grid, h[4] / 1e3, h[5] / 1e3);
+    return WNB_OK;
+  }
+  wgrad_tc_kernel<false><<<grid, kThreadsW, smem, st>>>(p);
   WNB_CHECK_LAUNCH("wgrad_tc");
   return WNB_OK;
 }
