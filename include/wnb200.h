@@ -99,6 +99,45 @@ WNB_API int wnb_resblock_fwd_supported(int R, int S, int Ap, int ks, int math_mo
 WNB_API int wnb_causal_conv1d_fwd(const float* x, const float* w, const float* bias, float* out, int B, int T,
                                   int Cin, int Cout, int ks, int dilation, void* stream);
 
+/* ---- residual stack in deferred-skip form (training path of WaveNet.forward, wavenet.py:229-236 over :525-536) ----
+ * The skip sum over all L blocks is one GEMM over the concatenated gate outputs,
+ *     skip = [z_0 | ... | z_{L-1}] Wskip^T + bskip,   Wskip[s][l*R+c] = skip_1x1_l.weight[s][c],  bskip = sum_l skip bias_l
+ * so a block only writes z_l into Z_all (B,T,L*R) and its residual output (no read-modify-write of skip per block),
+ * and the backward hoists dZ_all = dskip Wskip and dWskip = dskip^T Z_all out of the block loop the same way.
+ * WNB_MATH_TF32 only; wnb_stack_supported() says whether the shape is covered (else use the per-block entries). */
+WNB_API int wnb_stack_supported(int R, int S, int Ap, int ks, int L, int math_mode);
+
+/* one block: xout (B,T,R) = xin + res_1x1(z) (NULL for the last block), z -> zall[:, :, zcol0:zcol0+R] (row pitch ldz).
+ * w1 (2R,K1), b1 (2R) as for wnb_resblock_fwd; w2res (R,R) = res_1x1.weight[o][c], b2res (R). */
+WNB_API int wnb_resblock_fwd_z(const float* xin, const float* haux, const float* w1, const float* b1,
+                               const float* w2res, const float* b2res, float* xout, float* zall, int ldz, int zcol0,
+                               int B, int T, int R, int Ap, int ks, int dilation, void* stream);
+
+/* skip (B,T,S) = zall (B,T,K) wskip^T + bskip;  wskip (S,K) row-major, bskip (S) or NULL */
+WNB_API int wnb_skip_gemm(const float* zall, const float* wskip, const float* bskip, float* skip, int B, int T,
+                          int K, int S, void* stream);
+
+/* whole stack: xs (nxs,B,T,R) holds the block inputs, xs[0] filled by the caller (wnb_front_embed_fwd); block l reads
+ * xs[l % nxs] and writes xs[(l+1) % nxs] (nxs = L keeps every input for the backward, nxs = 2 ping-pongs).
+ * w1 (L,2R,K1), b1 (L,2R), w2res (L,R,R), b2res (L,R), wskip (S,L*R), bskip (S); dilations: L host ints.
+ * Outputs zall (B,T,L*R) and skip (B,T,S). */
+WNB_API int wnb_stack_fwd(float* xs, int nxs, const float* haux, const float* w1, const float* b1,
+                          const float* w2res, const float* b2res, const float* wskip, const float* bskip,
+                          float* zall, float* skip, const int* dilations, int L, int B, int T, int R, int S,
+                          int Ap, int ks, void* stream);
+
+/* backward of wnb_stack_fwd.  xs (L,B,T,R) and zall from the forward; dskip (B,T,S) = d loss / d skip.
+ * w1t (L,K1,2R) as for wnb_resblock_bwd, w2res_t (L,R,R) = w2res transposed ([c][o]), wskip_t (L*R,S) = wskip^T.
+ * dx0 (B,T,R) = gradient of xs[0]; dhaux (B,T,Ap) accumulated into (or NULL); dw1, db1, dw2res, db2res, dwskip
+ * (S,L*R), dbskip (S) are ACCUMULATED into (the last block's dw2res / db2res are left untouched: that conv has no
+ * gradient, like the reference).  workspace: wnb_stack_bwd_workspace() bytes. */
+WNB_API size_t wnb_stack_bwd_workspace(int L, int B, int T, int R, int S, int Ap, int ks);
+WNB_API int wnb_stack_bwd(const float* xs, const float* haux, const float* zall, const float* dskip, const float* w1,
+                          const float* b1, const float* w1t, const float* w2res_t, const float* wskip_t, float* dx0,
+                          float* dhaux, float* dw1, float* db1, float* dw2res, float* db2res, float* dwskip,
+                          float* dbskip, void* workspace, const int* dilations, int L, int B, int T, int R, int S,
+                          int Ap, int ks, void* stream);
+
 /* ---- a10 backward --------------------------------------------------------------------------
  * Recomputes the gate from xin/haux, then produces dxin and accumulates weight gradients.
  * dout = d(loss)/d(xout) (NULL for the last layer), dskip = d(loss)/d(skip_sum) (same for all layers).

@@ -38,6 +38,12 @@ SIGNATURES = {
     "wnb_resblock_fwd": (_I, [_P] * 9 + [_I] * 9 + [_P]),
     "wnb_resblock_fwd_supported": (_I, [_I] * 5),
     "wnb_causal_conv1d_fwd": (_I, [_P] * 4 + [_I] * 6 + [_P]),
+    "wnb_stack_supported": (_I, [_I] * 6),
+    "wnb_resblock_fwd_z": (_I, [_P] * 8 + [_I] * 8 + [_P]),
+    "wnb_skip_gemm": (_I, [_P] * 4 + [_I] * 4 + [_P]),
+    "wnb_stack_fwd": (_I, [_P, _I] + [_P] * 10 + [_I] * 7 + [_P]),
+    "wnb_stack_bwd_workspace": (_c.c_size_t, [_I] * 7),
+    "wnb_stack_bwd": (_I, [_P] * 19 + [_I] * 7 + [_P]),
     "wnb_resblock_bwd_workspace": (_c.c_size_t, [_I] * 6),
     "wnb_resblock_bwd": (_I, [_P] * 15 + [_I] * 8 + [_P]),
     "wnb_post_fwd": (_I, [_P] * 7 + [_I] * 5 + [_P]),

@@ -13,6 +13,7 @@
 #include <string.h>
 
 #include "common.cuh"
+#include "tc_host.h"
 #include "tc_ptx.cuh"
 
 namespace wnb {
@@ -41,6 +42,8 @@ struct alignas(64) Params {
   // split output: columns >= out2_col0 (> 0) are reduce-added into maps[9] at column c - out2_col0; bias / add /
   // mask / ReLU apply to the primary columns only
   int out2_col0;
+  // column blocks (NtTcOpts::n_blocks), dz row pitch and z suppression of the gate-backward epilogue
+  int nblk, gate_ld_dz, gate_skip_z;
 };
 
 // barrier layout in smem: full[nstages] empty[nstages] dfull[2] dempty[2]
@@ -75,7 +78,7 @@ __global__ void __launch_bounds__(kThreadsN, 1) gemm_nt_tc_kernel(const __grid_c
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dempty + 2);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_per_b = (p.T + kTM - 1) / kTM;
-  const int ntiles = p.B * tiles_per_b;
+  const int ntiles = p.B * tiles_per_b * p.nblk;   // column block fastest: the blocks of one time tile share A via L2
   int kchunks = 0;
   for (int s = 0; s < p.nseg; s++) kchunks += p.seg[s].K / 32;
 
@@ -104,7 +107,8 @@ __global__ void __launch_bounds__(kThreadsN, 1) gemm_nt_tc_kernel(const __grid_c
       for (int i = 0; i < 10; i++) ptx::prefetch_tmap(&p.maps[i]);
       uint32_t st = 0, ph = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int b = tile / tiles_per_b, t0 = (tile - b * tiles_per_b) * kTM;
+        const int tt = tile / p.nblk, ncol0 = (tile - tt * p.nblk) * N;
+        const int b = tt / tiles_per_b, t0 = (tt - b * tiles_per_b) * kTM;
         for (int s = 0; s < p.nseg; s++) {
           const Seg sg = p.seg[s];
           for (int kc = 0; kc < sg.K / 32; kc++) {
@@ -117,7 +121,7 @@ __global__ void __launch_bounds__(kThreadsN, 1) gemm_nt_tc_kernel(const __grid_c
               ptx::tma_load_2d(dst + kASub + (N / 2) * 128, &p.maps[sg.bmap], &full[st], sg.b_k0 + kc * 32, sg.b_n1);
             } else {
               for (int n0 = 0; n0 < N; n0 += 256)
-                ptx::tma_load_2d(dst + kASub + n0 * 128, &p.maps[sg.bmap], &full[st], sg.b_k0 + kc * 32, sg.b_n0 + n0);
+                ptx::tma_load_2d(dst + kASub + n0 * 128, &p.maps[sg.bmap], &full[st], sg.b_k0 + kc * 32, sg.b_n0 + ncol0 + n0);
             }
             if (++st == (uint32_t)p.nstages) { st = 0; ph ^= 1; }
           }
@@ -164,7 +168,8 @@ __global__ void __launch_bounds__(kThreadsN, 1) gemm_nt_tc_kernel(const __grid_c
     unsigned char* stg = stg_base + (warp - 2) * 2 * kStg;
     uint32_t it = 0, nstore = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
-      const int b = tile / tiles_per_b, t0 = (tile - b * tiles_per_b) * kTM;
+      const int tt = tile / p.nblk, ncol0 = (tile - tt * p.nblk) * N;
+      const int b = tt / tiles_per_b, t0 = (tt - b * tiles_per_b) * kTM;
       const int t = t0 + q * 32 + lane;
       const bool row_ok = t < p.T;
       const size_t grow = (size_t)b * p.T + (row_ok ? t : 0);
@@ -220,7 +225,7 @@ __global__ void __launch_bounds__(kThreadsN, 1) gemm_nt_tc_kernel(const __grid_c
             continue;
           }
           if (row_ok) {
-            const float4* dr = reinterpret_cast<const float4*>(p.gate_dz + grow * p.gate_R + p.gate_c0 + c0);
+            const float4* dr = reinterpret_cast<const float4*>(p.gate_dz + grow * p.gate_ld_dz + p.gate_c0 + c0);
 #pragma unroll
             for (int j = 0; j < 8; j++) {
               const float4 d4 = __ldg(dr + j);
@@ -240,7 +245,7 @@ __global__ void __launch_bounds__(kThreadsN, 1) gemm_nt_tc_kernel(const __grid_c
             dzv[i] = sg * th;                      // z
           }
 #pragma unroll
-          for (int which = 0; which < 3; which++) {
+          for (int which = p.gate_skip_z ? 1 : 0; which < 3; which++) {
             const float* src = which == 0 ? dzv : (which == 1 ? a : g);
             unsigned char* sb = stg + (nstore & 1) * kStg;
             {
@@ -286,10 +291,10 @@ __global__ void __launch_bounds__(kThreadsN, 1) gemm_nt_tc_kernel(const __grid_c
         const bool second = p.out2_col0 > 0 && c0 >= p.out2_col0;
         if (p.bias && !second) {
 #pragma unroll
-          for (int i = 0; i < 32; i++) v[i] += __ldg(p.bias + c0 + i);
+          for (int i = 0; i < 32; i++) v[i] += __ldg(p.bias + ncol0 + c0 + i);
         }
         if (p.add && row_ok && !second) {
-          const float4* ar = reinterpret_cast<const float4*>(p.add + grow * p.ldadd + c0);
+          const float4* ar = reinterpret_cast<const float4*>(p.add + grow * p.ldadd + ncol0 + c0);
 #pragma unroll
           for (int j = 0; j < 8; j++) {
             const float4 a = __ldg(ar + j);
@@ -301,7 +306,7 @@ __global__ void __launch_bounds__(kThreadsN, 1) gemm_nt_tc_kernel(const __grid_c
           for (int i = 0; i < 32; i++) v[i] = fmaxf(v[i], 0.f);
         }
         if (p.mask && row_ok && !second) {
-          const float4* mr = reinterpret_cast<const float4*>(p.mask + grow * p.ldmask + c0);
+          const float4* mr = reinterpret_cast<const float4*>(p.mask + grow * p.ldmask + ncol0 + c0);
 #pragma unroll
           for (int j = 0; j < 8; j++) {
             const float4 m = __ldg(mr + j);
@@ -324,8 +329,8 @@ __global__ void __launch_bounds__(kThreadsN, 1) gemm_nt_tc_kernel(const __grid_c
         __syncwarp();
         if (lane == 0) {
           if (second) ptx::tma_reduce_add_3d(&p.maps[9], sb, c0 - p.out2_col0, t0 + q * 32, b);
-          else if (p.accumulate) ptx::tma_reduce_add_3d(&p.maps[8], sb, c0, t0 + q * 32, b);
-          else ptx::tma_store_3d(&p.maps[8], sb, c0, t0 + q * 32, b);
+          else if (p.accumulate) ptx::tma_reduce_add_3d(&p.maps[8], sb, ncol0 + c0, t0 + q * 32, b);
+          else ptx::tma_store_3d(&p.maps[8], sb, ncol0 + c0, t0 + q * 32, b);
           ptx::bulk_commit();
         }
         nstore++;
@@ -387,16 +392,10 @@ static bool map2(CUtensorMap* m, const float* base, int K, int Nrows, int box_ro
 
 }  // namespace nt
 
-// One segment: activation tensor (B,T,CA) read at rows t+shift, channels [0,K); weight matrix w (rows x ldw,
-// K-contiguous) rows [n0, n0+N), columns [k0, k0+K).
-struct NtTcSeg { const float* a; int CA; int shift; int K; const float* w; int w_rows; int w_cols; int k0; int n0; };
-// gate epilogue request: mode 1 = forward (z out), 2 = backward (dz in, z + dpre out); channels c0..c0+63 of R
-struct NtTcGate { int mode; int c0; int R; const float* bias_sig; const float* bias_tanh; const float* dz; float* dpre; };
-
 int gemm_nt_tc(const NtTcSeg* segs, int nseg, int N, float* out, int ld_out, const float* bias, const float* mask,
                int ldmask, const float* add, int ldadd, int relu_out, int accumulate, int B, int T, cudaStream_t st,
-               const float* gate_dz = nullptr, float* gate_dpre = nullptr, float* out2 = nullptr, int ld_out2 = 0,
-               int out2_col0 = 0, const NtTcGate* gate = nullptr) {
+               const float* gate_dz, float* gate_dpre, float* out2, int ld_out2, int out2_col0, const NtTcGate* gate,
+               const NtTcOpts* opts) {
   using namespace nt;
   if (nseg < 1 || nseg > kMaxSeg || N % 32 != 0 || N < 32 || N > 512 || (N > 256 && N != 512) || ld_out % 4 != 0) {
     set_error("gemm_nt_tc: unsupported shape (nseg=%d N=%d)", nseg, N);
@@ -446,6 +445,13 @@ int gemm_nt_tc(const NtTcSeg* segs, int nseg, int N, float* out, int ld_out, con
     p.out2_col0 = out2_col0;
   }
   p.nseg = nseg; p.N = N; p.T = T; p.B = B;
+  p.nblk = (opts && opts->n_blocks > 1) ? opts->n_blocks : 1;
+  p.gate_ld_dz = (opts && opts->gate_ld_dz > 0) ? opts->gate_ld_dz : p.gate_R;
+  p.gate_skip_z = (opts && opts->gate_skip_z) ? 1 : 0;
+  if (p.nblk > 1 && (p.gate_mode || out2 || N > 256)) {
+    set_error("gemm_nt_tc: column blocks are for plain epilogues with N <= 256");
+    return WNB_ERR_INVALID;
+  }
   if (!p.gate_mode) p.bias = bias;   // (the gate modes have already installed their own bias pointers)
   p.mask = mask; p.ldmask = ldmask; p.add = add; p.ldadd = ldadd;
   p.relu_out = relu_out; p.accumulate = accumulate;
@@ -470,7 +476,7 @@ int gemm_nt_tc(const NtTcSeg* segs, int nseg, int N, float* out, int ld_out, con
     WNB_CUDA(cudaGetDevice(&dev));
     WNB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   }
-  const int ntiles = B * ((T + kTM - 1) / kTM);
+  const int ntiles = B * ((T + kTM - 1) / kTM) * p.nblk;
   const int grid = ntiles < sms ? ntiles : sms;
   static int prof = -1;
   if (prof < 0) { const char* e = getenv("WNB_PROF"); prof = (e && e[0] == '1') ? 1 : 0; }

@@ -13,6 +13,7 @@
 // All activations are channels-last (B,T,C).  Everything here is fp32 FFMA: this is the parity path and
 // the fallback for shapes the tcgen05 path (resblock_tc.cu) does not cover.
 #include "gemm_simt.cuh"
+#include "tc_host.h"
 
 namespace wnb {
 
@@ -347,22 +348,6 @@ static int pick_tchunk(int B, int T, int tiles) {
   if (chunk < 64) chunk = 64;
   return chunk;
 }
-
-// implemented in wgrad_tc.cu
-struct WgOperand { const float* base; int C; int c0; int groups; int shift; };
-struct WgBlock { WgOperand ops[2]; int nops; float* c; int m_valid; float* db; };
-int wgrad_tc_blocks(const WgBlock* blocks, int nblocks, const WgOperand* b_ops, int nb_ops, int ldc, int B, int T,
-                    cudaStream_t st);
-int wgrad_tc(const WgOperand* a_ops, int na_ops, const WgOperand* b_ops, int nb_ops, float* c, int ldc, int m_valid,
-             float* db, int B, int T, cudaStream_t st);
-
-// implemented in gemm_nt_tc.cu
-struct NtTcSeg { const float* a; int CA; int shift; int K; const float* w; int w_rows; int w_cols; int k0; int n0; };
-struct NtTcGate { int mode; int c0; int R; const float* bias_sig; const float* bias_tanh; const float* dz; float* dpre; };
-int gemm_nt_tc(const NtTcSeg* segs, int nseg, int N, float* out, int ld_out, const float* bias, const float* mask,
-               int ldmask, const float* add, int ldadd, int relu_out, int accumulate, int B, int T, cudaStream_t st,
-               const float* gate_dz = nullptr, float* gate_dpre = nullptr, float* out2 = nullptr, int ld_out2 = 0,
-               int out2_col0 = 0, const NtTcGate* gate = nullptr);
 
 static bool nt_tc_n_ok(int N) { return N % 32 == 0 && N >= 32 && (N <= 256 || N == 512); }
 

@@ -1,0 +1,199 @@
+// stack.cu -- the whole residual stack of WaveNet.forward (reference wavenet.py:229-236 over :525-536) and its
+// backward in "deferred skip" form, one C-ABI call each (WNB_MATH_TF32, n_resch = 64, kernel_size = 2, n_aux <= 32).
+//
+// The per-block formulation moves the (B,T,S) skip tensor through HBM in every block: a read-modify-write in the
+// forward (skip += ...), and two reads in the backward (dz = dskip W2skip, dW2skip = dskip^T z) -- about 60 % of all
+// bytes of a training step at 64 res / 512 skip channels.  Both directions are linear in the concatenated channel
+// axis, so they are hoisted out of the block loop:
+//
+//   forward    z_l -> Z_all[:, :, l*R:(l+1)*R]     (resblock_z.cu writes the slice)
+//              skip  = Z_all Wskip^T + bskip        one NT GEMM, K = L*R          (Wskip[s][l*R+c] = W2_l[R+s][c])
+//   backward   dZ_all = dskip Wskip                  one NT GEMM, N = L*R in column blocks (A tile shared via L2)
+//              per block: dz_l = dZ_all[l] + dout W2res_l ; gate backward ; dx ; dW1 ; dW2res_l
+//              dWskip = dskip^T Z_all                one weight-gradient GEMM, column groups of Z_all across CTAs
+//
+// Z_all is written once and read twice per step (it replaces the z recompute output of the per-block backward).
+#include <cuda_runtime.h>
+
+#include "../../include/wnb200.h"
+#include "common.cuh"
+#include "tc_host.h"
+
+namespace wnb {
+
+static int pick_block(int total, const int* cands, int n) {
+  for (int i = 0; i < n; i++)
+    if (total % cands[i] == 0) return cands[i];
+  return 0;
+}
+
+static bool stack_supported(int R, int S, int Ap, int ks, int L) {
+  if (!resblock_fwd_z_supported(R, Ap, ks)) return false;
+  if (L < 1 || S % 32 != 0 || S < 32 || (S > 256 && S != 512)) return false;
+  return true;
+}
+
+}  // namespace wnb
+
+using namespace wnb;
+
+WNB_API int wnb_stack_supported(int R, int S, int Ap, int ks, int L, int math_mode) {
+  return (math_mode == WNB_MATH_TF32 && stack_supported(R, S, Ap, ks, L)) ? 1 : 0;
+}
+
+WNB_API int wnb_resblock_fwd_z(const float* xin, const float* haux, const float* w1, const float* b1, const float* w2res,
+                               const float* b2res, float* xout, float* zall, int ldz, int zcol0, int B, int T, int R,
+                               int Ap, int ks, int dilation, void* stream) {
+  WNB_REQUIRE(B > 0 && T > 0 && dilation >= 1 && ldz >= R && zcol0 >= 0 && zcol0 + R <= ldz && ldz % 4 == 0,
+              "resblock_fwd_z: bad shape");
+  WNB_REQUIRE(xin && haux && w1 && b1 && zall && (!xout || (w2res && b2res)), "resblock_fwd_z: null pointer");
+  if (!resblock_fwd_z_supported(R, Ap, ks)) {
+    set_error("resblock_fwd_z: unsupported shape (R=%d Ap=%d ks=%d); use wnb_resblock_fwd", R, Ap, ks);
+    return WNB_ERR_UNSUPPORTED;
+  }
+  return resblock_fwd_z(xin, haux, w1, b1, w2res, b2res, xout, zall, ldz, zcol0, B, T, dilation, (cudaStream_t)stream);
+}
+
+WNB_API int wnb_skip_gemm(const float* zall, const float* wskip, const float* bskip, float* skip, int B, int T, int K,
+                          int S, void* stream) {
+  WNB_REQUIRE(zall && wskip && skip && B > 0 && T > 0 && K % 32 == 0 && S % 32 == 0 && (S <= 256 || S == 512),
+              "skip_gemm: bad arguments");
+  const NtTcSeg seg[1] = {{zall, K, 0, K, wskip, S, K, 0, 0}};
+  return gemm_nt_tc(seg, 1, S, skip, S, bskip, nullptr, 0, nullptr, 0, 0, 0, B, T, (cudaStream_t)stream);
+}
+
+WNB_API int wnb_stack_fwd(float* xs, int nxs, const float* haux, const float* w1, const float* b1, const float* w2res,
+                          const float* b2res, const float* wskip, const float* bskip, float* zall, float* skip,
+                          const int* dilations, int L, int B, int T, int R, int S, int Ap, int ks, void* stream) {
+  WNB_REQUIRE(xs && haux && w1 && b1 && w2res && b2res && wskip && bskip && zall && skip && dilations,
+              "stack_fwd: null pointer");
+  WNB_REQUIRE(B > 0 && T > 0 && L >= 1 && nxs >= (L > 1 ? 2 : 1), "stack_fwd: bad shape");
+  if (!stack_supported(R, S, Ap, ks, L)) {
+    set_error("stack_fwd: unsupported shape (R=%d S=%d Ap=%d ks=%d)", R, S, Ap, ks);
+    return WNB_ERR_UNSUPPORTED;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t xsz = (size_t)B * T * R;
+  const int K1 = ks * R + Ap, ldz = L * R;
+  int rc;
+  for (int l = 0; l < L; l++) {
+    WNB_REQUIRE(dilations[l] >= 1, "stack_fwd: bad dilation");
+    const float* xin = xs + (size_t)(l % nxs) * xsz;
+    float* xout = (l + 1 < L) ? xs + (size_t)((l + 1) % nxs) * xsz : nullptr;
+    if ((rc = resblock_fwd_z(xin, haux, w1 + (size_t)l * 2 * R * K1, b1 + (size_t)l * 2 * R, w2res + (size_t)l * R * R,
+                             b2res + (size_t)l * R, xout, zall, ldz, l * R, B, T, dilations[l], st)) != WNB_OK)
+      return rc;
+  }
+  return wnb_skip_gemm(zall, wskip, bskip, skip, B, T, ldz, S, stream);
+}
+
+// workspace: dZ_all (B,T,L*R) [+ one row of slack] | dpre (B,T,2R) | two (B,T,R) gradient buffers
+WNB_API size_t wnb_stack_bwd_workspace(int L, int B, int T, int R, int S, int Ap, int ks) {
+  (void)S; (void)Ap; (void)ks;
+  const size_t bt = (size_t)B * T;
+  return sizeof(float) * (bt * L * R + (size_t)L * R + bt * 2 * R + 2 * bt * R);
+}
+
+WNB_API int wnb_stack_bwd(const float* xs, const float* haux, const float* zall, const float* dskip, const float* w1,
+                          const float* b1, const float* w1t, const float* w2res_t, const float* wskip_t, float* dx0,
+                          float* dhaux, float* dw1, float* db1, float* dw2res, float* db2res, float* dwskip,
+                          float* dbskip, void* workspace, const int* dilations, int L, int B, int T, int R, int S,
+                          int Ap, int ks, void* stream) {
+  WNB_REQUIRE(xs && haux && zall && dskip && w1 && b1 && w1t && w2res_t && wskip_t && dx0 && dw1 && db1 && dw2res &&
+                  db2res && dwskip && dbskip && workspace && dilations,
+              "stack_bwd: null pointer");
+  WNB_REQUIRE(B > 0 && T > 0 && L >= 1, "stack_bwd: bad shape");
+  if (!stack_supported(R, S, Ap, ks, L)) {
+    set_error("stack_bwd: unsupported shape (R=%d S=%d Ap=%d ks=%d)", R, S, Ap, ks);
+    return WNB_ERR_UNSUPPORTED;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t bt = (size_t)B * T, xsz = bt * R;
+  const int K1 = ks * R + Ap, ldz = L * R;
+  float* dzall = (float*)workspace;
+  float* dpre = dzall + bt * ldz + ldz;
+  float* dbuf[2] = {dpre + bt * 2 * R, dpre + bt * 2 * R + xsz};
+  int rc;
+
+  {  // dZ_all = dskip Wskip   (wskip_t: rows n = l*R + c, K = S contiguous)
+    static const int cands[] = {256, 192, 128, 64, 32};
+    const int nb = pick_block(ldz, cands, 5);
+    WNB_REQUIRE(nb > 0, "stack_bwd: L*R must be a multiple of 32");
+    const NtTcSeg seg[1] = {{dskip, S, 0, S, wskip_t, ldz, S, 0, 0}};
+    const NtTcOpts o{ldz / nb, 0, 0};
+    if ((rc = gemm_nt_tc(seg, 1, nb, dzall, ldz, nullptr, nullptr, 0, nullptr, 0, 0, 0, B, T, st, nullptr, nullptr, nullptr,
+                         0, 0, nullptr, &o)) != WNB_OK)
+      return rc;
+  }
+
+  const float* dout = nullptr;   // gradient w.r.t. the block's residual output (none for the last block)
+  for (int l = L - 1; l >= 0; l--) {
+    const int d = dilations[l];
+    const float* xin = xs + (size_t)l * xsz;
+    const float* w1l = w1 + (size_t)l * 2 * R * K1;
+    const float* w1tl = w1t + (size_t)l * K1 * 2 * R;
+    float* dzl = dzall + (size_t)l * R;          // (B,T,R) view with row pitch ldz
+    float* dxin = (l == 0) ? dx0 : dbuf[l & 1];
+    if (dout) {  // dz_l += dout W2res_l   (w2res_t: rows c, K = o contiguous), in place on the slice
+      const NtTcSeg seg[1] = {{dout, R, 0, R, w2res_t + (size_t)l * R * R, R, R, 0, 0}};
+      if ((rc = gemm_nt_tc(seg, 1, R, dzl, ldz, nullptr, nullptr, 0, dzl, ldz, 0, 0, B, T, st)) != WNB_OK) return rc;
+    }
+    {  // gate recompute (pre = W1 [x(t-d) | x(t) | aux]) fused with dpre in the epilogue
+      const NtTcSeg sg[3] = {{xin, R, -d, R, w1l, 2 * R, K1, 0, 0}, {xin, R, 0, R, w1l, 2 * R, K1, R, 0},
+                             {haux, Ap, 0, Ap, w1l, 2 * R, K1, 2 * R, 0}};
+      const NtTcOpts o{1, ldz, 1};
+      if ((rc = gemm_nt_tc(sg, 3, 2 * R, dxin /* z output suppressed */, R, b1 + (size_t)l * 2 * R, nullptr, 0, nullptr, 0,
+                           0, 0, B, T, st, dzl, dpre, nullptr, 0, 0, nullptr, &o)) != WNB_OK)
+        return rc;
+    }
+    // dxin = dout + dpre(t+d) W1[:, tap0] + dpre(t) W1[:, tap1]   and   dhaux += dpre(t) W1[:, aux]
+    if (dhaux) {
+      const NtTcSeg sx[2] = {{dpre, 2 * R, d, 2 * R, w1tl, R, 2 * R, 0, 0}, {dpre, 2 * R, 0, 2 * R, w1tl, K1, 2 * R, 0, R}};
+      if ((rc = gemm_nt_tc(sx, 2, R + Ap, dxin, R, nullptr, nullptr, 0, dout, R, 0, 0, B, T, st, nullptr, nullptr, dhaux,
+                           Ap, R)) != WNB_OK)
+        return rc;
+    } else {
+      const NtTcSeg sx[2] = {{dpre, 2 * R, d, 2 * R, w1tl, K1, 2 * R, 0, 0}, {dpre, 2 * R, 0, 2 * R, w1tl, K1, 2 * R, 0, R}};
+      if ((rc = gemm_nt_tc(sx, 2, R, dxin, R, nullptr, nullptr, 0, dout, R, 0, 0, B, T, st)) != WNB_OK) return rc;
+    }
+    {  // dW1 (128 x 160) += dpre^T [x(t-d) | x(t) | aux(t)],  db1 = column sums of dpre
+      const WgOperand a[1] = {{dpre, 2 * R, 0, 4, 0}};
+      const WgOperand b[3] = {{xin, R, 0, 2, -d}, {xin, R, 0, 2, 0}, {haux, Ap, 0, 1, 0}};
+      if ((rc = wgrad_tc(a, 1, b, 3, dw1 + (size_t)l * 2 * R * K1, K1, 128, db1 + (size_t)l * 2 * R, B, T, st)) != WNB_OK)
+        return rc;
+    }
+    if (dout) {  // dW2res_l (R x R) += dout^T z_l, db2res_l = column sums of dout (rows 64..127 of the block: zero fill)
+      WgBlock blk;
+      blk.nops = 1;
+      blk.ops[0] = WgOperand{dout, R, 0, 4, 0};
+      blk.c = dw2res + (size_t)l * R * R;
+      blk.m_valid = R;
+      blk.db = db2res + (size_t)l * R;
+      const WgOperand bz[1] = {{zall, ldz, l * R, R / 32, 0}};
+      if ((rc = wgrad_tc_blocks(&blk, 1, bz, 1, R, B, T, st)) != WNB_OK) return rc;
+    }
+    dout = dxin;
+  }
+
+  {  // dWskip (S x L*R) += dskip^T Z_all, dbskip = column sums of dskip
+    const int groups = ldz / 32;
+    int nB = 0;
+    for (int c = 3; c >= 1 && !nB; c--)
+      if (groups % c == 0) nB = c;
+    for (int r0 = 0; r0 < S; r0 += 512) {
+      WgBlock blk[4];
+      int nblk = 0;
+      for (int r = r0; r < S && nblk < 4; r += 128, nblk++) {
+        blk[nblk].nops = 1;
+        blk[nblk].ops[0] = WgOperand{dskip, S, r, 4, 0};
+        blk[nblk].c = dwskip + (size_t)r * ldz;
+        blk[nblk].m_valid = (S - r) < 128 ? (S - r) : 128;
+        blk[nblk].db = dbskip + r;
+      }
+      const WgOperand bz[1] = {{zall, ldz, 0, nB, 0}};
+      const WgOpts o{groups / nB};
+      if ((rc = wgrad_tc_blocks(blk, nblk, bz, 1, ldz, B, T, st, &o)) != WNB_OK) return rc;
+    }
+  }
+  return WNB_OK;
+}

@@ -18,6 +18,7 @@
 #include <string.h>
 
 #include "common.cuh"
+#include "tc_host.h"
 #include "tc_ptx.cuh"
 
 namespace wnb {
@@ -39,6 +40,7 @@ struct alignas(64) Params {
   int T, B, tiles_per_b, ntiles, nstages;
   int tk;                        // time rows per stage (K of one stage): 64, 32 or 16
   int vec4;                      // C blocks are 16-byte aligned with ldc % 4 == 0: flush with red.v4
+  int n_split;                   // column groups of the B operand handled by different CTAs (WgOpts)
 };
 
 __device__ __forceinline__ uint64_t smem_desc_mn_sw128(uint32_t saddr, uint32_t lbo_bytes) {
@@ -86,8 +88,12 @@ __global__ void __launch_bounds__(kThreadsW, 1) wgrad_tc_kernel(const __grid_con
   const int N = 32 * nsubB;
 
   // tiles owned by this CTA: contiguous range (better L2 locality for shifted taps)
-  const int per = (p.ntiles + gridDim.x - 1) / gridDim.x;
-  const int tile_begin = blockIdx.x * per;
+  // with n_split column groups, CTA (g, s) = (blockIdx % n_split, blockIdx / n_split): neighbouring CTAs stream the
+  // same time range (A operand shared through L2) for different 32*nB-channel groups of the B operand
+  const int ng = blockIdx.x % p.n_split, tsplit = blockIdx.x / p.n_split, ntsplit = gridDim.x / p.n_split;
+  const int bcol0 = ng * 32 * p.nB;
+  const int per = (p.ntiles + ntsplit - 1) / ntsplit;
+  const int tile_begin = tsplit * per;
   const int tile_end = min(p.ntiles, tile_begin + per);
   const int my_tiles = max(0, tile_end - tile_begin);
 
@@ -128,7 +134,7 @@ __global__ void __launch_bounds__(kThreadsW, 1) wgrad_tc_kernel(const __grid_con
         for (int g = 0; g < nA; g++)
           ptx::tma_load_3d(st + g * kSubBytes, &p.maps[p.a[g].map], &full[s], p.a[g].c0, t0 + p.a[g].shift, b);
         for (int g = 0; g < p.nB; g++)
-          ptx::tma_load_3d(st + (nA + g) * kSubBytes, &p.maps[p.b[g].map], &full[s], p.b[g].c0, t0 + p.b[g].shift, b);
+          ptx::tma_load_3d(st + (nA + g) * kSubBytes, &p.maps[p.b[g].map], &full[s], p.b[g].c0 + bcol0, t0 + p.b[g].shift, b);
         if (++s == (uint32_t)p.nstages) { s = 0; ph ^= 1; }
       }
     }
@@ -176,7 +182,7 @@ __global__ void __launch_bounds__(kThreadsW, 1) wgrad_tc_kernel(const __grid_con
         ptx::tc_wait_ld();
         if (row < p.m_valid[mb]) {
           if (c0 < 32 * p.nB) {
-            float* dst = p.c[mb] + (size_t)row * p.ldc + c0;
+            float* dst = p.c[mb] + (size_t)row * p.ldc + bcol0 + c0;
             if (p.vec4) {   // 16-byte vector reductions: a quarter of the L2 atomic operations
 #pragma unroll
               for (int i = 0; i < 16; i += 4)
@@ -187,7 +193,7 @@ __global__ void __launch_bounds__(kThreadsW, 1) wgrad_tc_kernel(const __grid_con
 #pragma unroll
               for (int i = 0; i < 16; i++) atomicAdd(dst + i, v[i]);
             }
-          } else if (c0 == 32 * p.nB && p.db[mb]) {
+          } else if (c0 == 32 * p.nB && p.db[mb] && ng == 0) {
             atomicAdd(p.db[mb] + row, v[0]);
           }
         }
@@ -242,14 +248,9 @@ static bool make_act_map(CUtensorMap* m, const float* base, int C, int T, int B,
 
 }  // namespace wg
 
-// One operand = a channels-last tensor (B,T,C); `groups` 32-channel groups starting at channel c0, shifted in time.
-struct WgOperand { const float* base; int C; int c0; int groups; int shift; };
-// One M-block: 128 output rows = 4 groups taken from up to 2 operands (TMA zero fill past a tensor's channels).
-struct WgBlock { WgOperand ops[2]; int nops; float* c; int m_valid; float* db; };
-
 // For every block i:  C_i[128 x 32*sum(groups_b)] += A_i^T B   (+ db_i = column sums of A_i), one launch.
 int wgrad_tc_blocks(const WgBlock* blocks, int nblocks, const WgOperand* b_ops, int nb_ops, int ldc, int B, int T,
-                    cudaStream_t st) {
+                    cudaStream_t st, const WgOpts* opts) {
   using namespace wg;
   if (nblocks < 1 || nblocks > kMaxMB) { set_error("wgrad_tc: 1..%d M-blocks per launch", kMaxMB); return WNB_ERR_INVALID; }
   Params p;
@@ -311,6 +312,7 @@ int wgrad_tc_blocks(const WgBlock* blocks, int nblocks, const WgOperand* b_ops, 
   }
   for (int i = nmaps; i < kMaxMaps; i++) p.maps[i] = p.maps[0];
   p.ldc = ldc;
+  p.n_split = (opts && opts->n_split > 1) ? opts->n_split : 1;
   p.vec4 = (ldc % 4 == 0) ? 1 : 0;
   for (int i = 0; i < nblocks; i++)
     if (reinterpret_cast<uintptr_t>(blocks[i].c) & 15) p.vec4 = 0;
@@ -330,7 +332,11 @@ int wgrad_tc_blocks(const WgBlock* blocks, int nblocks, const WgOperand* b_ops, 
     WNB_CUDA(cudaGetDevice(&dev));
     WNB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   }
-  const int grid = p.ntiles < sms ? p.ntiles : sms;
+  int grid = p.ntiles < sms ? p.ntiles : sms;
+  if (p.n_split > 1) {
+    if (p.n_split > sms) { set_error("wgrad_tc: n_split exceeds the SM count"); return WNB_ERR_INVALID; }
+    grid = (sms / p.n_split) * p.n_split;
+  }
   static int prof = -1;
   if (prof < 0) { const char* e = getenv("WNB_PROF"); prof = (e && e[0] == '1') ? 1 : 0; }
   if (prof) {

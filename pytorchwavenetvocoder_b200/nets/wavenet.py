@@ -244,6 +244,92 @@ class _WaveNetFn(torch.autograd.Function):
         return None, dhaux, dwf, dbf, dW1, db1, dW2, db2, dWp1, dbp1, dWp2, dbp2, None
 
 
+class _WaveNetStackFn(torch.autograd.Function):
+    """WaveNet.forward (reference wavenet.py:212-241) with the skip path in deferred form (csrc/stack.cu): the blocks
+    write their gate outputs z_l into Z_all (B,T,L*R) and ONE GEMM forms skip = Z_all Wskip^T + bskip; the backward
+    hoists dZ_all = dskip Wskip and dWskip = dskip^T Z_all out of the block loop the same way.  Same numbers as the
+    per-block form (different summation order inside tf32/fp32 accumulation only)."""
+
+    @staticmethod
+    def forward(ctx, x, haux, wf, bf, W1, b1, W2res, b2res, Wskip, bskip, Wp1, bp1, Wp2, bp2, meta):
+        lib = _lib.load()
+        Q, R, S, Ap, ks, dilations, math_mode = meta
+        B, T = x.shape
+        L = len(dilations)
+        dev = x.device
+        x = x.contiguous()
+        need_grad = any(ctx.needs_input_grad)
+        st = stream()
+        nbuf = L if need_grad else min(L, 2)
+        xs = torch.empty(nbuf, B, T, R, device=dev, dtype=torch.float32)
+        check(lib.wnb_front_embed_fwd(ptr(x), ptr(wf), ptr(bf), ptr(xs[0]), B, T, Q, R, ks, st), "front_embed_fwd")
+        zall = torch.empty(B, T, L * R, device=dev, dtype=torch.float32)
+        skip = torch.empty(B, T, S, device=dev, dtype=torch.float32)
+        dil = (ctypes.c_int * L)(*[int(d) for d in dilations])
+        prof = PROFILE_EVENTS
+        if prof is None:
+            check(lib.wnb_stack_fwd(ptr(xs), nbuf, ptr(haux), ptr(W1), ptr(b1), ptr(W2res), ptr(b2res), ptr(Wskip),
+                                    ptr(bskip), ptr(zall), ptr(skip), dil, L, B, T, R, S, Ap, ks, st), "stack_fwd")
+        else:   # same launches, one ABI call per block so that each can be bracketed by CUDA events
+            for l, d in enumerate(dilations):
+                xout = xs[(l + 1) % nbuf] if l + 1 < L else None
+                ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                ev[0].record()
+                check(lib.wnb_resblock_fwd_z(ptr(xs[l % nbuf]), ptr(haux), ptr(W1[l]), ptr(b1[l]), ptr(W2res[l]),
+                                             ptr(b2res[l]), ptr(xout), ptr(zall), L * R, l * R, B, T, R, Ap, ks,
+                                             int(d), st), "resblock_fwd_z")
+                ev[1].record()
+                prof.append(ev)
+            check(lib.wnb_skip_gemm(ptr(zall), ptr(Wskip), ptr(bskip), ptr(skip), B, T, L * R, S, st), "skip_gemm")
+        r1 = torch.empty(B, T, S, device=dev, dtype=torch.float32)
+        logits = torch.empty(B, T, Q, device=dev, dtype=torch.float32)
+        check(lib.wnb_post_fwd(ptr(skip), ptr(Wp1), ptr(bp1), ptr(Wp2), ptr(bp2), ptr(r1), ptr(logits),
+                               B, T, S, Q, math_mode, st), "post_fwd")
+        if need_grad:
+            ctx.save_for_backward(x, haux, wf, W1, b1, W2res, Wskip, Wp1, Wp2, xs, zall, skip, r1)
+            ctx.meta = meta
+            ctx.haux_needs_grad = ctx.needs_input_grad[1]
+        return logits
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        lib = _lib.load()
+        x, haux, wf, W1, b1, W2res, Wskip, Wp1, Wp2, xs, zall, skip, r1 = ctx.saved_tensors
+        Q, R, S, Ap, ks, dilations, math_mode = ctx.meta
+        B, T = x.shape
+        L = len(dilations)
+        dev = x.device
+        st = stream()
+        dlogits = dlogits.contiguous()
+        z = lambda *s: torch.zeros(*s, device=dev, dtype=torch.float32)  # noqa: E731
+        K1 = ks * R + Ap
+        dWp1, dbp1, dWp2, dbp2 = z(S, S), z(S), z(Q, S), z(Q)
+        dskip = torch.empty(B, T, S, device=dev, dtype=torch.float32)
+        ws_post = torch.empty(B, T, S, device=dev, dtype=torch.float32)
+        wp1t = Wp1.t().contiguous()
+        wp2t = Wp2.t().contiguous()
+        check(lib.wnb_post_bwd(ptr(skip), ptr(r1), ptr(dlogits), ptr(wp1t), ptr(wp2t), ptr(dskip), ptr(dWp1),
+                               ptr(dbp1), ptr(dWp2), ptr(dbp2), ptr(ws_post), B, T, S, Q, math_mode, st), "post_bwd")
+        del ws_post
+        dW1, db1, dW2res, db2res = z(L, 2 * R, K1), z(L, 2 * R), z(L, R, R), z(L, R)
+        dWskip, dbskip = z(S, L * R), z(S)
+        dhaux = z(B, T, Ap) if ctx.haux_needs_grad else None
+        w1t = W1.transpose(1, 2).contiguous()         # (L, K1, 2R)
+        w2rt = W2res.transpose(1, 2).contiguous()     # (L, R, R)  [c][o]
+        wskt = Wskip.t().contiguous()                 # (L*R, S)
+        nbytes = lib.wnb_stack_bwd_workspace(L, B, T, R, S, Ap, ks)
+        ws = torch.empty(nbytes // 4, device=dev, dtype=torch.float32)
+        dx0 = torch.empty(B, T, R, device=dev, dtype=torch.float32)
+        dil = (ctypes.c_int * L)(*[int(d) for d in dilations])
+        check(lib.wnb_stack_bwd(ptr(xs), ptr(haux), ptr(zall), ptr(dskip), ptr(W1), ptr(b1), ptr(w1t), ptr(w2rt),
+                                ptr(wskt), ptr(dx0), ptr(dhaux), ptr(dW1), ptr(db1), ptr(dW2res), ptr(db2res),
+                                ptr(dWskip), ptr(dbskip), ptr(ws), dil, L, B, T, R, S, Ap, ks, st), "stack_bwd")
+        del ws
+        dwf, dbf = z(ks, Q, R), z(R)
+        check(lib.wnb_front_embed_bwd(ptr(x), ptr(dx0), ptr(dwf), ptr(dbf), B, T, Q, R, ks, st), "front_embed_bwd")
+        return (None, dhaux, dwf, dbf, dW1, db1, dW2res, db2res, dWskip, dbskip, dWp1, dbp1, dWp2, dbp2, None)
+
+
 # ------------------------------------------------------------------------------------------
 # modules (same names / parameters / state_dict keys as the reference)
 # ------------------------------------------------------------------------------------------
@@ -440,6 +526,15 @@ class WaveNet(nn.Module):
         packed = self._pack()
         meta = (self.n_quantize, self.n_resch, self.n_skipch, self.n_aux_pad, self.kernel_size,
                 tuple(self.dilations), self._math())
+        if getattr(self, "deferred_skip", True) and _lib.load().wnb_stack_supported(self.n_resch, self.n_skipch, self.n_aux_pad, self.kernel_size,
+                                           len(self.dilations), self._math()):
+            # deferred-skip form: split W2 / b2 into the residual part and the concatenated skip GEMM operand
+            wf, bf, W1, b1, W2, b2, Wp1, bp1, Wp2, bp2 = packed
+            R, S, L = self.n_resch, self.n_skipch, len(self.dilations)
+            W2res, b2res = W2[:, :R].contiguous(), b2[:, :R].contiguous()
+            Wskip = W2[:, R:].permute(1, 0, 2).reshape(S, L * R).contiguous()      # [s][l*R + c]
+            bskip = b2[:, R:].sum(0)
+            return _WaveNetStackFn.apply(x, haux, wf, bf, W1, b1, W2res, b2res, Wskip, bskip, Wp1, bp1, Wp2, bp2, meta)
         return _WaveNetFn.apply(x, haux, *packed, meta)
 
     def forward(self, x, h):
