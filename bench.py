@@ -185,7 +185,16 @@ def run_ours(args):
         # --- device-resident timing (value) ---
         barrier()
         l0 = _lib.launch_count()
-        wn.PROFILE_EVENTS = []
+        lib = _lib.load()
+        L = len(net.dilations)
+        stack = bool(args.math == "tf32" and lib.wnb_stack_supported(cfg.n_resch, cfg.n_skipch, net.n_aux_pad,
+                                                                     cfg.kernel_size, L, _lib.MATH_TF32))
+        if stack:
+            # the product path is ONE ABI call per direction (csrc/stack.cu); it brackets each of its launches
+            # with CUDA events on the launching stream while this switch is on
+            _lib.check(lib.wnb_profile_enable(1), "profile_enable")
+        else:
+            wn.PROFILE_EVENTS = []
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(args.steps):
@@ -194,9 +203,17 @@ def run_ours(args):
         barrier()
         ms = e0.elapsed_time(e1)
         launches = _lib.launch_count() - l0
-        evs = wn.PROFILE_EVENTS
+        evs = wn.PROFILE_EVENTS or []
         wn.PROFILE_EVENTS = None
         blk_ms = [a.elapsed_time(b) for a, b in evs]
+        kinds = []
+        if stack:
+            import ctypes
+            for k, name in enumerate(STACK_KINDS):
+                tot, n = ctypes.c_double(0.0), ctypes.c_int(0)
+                _lib.check(lib.wnb_profile_read(k, ctypes.byref(tot), ctypes.byref(n)), "profile_read")
+                kinds.append((name, tot.value, n.value))
+            _lib.check(lib.wnb_profile_enable(0), "profile_enable")
         clocks = sampler.stop() if rank == 0 else None
         # --- end-to-end timing: pinned host -> device every step, loss read back every step ---
         for _ in range(2):
@@ -223,6 +240,33 @@ def run_ours(args):
         alg_bytes = float(Bq) * T * s * (2 * R + A + 2 * S)
         blk = float(np.mean(blk_ms)) if blk_ms else None
         ach = alg_bytes / (blk * 1e-3) / 1e9 if blk else None
+        roof = {"kernel": "resblock_fwd (%s)" % args.math, "bound": "hbm", "achieved": ach, "peak": hbm,
+                "unit": "GB/s", "frac": (ach / hbm) if ach else None, "traffic": TRAFFIC_NCU.get(args.math),
+                "peak_source": how, "algorithmic_bytes_per_launch": alg_bytes,
+                "mean_launch_ms": blk, "launches_timed": len(blk_ms)}
+        roof_all = None
+        if stack:
+            # algorithmic bytes per launch of every kernel kind of the deferred-skip stack:
+            # fp32 channels-last tensors, each streamed once; weights (<= 4 MB) not counted
+            bt4, Ap, LR = float(Bq) * T * 4, net.n_aux_pad, L * R
+            alg = {"fwd_block": bt4 * (3 * R + Ap), "skip_gemm": bt4 * (LR + S), "dzall_gemm": bt4 * (S + LR),
+                   "gate_bwd": bt4 * (5 * R + Ap), "dx_gemm": bt4 * (4 * R + 2 * Ap), "dw1": bt4 * (3 * R + Ap),
+                   "dw2res": bt4 * 2 * R, "dwskip": bt4 * (S + LR)}
+            roof_all = []
+            for name, tot, n in kinds:
+                if n == 0:
+                    continue
+                mean = tot / n
+                a = alg[name] / (mean * 1e-3) / 1e9
+                roof_all.append({"kernel": name, "launches_timed": n, "mean_launch_ms": mean,
+                                 "share_of_step": tot / ms, "algorithmic_bytes_per_launch": alg[name],
+                                 "achieved": a, "frac": a / hbm, "traffic": TRAFFIC_NCU_STACK.get(name)})
+            top = max(roof_all, key=lambda r: r["share_of_step"])
+            roof = {"kernel": "%s (tf32, deferred-skip stack)" % top["kernel"], "bound": "hbm", "achieved": top["achieved"],
+                    "peak": hbm, "unit": "GB/s", "frac": top["frac"], "traffic": top["traffic"], "peak_source": how,
+                    "algorithmic_bytes_per_launch": top["algorithmic_bytes_per_launch"],
+                    "mean_launch_ms": top["mean_launch_ms"], "launches_timed": top["launches_timed"],
+                    "share_of_step": top["share_of_step"]}
         out = {
             "metric": "train waveform-samples/s (fwd+CE+bwd+Adam), arctic/sd 30-layer 64res/512skip",
             "value": samples / (per_step * 1e-3), "unit": "samples/s", "n_gpus": world, "steps": args.steps,
@@ -239,11 +283,10 @@ def run_ours(args):
                     "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps, "last_loss": last},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"kernel": "resblock_fwd (%s)" % args.math, "bound": "hbm", "achieved": ach, "peak": hbm,
-                         "unit": "GB/s", "frac": (ach / hbm) if ach else None, "traffic": TRAFFIC_NCU.get(args.math),
-                         "peak_source": how, "algorithmic_bytes_per_launch": alg_bytes,
-                         "mean_launch_ms": blk, "launches_timed": len(blk_ms)},
+            "roofline": roof,
         }
+        if roof_all:
+            out["roofline_kernels"] = roof_all
     if args.workload == "decode" or (args.workload == "train" and args.with_decode):
         dec = run_decode(args, dev, rank, world, dist)
         if args.workload == "decode":
@@ -263,6 +306,9 @@ def run_ours(args):
 # capture committed under profiles/ (filled in by hand from that capture; None = not captured yet)
 # tf32: profiles/r1_ncu_resblock_fwd_tc_summary.txt launch 1 (layer 1): 448.57 MB read + 365.57 MB write
 TRAFFIC_NCU = {"fp32": None, "tf32": 814.14e6}
+# kernel kinds timed by wnb_profile_read (WNB_PROF_* order) and their ncu DRAM bytes per launch (None = not captured)
+STACK_KINDS = ["fwd_block", "skip_gemm", "dzall_gemm", "gate_bwd", "dx_gemm", "dw1", "dw2res", "dwskip"]
+TRAFFIC_NCU_STACK = {}
 
 
 def run_decode(args, dev, rank, world, dist):

@@ -99,6 +99,22 @@ WNB_API int wnb_resblock_fwd_supported(int R, int S, int Ap, int ks, int math_mo
 WNB_API int wnb_causal_conv1d_fwd(const float* x, const float* w, const float* bias, float* out, int B, int T,
                                   int Cin, int Cout, int ks, int dilation, void* stream);
 
+/* ---- per-launch timing of the stack kernels (measurement aid for bench.py's roofline block) ----
+ * While enabled, wnb_stack_fwd / wnb_stack_bwd bracket every kernel launch with CUDA events on the launching stream;
+ * wnb_profile_read() waits for them and returns the summed duration and launch count of one kind since the last
+ * wnb_profile_enable().  Single-threaded use. */
+#define WNB_PROF_FWD_BLOCK 0   /* resblock_fwd_z: one residual block, deferred-skip form */
+#define WNB_PROF_SKIP_GEMM 1   /* skip = Z_all Wskip^T */
+#define WNB_PROF_DZALL_GEMM 2  /* dZ_all = dskip Wskip */
+#define WNB_PROF_GATE_BWD 3    /* gate recompute + dz + dpre */
+#define WNB_PROF_DX_GEMM 4     /* dx (+ dhaux) */
+#define WNB_PROF_DW1 5         /* dW1, db1 */
+#define WNB_PROF_DW2RES 6      /* dW2res, db2res */
+#define WNB_PROF_DWSKIP 7      /* dWskip, dbskip */
+#define WNB_PROF_KINDS 8
+WNB_API int wnb_profile_enable(int on);
+WNB_API int wnb_profile_read(int kind, double* total_ms, int* launches);
+
 /* ---- residual stack in deferred-skip form (training path of WaveNet.forward, wavenet.py:229-236 over :525-536) ----
  * The skip sum over all L blocks is one GEMM over the concatenated gate outputs,
  *     skip = [z_0 | ... | z_{L-1}] Wskip^T + bskip,   Wskip[s][l*R+c] = skip_1x1_l.weight[s][c],  bskip = sum_l skip bias_l
@@ -127,13 +143,14 @@ WNB_API int wnb_stack_fwd(float* xs, int nxs, const float* haux, const float* w1
                           int Ap, int ks, void* stream);
 
 /* backward of wnb_stack_fwd.  xs (L,B,T,R) and zall from the forward; dskip (B,T,S) = d loss / d skip.
- * w1t (L,K1,2R) as for wnb_resblock_bwd, w2res_t (L,R,R) = w2res transposed ([c][o]), wskip_t (L*R,S) = wskip^T.
+ * w1t (L,K1,2R) as for wnb_resblock_bwd; wgate (L,3R,K1+R) = block matrix [[w1, 0], [0, w2res^T]] per block (gate
+ * recompute and the residual part of dz share one GEMM); wskip_t (L*R,S) = wskip^T.
  * dx0 (B,T,R) = gradient of xs[0]; dhaux (B,T,Ap) accumulated into (or NULL); dw1, db1, dw2res, db2res, dwskip
  * (S,L*R), dbskip (S) are ACCUMULATED into (the last block's dw2res / db2res are left untouched: that conv has no
  * gradient, like the reference).  workspace: wnb_stack_bwd_workspace() bytes. */
 WNB_API size_t wnb_stack_bwd_workspace(int L, int B, int T, int R, int S, int Ap, int ks);
 WNB_API int wnb_stack_bwd(const float* xs, const float* haux, const float* zall, const float* dskip, const float* w1,
-                          const float* b1, const float* w1t, const float* w2res_t, const float* wskip_t, float* dx0,
+                          const float* b1, const float* w1t, const float* wgate, const float* wskip_t, float* dx0,
                           float* dhaux, float* dw1, float* db1, float* dw2res, float* db2res, float* dwskip,
                           float* dbskip, void* workspace, const int* dilations, int L, int B, int T, int R, int S,
                           int Ap, int ks, void* stream);

@@ -38,6 +38,8 @@ SIGNATURES = {
     "wnb_resblock_fwd": (_I, [_P] * 9 + [_I] * 9 + [_P]),
     "wnb_resblock_fwd_supported": (_I, [_I] * 5),
     "wnb_causal_conv1d_fwd": (_I, [_P] * 4 + [_I] * 6 + [_P]),
+    "wnb_profile_enable": (_I, [_I]),
+    "wnb_profile_read": (_I, [_I, _P, _P]),
     "wnb_stack_supported": (_I, [_I] * 6),
     "wnb_resblock_fwd_z": (_I, [_P] * 8 + [_I] * 8 + [_P]),
     "wnb_skip_gemm": (_I, [_P] * 4 + [_I] * 4 + [_P]),

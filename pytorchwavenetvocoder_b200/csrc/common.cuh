@@ -10,6 +10,14 @@ namespace wnb {
 
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
+// Optional per-launch CUDA-event timing by kernel kind (WNB_PROF_* in wnb200.h), see wnb_profile_enable().
+void prof_begin(int kind, cudaStream_t st);
+void prof_end(int kind, cudaStream_t st);
+struct ProfScope {
+  int kind; cudaStream_t st;
+  ProfScope(int k, cudaStream_t s) : kind(k), st(s) { prof_begin(k, s); }
+  ~ProfScope() { prof_end(kind, st); }
+};
 
 #define WNB_REQUIRE(cond, ...)            \
   do {                                    \

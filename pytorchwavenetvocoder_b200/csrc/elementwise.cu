@@ -5,6 +5,7 @@
 #include <stdarg.h>
 
 #include <atomic>
+#include <vector>
 
 #include "common.cuh"
 
@@ -20,6 +21,28 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 void count_launch(int n) { g_launches.fetch_add(n); }
+
+// ---- per-launch event timing (off by default; bench.py switches it on for the timed region) ----
+struct ProfRec { int kind; cudaEvent_t e0, e1; };
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof_recs;      // records of the current session
+static std::vector<cudaEvent_t> g_prof_pool;  // recycled events
+static cudaEvent_t prof_event() {
+  if (!g_prof_pool.empty()) { cudaEvent_t e = g_prof_pool.back(); g_prof_pool.pop_back(); return e; }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+void prof_begin(int kind, cudaStream_t st) {
+  if (!g_prof_on) return;
+  ProfRec r{kind, prof_event(), prof_event()};
+  cudaEventRecord(r.e0, st);
+  g_prof_recs.push_back(r);
+}
+void prof_end(int kind, cudaStream_t st) {
+  if (!g_prof_on || g_prof_recs.empty() || g_prof_recs.back().kind != kind) return;
+  cudaEventRecord(g_prof_recs.back().e1, st);
+}
 
 static int grid_for(int64_t work_items, int threads) {
   int64_t blocks = (work_items + threads - 1) / threads;
@@ -262,6 +285,32 @@ extern "C" {
 WNB_API int wnb_version(void) { return 100; }
 WNB_API const char* wnb_last_error(void) { return wnb::g_err; }
 WNB_API int64_t wnb_launch_count(void) { return wnb::g_launches.load(); }
+
+WNB_API int wnb_profile_enable(int on) {
+  using namespace wnb;
+  for (auto& r : g_prof_recs) { g_prof_pool.push_back(r.e0); g_prof_pool.push_back(r.e1); }
+  g_prof_recs.clear();
+  g_prof_on = on != 0;
+  return WNB_OK;
+}
+
+WNB_API int wnb_profile_read(int kind, double* total_ms, int* launches) {
+  using namespace wnb;
+  WNB_REQUIRE(total_ms && launches && kind >= 0 && kind < WNB_PROF_KINDS, "profile_read: bad arguments");
+  double tot = 0.0;
+  int n = 0;
+  for (auto& r : g_prof_recs) {
+    if (r.kind != kind) continue;
+    WNB_CUDA(cudaEventSynchronize(r.e1));
+    float ms = 0.f;
+    WNB_CUDA(cudaEventElapsedTime(&ms, r.e0, r.e1));
+    tot += ms;
+    n++;
+  }
+  *total_ms = tot;
+  *launches = n;
+  return WNB_OK;
+}
 
 WNB_API int wnb_mulaw_encode_f32(const float* x, int64_t* y, int64_t n, int mu, void* stream) {
   WNB_REQUIRE(n >= 0 && mu >= 2, "mulaw_encode_f32: bad n/mu");

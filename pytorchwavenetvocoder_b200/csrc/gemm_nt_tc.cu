@@ -36,6 +36,8 @@ struct alignas(64) Params {
   // gate epilogues (N == 128 = [64 sigmoid pre | 64 tanh pre] of gate channels gate_c0 .. gate_c0+63 of gate_R):
   //   forward  (gate_mode 1): z -> maps[8] at column gate_c0 + c
   //   backward (gate_mode 2): dz (B,T,gate_R) in;  z -> maps[8];  dpre -> maps[9] at columns gate_c0+c / gate_R+gate_c0+c
+  //   backward (gate_mode 3): as 2, but N == 192 and accumulator columns 128..191 hold a partial dz (an extra GEMM
+  //                           segment, e.g. dout W2res) that is added to the dz read from memory
   // bias = sigmoid-branch bias, bias2 = tanh-branch bias (already offset by gate_c0)
   const float* gate_dz; const float* bias2;
   int gate_mode, gate_c0, gate_R;
@@ -175,6 +177,20 @@ __global__ void __launch_bounds__(kThreadsN, 1) gemm_nt_tc_kernel(const __grid_c
       const size_t grow = (size_t)b * p.T + (row_ok ? t : 0);
       const uint32_t buf = (p.nacc == 2) ? (it & 1) : 0;
       const uint32_t use = (p.nacc == 2) ? (it >> 1) : it;
+      // operands of the epilogue that do not depend on the accumulator are requested before waiting for it, so
+      // their DRAM latency overlaps the mainloop of this tile: dz of the gate backward, `add` of the first chunk
+      float4 pre[8];
+      const bool pre_dz = p.gate_mode >= 2 && row_ok && hf * 32 < 64;
+      const bool pre_add = !p.gate_mode && p.add && row_ok && hf * 32 < N && !(p.out2_col0 > 0 && hf * 32 >= p.out2_col0);
+      if (pre_dz) {
+        const float4* dr = reinterpret_cast<const float4*>(p.gate_dz + grow * p.gate_ld_dz + p.gate_c0 + hf * 32);
+#pragma unroll
+        for (int j = 0; j < 8; j++) pre[j] = __ldg(dr + j);
+      } else if (pre_add) {
+        const float4* ar = reinterpret_cast<const float4*>(p.add + grow * p.ldadd + ncol0 + hf * 32);
+#pragma unroll
+        for (int j = 0; j < 8; j++) pre[j] = __ldg(ar + j);
+      }
       wait(&dfull[buf], use & 1, NP_E_DFULL);
       ptx::tc_fence_after();
       if (p.gate_mode) {
@@ -193,6 +209,15 @@ __global__ void __launch_bounds__(kThreadsN, 1) gemm_nt_tc_kernel(const __grid_c
             ptx::tc_wait_ld();
 #pragma unroll
             for (int i = 0; i < 16; i++) { g[i] = lo[i]; g[16 + i] = hi[i]; }
+          }
+          float dzp[32];
+          if (p.gate_mode == 3) {
+            float lo[16], hi[16];
+            ptx::tmem_ld16(tmem + lane_base + buf * N + 128 + c0, lo);
+            ptx::tmem_ld16(tmem + lane_base + buf * N + 128 + c0 + 16, hi);
+            ptx::tc_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 16; i++) { dzp[i] = lo[i]; dzp[16 + i] = hi[i]; }
           }
           ptx::tc_fence_before();
           ptx::mbar_arrive(&dempty[buf]);   // this warp's share of the accumulator is in registers
@@ -225,15 +250,18 @@ __global__ void __launch_bounds__(kThreadsN, 1) gemm_nt_tc_kernel(const __grid_c
             continue;
           }
           if (row_ok) {
-            const float4* dr = reinterpret_cast<const float4*>(p.gate_dz + grow * p.gate_ld_dz + p.gate_c0 + c0);
 #pragma unroll
             for (int j = 0; j < 8; j++) {
-              const float4 d4 = __ldg(dr + j);
+              const float4 d4 = pre[j];   // requested before the accumulator wait (c0 == hf * 32)
               dzv[4 * j] = d4.x; dzv[4 * j + 1] = d4.y; dzv[4 * j + 2] = d4.z; dzv[4 * j + 3] = d4.w;
             }
           } else {
 #pragma unroll
             for (int i = 0; i < 32; i++) dzv[i] = 0.f;
+          }
+          if (p.gate_mode == 3) {
+#pragma unroll
+            for (int i = 0; i < 32; i++) dzv[i] += dzp[i];
           }
 #pragma unroll
           for (int i = 0; i < 32; i++) {
@@ -245,7 +273,8 @@ __global__ void __launch_bounds__(kThreadsN, 1) gemm_nt_tc_kernel(const __grid_c
             dzv[i] = sg * th;                      // z
           }
 #pragma unroll
-          for (int which = p.gate_skip_z ? 1 : 0; which < 3; which++) {
+          for (int which = 0; which < 3; which++) {
+            if (which == 0 && p.gate_skip_z) continue;   // (constant trip count: a / g / dzv stay in registers)
             const float* src = which == 0 ? dzv : (which == 1 ? a : g);
             unsigned char* sb = stg + (nstore & 1) * kStg;
             {
@@ -295,9 +324,10 @@ __global__ void __launch_bounds__(kThreadsN, 1) gemm_nt_tc_kernel(const __grid_c
         }
         if (p.add && row_ok && !second) {
           const float4* ar = reinterpret_cast<const float4*>(p.add + grow * p.ldadd + ncol0 + c0);
+          const bool use_pre = pre_add && c0 == hf * 32;
 #pragma unroll
           for (int j = 0; j < 8; j++) {
-            const float4 a = __ldg(ar + j);
+            const float4 a = use_pre ? pre[j] : __ldg(ar + j);
             v[4 * j] += a.x; v[4 * j + 1] += a.y; v[4 * j + 2] += a.z; v[4 * j + 3] += a.w;
           }
         }
@@ -417,11 +447,12 @@ int gemm_nt_tc(const NtTcSeg* segs, int nseg, int N, float* out, int ld_out, con
   if (!map3(&p.maps[8], out, ld_out, T, B, 32)) { set_error("gemm_nt_tc: output map failed"); return WNB_ERR_CUDA; }
   p.maps[9] = p.maps[8];
   if (gate_dz) {   // R = 64 shorthand used by the fused-shape backward: whole gate in one launch
-    if (N != 128 || !gate_dpre || !bias || !map3(&p.maps[9], gate_dpre, 128, T, B, 32)) {
+    const bool fused_dz = opts && opts->gate_fused_dz;
+    if (N != (fused_dz ? 192 : 128) || !gate_dpre || !bias || !map3(&p.maps[9], gate_dpre, 128, T, B, 32)) {
       set_error("gemm_nt_tc: bad gate-backward configuration");
       return WNB_ERR_INVALID;
     }
-    p.gate_dz = gate_dz; p.bias = bias; p.bias2 = bias + 64; p.gate_mode = 2; p.gate_c0 = 0; p.gate_R = 64;
+    p.gate_dz = gate_dz; p.bias = bias; p.bias2 = bias + 64; p.gate_mode = fused_dz ? 3 : 2; p.gate_c0 = 0; p.gate_R = 64;
   }
   if (gate) {      // general form: 64 gate channels [c0, c0+64) of R; W rows c0.. (sigmoid) and R+c0.. (tanh)
     if (N != 128 || gate->R % 64 != 0 || gate->c0 % 64 != 0 || gate->c0 + 64 > gate->R || !gate->bias_sig ||

@@ -9,7 +9,8 @@
 //   forward    z_l -> Z_all[:, :, l*R:(l+1)*R]     (resblock_z.cu writes the slice)
 //              skip  = Z_all Wskip^T + bskip        one NT GEMM, K = L*R          (Wskip[s][l*R+c] = W2_l[R+s][c])
 //   backward   dZ_all = dskip Wskip                  one NT GEMM, N = L*R in column blocks (A tile shared via L2)
-//              per block: dz_l = dZ_all[l] + dout W2res_l ; gate backward ; dx ; dW1 ; dW2res_l
+//              per block: gate recompute + dz_l = dZ_all[l] + dout W2res_l + gate backward (one GEMM) ; dx ; dW1 ;
+//              dW2res_l
 //              dWskip = dskip^T Z_all                one weight-gradient GEMM, column groups of Z_all across CTAs
 //
 // Z_all is written once and read twice per step (it replaces the z recompute output of the per-block backward).
@@ -80,10 +81,12 @@ WNB_API int wnb_stack_fwd(float* xs, int nxs, const float* haux, const float* w1
     WNB_REQUIRE(dilations[l] >= 1, "stack_fwd: bad dilation");
     const float* xin = xs + (size_t)(l % nxs) * xsz;
     float* xout = (l + 1 < L) ? xs + (size_t)((l + 1) % nxs) * xsz : nullptr;
+    ProfScope ps(WNB_PROF_FWD_BLOCK, st);
     if ((rc = resblock_fwd_z(xin, haux, w1 + (size_t)l * 2 * R * K1, b1 + (size_t)l * 2 * R, w2res + (size_t)l * R * R,
                              b2res + (size_t)l * R, xout, zall, ldz, l * R, B, T, dilations[l], st)) != WNB_OK)
       return rc;
   }
+  ProfScope ps(WNB_PROF_SKIP_GEMM, st);
   return wnb_skip_gemm(zall, wskip, bskip, skip, B, T, ldz, S, stream);
 }
 
@@ -95,11 +98,11 @@ WNB_API size_t wnb_stack_bwd_workspace(int L, int B, int T, int R, int S, int Ap
 }
 
 WNB_API int wnb_stack_bwd(const float* xs, const float* haux, const float* zall, const float* dskip, const float* w1,
-                          const float* b1, const float* w1t, const float* w2res_t, const float* wskip_t, float* dx0,
+                          const float* b1, const float* w1t, const float* wgate, const float* wskip_t, float* dx0,
                           float* dhaux, float* dw1, float* db1, float* dw2res, float* db2res, float* dwskip,
                           float* dbskip, void* workspace, const int* dilations, int L, int B, int T, int R, int S,
                           int Ap, int ks, void* stream) {
-  WNB_REQUIRE(xs && haux && zall && dskip && w1 && b1 && w1t && w2res_t && wskip_t && dx0 && dw1 && db1 && dw2res &&
+  WNB_REQUIRE(xs && haux && zall && dskip && w1 && b1 && w1t && wgate && wskip_t && dx0 && dw1 && db1 && dw2res &&
                   db2res && dwskip && dbskip && workspace && dilations,
               "stack_bwd: null pointer");
   WNB_REQUIRE(B > 0 && T > 0 && L >= 1, "stack_bwd: bad shape");
@@ -120,7 +123,8 @@ WNB_API int wnb_stack_bwd(const float* xs, const float* haux, const float* zall,
     const int nb = pick_block(ldz, cands, 5);
     WNB_REQUIRE(nb > 0, "stack_bwd: L*R must be a multiple of 32");
     const NtTcSeg seg[1] = {{dskip, S, 0, S, wskip_t, ldz, S, 0, 0}};
-    const NtTcOpts o{ldz / nb, 0, 0};
+    const NtTcOpts o{ldz / nb, 0, 0, 0};
+    ProfScope ps(WNB_PROF_DZALL_GEMM, st);
     if ((rc = gemm_nt_tc(seg, 1, nb, dzall, ldz, nullptr, nullptr, 0, nullptr, 0, 0, 0, B, T, st, nullptr, nullptr, nullptr,
                          0, 0, nullptr, &o)) != WNB_OK)
       return rc;
@@ -130,35 +134,38 @@ WNB_API int wnb_stack_bwd(const float* xs, const float* haux, const float* zall,
   for (int l = L - 1; l >= 0; l--) {
     const int d = dilations[l];
     const float* xin = xs + (size_t)l * xsz;
-    const float* w1l = w1 + (size_t)l * 2 * R * K1;
     const float* w1tl = w1t + (size_t)l * K1 * 2 * R;
     float* dzl = dzall + (size_t)l * R;          // (B,T,R) view with row pitch ldz
     float* dxin = (l == 0) ? dx0 : dbuf[l & 1];
-    if (dout) {  // dz_l += dout W2res_l   (w2res_t: rows c, K = o contiguous), in place on the slice
-      const NtTcSeg seg[1] = {{dout, R, 0, R, w2res_t + (size_t)l * R * R, R, R, 0, 0}};
-      if ((rc = gemm_nt_tc(seg, 1, R, dzl, ldz, nullptr, nullptr, 0, dzl, ldz, 0, 0, B, T, st)) != WNB_OK) return rc;
-    }
-    {  // gate recompute (pre = W1 [x(t-d) | x(t) | aux]) fused with dpre in the epilogue
-      const NtTcSeg sg[3] = {{xin, R, -d, R, w1l, 2 * R, K1, 0, 0}, {xin, R, 0, R, w1l, 2 * R, K1, R, 0},
-                             {haux, Ap, 0, Ap, w1l, 2 * R, K1, 2 * R, 0}};
-      const NtTcOpts o{1, ldz, 1};
-      if ((rc = gemm_nt_tc(sg, 3, 2 * R, dxin /* z output suppressed */, R, b1 + (size_t)l * 2 * R, nullptr, 0, nullptr, 0,
-                           0, 0, B, T, st, dzl, dpre, nullptr, 0, 0, nullptr, &o)) != WNB_OK)
+    {  // gate recompute (pre = W1 [x(t-d) | x(t) | aux]) and dz_l = dZ_all[l] + dout W2res_l in ONE GEMM over the block
+       // matrix wgate_l = [[W1, 0], [0, W2res^T]] (3R x (K1+R)): accumulator columns 0..2R-1 are the gate
+       // pre-activations, columns 2R..3R-1 the residual part of dz; the epilogue turns both into dpre.
+      const float* wg = wgate + (size_t)l * 3 * R * (K1 + R);
+      const NtTcSeg sg[4] = {{xin, R, -d, R, wg, 3 * R, K1 + R, 0, 0}, {xin, R, 0, R, wg, 3 * R, K1 + R, R, 0},
+                             {haux, Ap, 0, Ap, wg, 3 * R, K1 + R, 2 * R, 0}, {dout, R, 0, R, wg, 3 * R, K1 + R, K1, 0}};
+      const NtTcOpts o{1, ldz, 1, dout ? 1 : 0};
+      ProfScope ps(WNB_PROF_GATE_BWD, st);
+      if ((rc = gemm_nt_tc(sg, dout ? 4 : 3, dout ? 3 * R : 2 * R, dxin /* z output suppressed */, R,
+                           b1 + (size_t)l * 2 * R, nullptr, 0, nullptr, 0, 0, 0, B, T, st, dzl, dpre, nullptr, 0, 0,
+                           nullptr, &o)) != WNB_OK)
         return rc;
     }
     // dxin = dout + dpre(t+d) W1[:, tap0] + dpre(t) W1[:, tap1]   and   dhaux += dpre(t) W1[:, aux]
     if (dhaux) {
+      ProfScope ps(WNB_PROF_DX_GEMM, st);
       const NtTcSeg sx[2] = {{dpre, 2 * R, d, 2 * R, w1tl, R, 2 * R, 0, 0}, {dpre, 2 * R, 0, 2 * R, w1tl, K1, 2 * R, 0, R}};
       if ((rc = gemm_nt_tc(sx, 2, R + Ap, dxin, R, nullptr, nullptr, 0, dout, R, 0, 0, B, T, st, nullptr, nullptr, dhaux,
                            Ap, R)) != WNB_OK)
         return rc;
     } else {
+      ProfScope ps(WNB_PROF_DX_GEMM, st);
       const NtTcSeg sx[2] = {{dpre, 2 * R, d, 2 * R, w1tl, K1, 2 * R, 0, 0}, {dpre, 2 * R, 0, 2 * R, w1tl, K1, 2 * R, 0, R}};
       if ((rc = gemm_nt_tc(sx, 2, R, dxin, R, nullptr, nullptr, 0, dout, R, 0, 0, B, T, st)) != WNB_OK) return rc;
     }
     {  // dW1 (128 x 160) += dpre^T [x(t-d) | x(t) | aux(t)],  db1 = column sums of dpre
       const WgOperand a[1] = {{dpre, 2 * R, 0, 4, 0}};
       const WgOperand b[3] = {{xin, R, 0, 2, -d}, {xin, R, 0, 2, 0}, {haux, Ap, 0, 1, 0}};
+      ProfScope ps(WNB_PROF_DW1, st);
       if ((rc = wgrad_tc(a, 1, b, 3, dw1 + (size_t)l * 2 * R * K1, K1, 128, db1 + (size_t)l * 2 * R, B, T, st)) != WNB_OK)
         return rc;
     }
@@ -170,6 +177,7 @@ WNB_API int wnb_stack_bwd(const float* xs, const float* haux, const float* zall,
       blk.m_valid = R;
       blk.db = db2res + (size_t)l * R;
       const WgOperand bz[1] = {{zall, ldz, l * R, R / 32, 0}};
+      ProfScope ps(WNB_PROF_DW2RES, st);
       if ((rc = wgrad_tc_blocks(&blk, 1, bz, 1, R, B, T, st)) != WNB_OK) return rc;
     }
     dout = dxin;
@@ -192,6 +200,7 @@ WNB_API int wnb_stack_bwd(const float* xs, const float* haux, const float* zall,
       }
       const WgOperand bz[1] = {{zall, ldz, 0, nB, 0}};
       const WgOpts o{groups / nB};
+      ProfScope ps(WNB_PROF_DWSKIP, st);
       if ((rc = wgrad_tc_blocks(blk, nblk, bz, 1, ldz, B, T, st, &o)) != WNB_OK) return rc;
     }
   }

@@ -29,6 +29,7 @@ struct NtTcOpts {
                      //      mask columns j*N.. (tiles are ordered block-fastest, so the A tile is shared through L2)
   int gate_ld_dz;    // row pitch (floats) of the gate-backward dz input (0: gate_R)
   int gate_skip_z;   // gate-backward: do not write z
+  int gate_fused_dz; // gate-backward shorthand with N == 192: accumulator columns 128..191 are added to dz
 };
 int gemm_nt_tc(const NtTcSeg* segs, int nseg, int N, float* out, int ld_out, const float* bias, const float* mask,
                int ldmask, const float* add, int ldadd, int relu_out, int accumulate, int B, int T, cudaStream_t st,

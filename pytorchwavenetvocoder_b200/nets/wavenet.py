@@ -315,13 +315,15 @@ class _WaveNetStackFn(torch.autograd.Function):
         dWskip, dbskip = z(S, L * R), z(S)
         dhaux = z(B, T, Ap) if ctx.haux_needs_grad else None
         w1t = W1.transpose(1, 2).contiguous()         # (L, K1, 2R)
-        w2rt = W2res.transpose(1, 2).contiguous()     # (L, R, R)  [c][o]
+        wgate = torch.zeros(L, 3 * R, K1 + R, device=dev, dtype=torch.float32)   # [[W1, 0], [0, W2res^T]]
+        wgate[:, :2 * R, :K1] = W1
+        wgate[:, 2 * R:, K1:] = W2res.transpose(1, 2)
         wskt = Wskip.t().contiguous()                 # (L*R, S)
         nbytes = lib.wnb_stack_bwd_workspace(L, B, T, R, S, Ap, ks)
         ws = torch.empty(nbytes // 4, device=dev, dtype=torch.float32)
         dx0 = torch.empty(B, T, R, device=dev, dtype=torch.float32)
         dil = (ctypes.c_int * L)(*[int(d) for d in dilations])
-        check(lib.wnb_stack_bwd(ptr(xs), ptr(haux), ptr(zall), ptr(dskip), ptr(W1), ptr(b1), ptr(w1t), ptr(w2rt),
+        check(lib.wnb_stack_bwd(ptr(xs), ptr(haux), ptr(zall), ptr(dskip), ptr(W1), ptr(b1), ptr(w1t), ptr(wgate),
                                 ptr(wskt), ptr(dx0), ptr(dhaux), ptr(dW1), ptr(db1), ptr(dW2res), ptr(db2res),
                                 ptr(dWskip), ptr(dbskip), ptr(ws), dil, L, B, T, R, S, Ap, ks, st), "stack_bwd")
         del ws

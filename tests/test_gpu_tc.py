@@ -254,3 +254,91 @@ def test_composed_full_model_step_tf32_vs_fp32():
         else:
             tol = 0.10 if g.dim() == 1 else 0.08     # K = 3*128+96 per gate GEMM: a little more tf32 rounding
             assert (g - g2).norm().item() <= tol * g.norm().item() + 1e-7, k
+
+
+# ------------------------------------------------------------------------------------------
+# deferred-skip stack (csrc/stack.cu, resblock_z.cu) against the per-block formulation
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("d,T,last", [(1, 256, False), (8, 1000, False), (512, 2048, False), (4, 300, True)])
+def test_block_z_and_skip_gemm_vs_fp32_block(d, T, last):
+    """wnb_resblock_fwd_z (+ wnb_skip_gemm over a 3-block Z_all whose other slices are zero) reproduces the fp32
+    per-block kernel: xout, and skip = z W2skip^T + b2skip.  Tolerance: the tf32 bound of this file."""
+    from pytorchwavenetvocoder_b200 import _lib
+    lib = _lib.load()
+    torch.manual_seed(d + T)
+    B, R, S, Ap, L, slot = 2, 64, 512, 32, 3, 1
+    K1 = 2 * R + Ap
+    xin = torch.randn(B, T, R, device="cuda")
+    haux = torch.randn(B, T, Ap, device="cuda"); haux[:, :, 28:] = 0
+    W1 = (torch.randn(2 * R, K1, device="cuda") / np.sqrt(K1)).contiguous()
+    W2 = (torch.randn(R + S, R, device="cuda") / np.sqrt(R)).contiguous()
+    b1, b2 = 0.1 * torch.randn(2 * R, device="cuda"), 0.1 * torch.randn(R + S, device="cuda")
+    ref_x, ref_skip = _block(_lib.MATH_FP32, xin, haux, W1, b1, W2, b2, d, None, last)
+    zall = torch.zeros(B, T, L * R, device="cuda")
+    xout = None if last else torch.full_like(xin, float("nan"))
+    w2res, b2res = W2[:R].contiguous(), b2[:R].contiguous()
+    _lib.check(lib.wnb_resblock_fwd_z(_lib.ptr(xin), _lib.ptr(haux), _lib.ptr(W1), _lib.ptr(b1), _lib.ptr(w2res),
+                                      _lib.ptr(b2res), _lib.ptr(xout), _lib.ptr(zall), L * R, slot * R, B, T, R, Ap, 2,
+                                      d, _lib.stream()), "resblock_fwd_z")
+    wskip = torch.zeros(S, L * R, device="cuda")
+    wskip[:, slot * R:(slot + 1) * R] = W2[R:]
+    bskip = b2[R:].contiguous()
+    skip = torch.full((B, T, S), float("nan"), device="cuda")
+    _lib.check(lib.wnb_skip_gemm(_lib.ptr(zall), _lib.ptr(wskip), _lib.ptr(bskip), _lib.ptr(skip), B, T, L * R, S,
+                                 _lib.stream()), "skip_gemm")
+    torch.cuda.synchronize()
+    assert torch.all(zall[:, :, :slot * R] == 0) and torch.all(zall[:, :, (slot + 1) * R:] == 0)   # only its slice
+    if not last:
+        assert (xout - ref_x).abs().max().item() <= 4e-3 * ref_x.abs().max().item()
+    assert (skip - ref_skip).abs().max().item() <= 4e-3 * ref_skip.abs().max().item()
+
+
+def test_deferred_skip_stack_matches_per_block_training_step():
+    """Same model, same batch: WaveNet.forward/backward through the deferred-skip stack (one ABI call per
+    direction) vs the per-block tf32 path.  Both are tf32; they differ only in summation order, so logits agree to
+    2e-3 abs and every gradient to 3 % (relative Frobenius norm; bias gradients 5 %) -- the gradients at the bottom
+    of the stack carry the tf32 rounding of every block above them in both runs."""
+    from pytorchwavenetvocoder_b200.nets import cross_entropy
+    cfg = O.Config(256, 28, 64, 512, 5, 2, 2, 16)
+    p = O.make_params(cfg, 21)
+    rng = np.random.RandomState(4)
+    B, T = 3, 1040                       # not a multiple of the 128-row tile
+    x = torch.from_numpy(rng.randint(0, 256, size=(B, T)).astype(np.int64)).cuda()
+    t = torch.from_numpy(rng.randint(0, 256, size=(B, T)).astype(np.int64)).cuda()
+    h = torch.from_numpy(rng.standard_normal((B, 28, T // 16)).astype(np.float32)).cuda()
+    res = {}
+    for deferred in (False, True):
+        net = our_model(cfg, p, math_mode="tf32").train()
+        net.deferred_skip = deferred
+        y = net(x, h)
+        loss = cross_entropy(y, t, 32)
+        loss.backward()
+        res[deferred] = (y.detach().clone(), loss.item(),
+                         {k: (None if v.grad is None else v.grad.clone()) for k, v in net.named_parameters()})
+    assert (res[True][0] - res[False][0]).abs().max().item() <= 2e-3
+    assert abs(res[True][1] - res[False][1]) < 2e-4
+    for k, g in res[False][2].items():
+        g2 = res[True][2][k]
+        assert (g is None) == (g2 is None), k          # the last block's res_1x1 has no gradient in either form
+        if g is None:
+            continue
+        if g.numel() == 1:
+            assert (g - g2).abs().item() <= 3e-3, k
+        else:
+            tol = 0.05 if g.dim() == 1 else 0.03
+            assert (g - g2).norm().item() <= tol * g.norm().item() + 1e-7, (k, (g - g2).norm().item(), g.norm().item())
+
+
+def test_deferred_skip_inference_ping_pong():
+    """No-grad forward uses two residual buffers (nxs = 2) instead of L: same logits as the training-mode forward."""
+    cfg = O.Config(256, 28, 64, 256, 4, 2, 2, 0)
+    p = O.make_params(cfg, 2)
+    rng = np.random.RandomState(9)
+    B, T = 2, 700
+    x = torch.from_numpy(rng.randint(0, 256, size=(B, T)).astype(np.int64)).cuda()
+    h = torch.from_numpy(rng.standard_normal((B, 28, T)).astype(np.float32)).cuda()
+    net = our_model(cfg, p, math_mode="tf32")
+    with torch.no_grad():
+        y0 = net(x, h)
+    y1 = net.train()(x, h)
+    assert torch.equal(y0, y1.detach())
