@@ -129,18 +129,19 @@ WNB_API int wnb_resblock_fwd_z(const float* xin, const float* haux, const float*
                                const float* w2res, const float* b2res, float* xout, float* zall, int ldz, int zcol0,
                                int B, int T, int R, int Ap, int ks, int dilation, void* stream);
 
-/* skip (B,T,S) = zall (B,T,K) wskip^T + bskip;  wskip (S,K) row-major, bskip (S) or NULL */
+/* skip (B,T,S) = zall (B,T,K) wskip^T + bskip (relu != 0: rectified, the form wnb_post_fwd consumes);
+ * wskip (S,K) row-major, bskip (S) or NULL */
 WNB_API int wnb_skip_gemm(const float* zall, const float* wskip, const float* bskip, float* skip, int B, int T,
-                          int K, int S, void* stream);
+                          int K, int S, int relu, void* stream);
 
 /* whole stack: xs (nxs,B,T,R) holds the block inputs, xs[0] filled by the caller (wnb_front_embed_fwd); block l reads
  * xs[l % nxs] and writes xs[(l+1) % nxs] (nxs = L keeps every input for the backward, nxs = 2 ping-pongs).
  * w1 (L,2R,K1), b1 (L,2R), w2res (L,R,R), b2res (L,R), wskip (S,L*R), bskip (S); dilations: L host ints.
- * Outputs zall (B,T,L*R) and skip (B,T,S). */
+ * Outputs zall (B,T,L*R) and skip (B,T,S) (rectified when skip_relu != 0). */
 WNB_API int wnb_stack_fwd(float* xs, int nxs, const float* haux, const float* w1, const float* b1,
                           const float* w2res, const float* b2res, const float* wskip, const float* bskip,
                           float* zall, float* skip, const int* dilations, int L, int B, int T, int R, int S,
-                          int Ap, int ks, void* stream);
+                          int Ap, int ks, int skip_relu, void* stream);
 
 /* backward of wnb_stack_fwd.  xs (L,B,T,R) and zall from the forward; dskip (B,T,S) = d loss / d skip.
  * w1t (L,K1,2R) as for wnb_resblock_bwd; wgate (L,3R,K1+R) = block matrix [[w1, 0], [0, w2res^T]] per block (gate
@@ -173,10 +174,11 @@ WNB_API int wnb_resblock_bwd(const float* xin, const float* haux, const float* d
 /* ---- a11: post network (wavenet.py:518-523) -------------------------------------------------
  * logits (B,T,Q) = wp2 * relu(wp1 * relu(skip) + bp1) + bp2 ; r1 (B,T,S) = relu(h1) is kept (needed by the
  * backward).  With WNB_MATH_TF32 `skip` is rectified IN PLACE first (its sign pattern -- all that
- * wnb_post_bwd needs from it -- is unchanged; wnb_post_bwd in tf32 mode relies on it). */
+ * wnb_post_bwd needs from it -- is unchanged; wnb_post_bwd in tf32 mode relies on it); skip_rectified != 0
+ * (tf32 only) says the producer already did that (wnb_skip_gemm / wnb_stack_fwd with relu) and skips the pass. */
 WNB_API int wnb_post_fwd(float* skip, const float* wp1, const float* bp1, const float* wp2,
                  const float* bp2, float* r1, float* logits, int B, int T, int S, int Q,
-                 int math_mode, void* stream);
+                 int math_mode, int skip_rectified, void* stream);
 /* dskip (B,T,S) out; dwp1,dbp1,dwp2,dbp2 accumulated into; workspace (B,T,S) floats */
 WNB_API int wnb_post_bwd(const float* skip, const float* r1, const float* dlogits, const float* wp1t /*(S,S) [c][o]*/,
                  const float* wp2t /*(S,Q) [c][o]*/, float* dskip, float* dwp1, float* dbp1, float* dwp2,

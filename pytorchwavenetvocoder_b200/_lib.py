@@ -42,13 +42,13 @@ SIGNATURES = {
     "wnb_profile_read": (_I, [_I, _P, _P]),
     "wnb_stack_supported": (_I, [_I] * 6),
     "wnb_resblock_fwd_z": (_I, [_P] * 8 + [_I] * 8 + [_P]),
-    "wnb_skip_gemm": (_I, [_P] * 4 + [_I] * 4 + [_P]),
-    "wnb_stack_fwd": (_I, [_P, _I] + [_P] * 10 + [_I] * 7 + [_P]),
+    "wnb_skip_gemm": (_I, [_P] * 4 + [_I] * 5 + [_P]),
+    "wnb_stack_fwd": (_I, [_P, _I] + [_P] * 10 + [_I] * 8 + [_P]),
     "wnb_stack_bwd_workspace": (_c.c_size_t, [_I] * 7),
     "wnb_stack_bwd": (_I, [_P] * 19 + [_I] * 7 + [_P]),
     "wnb_resblock_bwd_workspace": (_c.c_size_t, [_I] * 6),
     "wnb_resblock_bwd": (_I, [_P] * 15 + [_I] * 8 + [_P]),
-    "wnb_post_fwd": (_I, [_P] * 7 + [_I] * 5 + [_P]),
+    "wnb_post_fwd": (_I, [_P] * 7 + [_I] * 6 + [_P]),
     "wnb_post_bwd": (_I, [_P] * 11 + [_I] * 5 + [_P]),
     "wnb_cross_entropy": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "wnb_decode_workspace": (_c.c_size_t, [_I, _I, _I, _P, _I]),

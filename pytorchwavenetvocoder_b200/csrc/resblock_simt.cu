@@ -378,6 +378,34 @@ static int wgrad_tc_full(const float* a, int CA, int M, const float* b, int CB, 
   return WNB_OK;
 }
 
+// C (M x N, ldc) += A^T B, db (M) += colsum A, with A = channels [0, M) of a (CA), B = channels [0, N) of b (CB):
+// up to 4 M-blocks per launch (their accumulators share TMEM) and the N axis split into column groups handled by
+// different CTAs (WgOpts::n_split), so a 512 x 512 gradient is ONE launch that streams A and B once from HBM.
+static int wgrad_tc_split(const float* a, int CA, int M, const float* b, int CB, int N, float* c, int ldc, float* db,
+                          int B, int T, cudaStream_t st) {
+  int rc;
+  for (int m0 = 0; m0 < M; m0 += 512) {
+    WgBlock blk[4];
+    int nblk = 0;
+    for (int m = m0; m < M && nblk < 4; m += 128, nblk++) {
+      blk[nblk].nops = 1;
+      blk[nblk].ops[0] = WgOperand{a, CA, m, 4, 0};
+      blk[nblk].c = c + (size_t)m * ldc;
+      blk[nblk].m_valid = (M - m) < 128 ? (M - m) : 128;
+      blk[nblk].db = db ? db + m : nullptr;
+    }
+    const int groups = N / 32, budget = 512 / nblk / 32 - (db ? 1 : 0);
+    int nB = 0;
+    for (int g = budget < 7 ? budget : 7; g >= 1 && !nB; g--)
+      if (groups % g == 0) nB = g;
+    if (!nB || groups / nB > 128) return wgrad_tc_full(a, CA, M, b, CB, N, c, ldc, db, B, T, st);
+    const WgOperand bo[1] = {{b, CB, 0, nB, 0}};
+    const WgOpts o{groups / nB};
+    if ((rc = wgrad_tc_blocks(blk, nblk, bo, 1, ldc, B, T, st, &o)) != WNB_OK) return rc;
+  }
+  return WNB_OK;
+}
+
 // Weight gradient with A = the channel concatenation [a0 (C0) | a1 (C1)] (a1 may be null), M = rows used,
 // B = channels [0, N) of tensor b (CB channels) read at time t + shift:  C (M x N, ldc) += A^T B, db (M) += colsum A.
 // M-blocks of 128 rows are batched per launch as far as TMEM allows; N goes in chunks of <= 224 columns.
@@ -680,7 +708,8 @@ WNB_API int wnb_resblock_bwd(const float* xin, const float* haux, const float* d
 }
 
 WNB_API int wnb_post_fwd(float* skip, const float* wp1, const float* bp1, const float* wp2, const float* bp2,
-                 float* r1, float* logits, int B, int T, int S, int Q, int math_mode, void* stream) {
+                 float* r1, float* logits, int B, int T, int S, int Q, int math_mode, int skip_rectified,
+                 void* stream) {
   WNB_REQUIRE(B > 0 && T > 0 && S > 0 && Q > 0, "post_fwd: bad shape");
   WNB_REQUIRE(skip && wp1 && bp1 && wp2 && bp2 && r1 && logits, "post_fwd: null pointer (r1 scratch is required)");
   cudaStream_t st = (cudaStream_t)stream;
@@ -689,13 +718,16 @@ WNB_API int wnb_post_fwd(float* skip, const float* wp1, const float* bp1, const 
     // rectify the skip sum in place (its sign pattern, all the backward needs, is unchanged), then two
     // tensor-core GEMMs with fused bias / ReLU epilogues
     const int64_t n4 = (int64_t)B * T * S / 4;
-    relu_inplace_kernel<<<148 * 8, 256, 0, st>>>(reinterpret_cast<float4*>(skip), n4);
-    WNB_CHECK_LAUNCH("relu_inplace");
+    if (!skip_rectified) {
+      relu_inplace_kernel<<<148 * 8, 256, 0, st>>>(reinterpret_cast<float4*>(skip), n4);
+      WNB_CHECK_LAUNCH("relu_inplace");
+    }
     const NtTcSeg s1[1] = {{skip, S, 0, S, wp1, S, S, 0, 0}};
     if ((rc = gemm_nt_tc(s1, 1, S, r1, S, bp1, nullptr, 0, nullptr, 0, 1, 0, B, T, st)) != WNB_OK) return rc;
     const NtTcSeg s2[1] = {{r1, S, 0, S, wp2, Q, S, 0, 0}};
     return gemm_nt_tc(s2, 1, Q, logits, Q, bp2, nullptr, 0, nullptr, 0, 0, 0, B, T, st);
   }
+  WNB_REQUIRE(!skip_rectified, "post_fwd: skip_rectified is a tf32-path option");
   {  // r1 = relu(wp1 * relu(skip) + bp1)
     NtParams p{};
     p.nseg = 1; p.seg[0] = NtSeg{wp1, S, skip, S, 0, S};
@@ -726,8 +758,8 @@ WNB_API int wnb_post_bwd(const float* skip, const float* r1, const float* dlogit
     if ((rc = gemm_nt_tc(s1, 1, S, dh1, S, nullptr, r1, S, nullptr, 0, 0, 0, B, T, st)) != WNB_OK) return rc;
     const NtTcSeg s2[1] = {{dh1, S, 0, S, wp1t, S, S, 0, 0}};
     if ((rc = gemm_nt_tc(s2, 1, S, dskip, S, nullptr, skip, S, nullptr, 0, 0, 0, B, T, st)) != WNB_OK) return rc;
-    if ((rc = wgrad_tc_full(dlogits, Q, Q, r1, S, S, dwp2, S, dbp2, B, T, st)) != WNB_OK) return rc;
-    return wgrad_tc_full(dh1, S, S, skip, S, S, dwp1, S, dbp1, B, T, st);
+    if ((rc = wgrad_tc_split(dlogits, Q, Q, r1, S, S, dwp2, S, dbp2, B, T, st)) != WNB_OK) return rc;
+    return wgrad_tc_split(dh1, S, S, skip, S, S, dwp1, S, dbp1, B, T, st);
   }
   {  // dh1[t][c] = (sum_q wp2[q][c] dlogits[t][q]) * (r1 > 0)
     NtParams p{};

@@ -56,16 +56,17 @@ WNB_API int wnb_resblock_fwd_z(const float* xin, const float* haux, const float*
 }
 
 WNB_API int wnb_skip_gemm(const float* zall, const float* wskip, const float* bskip, float* skip, int B, int T, int K,
-                          int S, void* stream) {
+                          int S, int relu, void* stream) {
   WNB_REQUIRE(zall && wskip && skip && B > 0 && T > 0 && K % 32 == 0 && S % 32 == 0 && (S <= 256 || S == 512),
               "skip_gemm: bad arguments");
   const NtTcSeg seg[1] = {{zall, K, 0, K, wskip, S, K, 0, 0}};
-  return gemm_nt_tc(seg, 1, S, skip, S, bskip, nullptr, 0, nullptr, 0, 0, 0, B, T, (cudaStream_t)stream);
+  return gemm_nt_tc(seg, 1, S, skip, S, bskip, nullptr, 0, nullptr, 0, relu ? 1 : 0, 0, B, T, (cudaStream_t)stream);
 }
 
 WNB_API int wnb_stack_fwd(float* xs, int nxs, const float* haux, const float* w1, const float* b1, const float* w2res,
                           const float* b2res, const float* wskip, const float* bskip, float* zall, float* skip,
-                          const int* dilations, int L, int B, int T, int R, int S, int Ap, int ks, void* stream) {
+                          const int* dilations, int L, int B, int T, int R, int S, int Ap, int ks, int skip_relu,
+                          void* stream) {
   WNB_REQUIRE(xs && haux && w1 && b1 && w2res && b2res && wskip && bskip && zall && skip && dilations,
               "stack_fwd: null pointer");
   WNB_REQUIRE(B > 0 && T > 0 && L >= 1 && nxs >= (L > 1 ? 2 : 1), "stack_fwd: bad shape");
@@ -87,7 +88,7 @@ WNB_API int wnb_stack_fwd(float* xs, int nxs, const float* haux, const float* w1
       return rc;
   }
   ProfScope ps(WNB_PROF_SKIP_GEMM, st);
-  return wnb_skip_gemm(zall, wskip, bskip, skip, B, T, ldz, S, stream);
+  return wnb_skip_gemm(zall, wskip, bskip, skip, B, T, ldz, S, skip_relu, stream);
 }
 
 // workspace: dZ_all (B,T,L*R) [+ one row of slack] | dpre (B,T,2R) | two (B,T,R) gradient buffers

@@ -197,7 +197,7 @@ class _WaveNetFn(torch.autograd.Function):
         r1 = torch.empty(B, T, S, device=dev, dtype=torch.float32)
         logits = torch.empty(B, T, Q, device=dev, dtype=torch.float32)
         check(lib.wnb_post_fwd(ptr(skip), ptr(Wp1), ptr(bp1), ptr(Wp2), ptr(bp2), ptr(r1), ptr(logits),
-                               B, T, S, Q, math_mode, st), "post_fwd")
+                               B, T, S, Q, math_mode, 0, st), "post_fwd")
         if need_grad:
             ctx.save_for_backward(x, haux, wf, W1, b1, W2, Wp1, Wp2, xs, skip, r1)
             ctx.meta = meta
@@ -269,7 +269,7 @@ class _WaveNetStackFn(torch.autograd.Function):
         prof = PROFILE_EVENTS
         if prof is None:
             check(lib.wnb_stack_fwd(ptr(xs), nbuf, ptr(haux), ptr(W1), ptr(b1), ptr(W2res), ptr(b2res), ptr(Wskip),
-                                    ptr(bskip), ptr(zall), ptr(skip), dil, L, B, T, R, S, Ap, ks, st), "stack_fwd")
+                                    ptr(bskip), ptr(zall), ptr(skip), dil, L, B, T, R, S, Ap, ks, 1, st), "stack_fwd")
         else:   # same launches, one ABI call per block so that each can be bracketed by CUDA events
             for l, d in enumerate(dilations):
                 xout = xs[(l + 1) % nbuf] if l + 1 < L else None
@@ -280,11 +280,11 @@ class _WaveNetStackFn(torch.autograd.Function):
                                              int(d), st), "resblock_fwd_z")
                 ev[1].record()
                 prof.append(ev)
-            check(lib.wnb_skip_gemm(ptr(zall), ptr(Wskip), ptr(bskip), ptr(skip), B, T, L * R, S, st), "skip_gemm")
+            check(lib.wnb_skip_gemm(ptr(zall), ptr(Wskip), ptr(bskip), ptr(skip), B, T, L * R, S, 1, st), "skip_gemm")
         r1 = torch.empty(B, T, S, device=dev, dtype=torch.float32)
         logits = torch.empty(B, T, Q, device=dev, dtype=torch.float32)
         check(lib.wnb_post_fwd(ptr(skip), ptr(Wp1), ptr(bp1), ptr(Wp2), ptr(bp2), ptr(r1), ptr(logits),
-                               B, T, S, Q, math_mode, st), "post_fwd")
+                               B, T, S, Q, math_mode, 1, st), "post_fwd")
         if need_grad:
             ctx.save_for_backward(x, haux, wf, W1, b1, W2res, Wskip, Wp1, Wp2, xs, zall, skip, r1)
             ctx.meta = meta

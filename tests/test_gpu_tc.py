@@ -284,7 +284,7 @@ def test_block_z_and_skip_gemm_vs_fp32_block(d, T, last):
     wskip[:, slot * R:(slot + 1) * R] = W2[R:]
     bskip = b2[R:].contiguous()
     skip = torch.full((B, T, S), float("nan"), device="cuda")
-    _lib.check(lib.wnb_skip_gemm(_lib.ptr(zall), _lib.ptr(wskip), _lib.ptr(bskip), _lib.ptr(skip), B, T, L * R, S,
+    _lib.check(lib.wnb_skip_gemm(_lib.ptr(zall), _lib.ptr(wskip), _lib.ptr(bskip), _lib.ptr(skip), B, T, L * R, S, 0,
                                  _lib.stream()), "skip_gemm")
     torch.cuda.synchronize()
     assert torch.all(zall[:, :, :slot * R] == 0) and torch.all(zall[:, :, (slot + 1) * R:] == 0)   # only its slice
