@@ -19,6 +19,26 @@ struct ProfScope {
   ~ProfScope() { prof_end(kind, st); }
 };
 
+// Launch with programmatic stream serialization (PDL): the kernel may become resident while its predecessor in the
+// stream drains; it must call ptx::pdl_wait() before touching global memory (all kernels launched this way do).
+// WNB_PDL=0 in the environment turns the attribute off.
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t st,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 #define WNB_REQUIRE(cond, ...)            \
   do {                                    \
     if (!(cond)) {                        \

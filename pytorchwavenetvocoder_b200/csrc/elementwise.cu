@@ -3,6 +3,7 @@
 // float4 where the row width allows, grids sized in multiples of the SM count by grid-stride loops.
 #include <math.h>
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include <atomic>
 #include <vector>
@@ -21,6 +22,11 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 void count_launch(int n) { g_launches.fetch_add(n); }
+bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("WNB_PDL"); on = (e && e[0] == '0') ? 0 : 1; }
+  return on == 1;
+}
 
 // ---- per-launch event timing (off by default; bench.py switches it on for the timed region) ----
 struct ProfRec { int kind; cudaEvent_t e0, e1; };

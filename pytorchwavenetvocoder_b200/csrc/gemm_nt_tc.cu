@@ -101,6 +101,10 @@ __global__ void __launch_bounds__(kThreadsN, 1) gemm_nt_tc_kernel(const __grid_c
   ptx::tc_fence_after();
   ptx::tmem_base_must_be_zero(*tmem_slot);
   constexpr uint32_t tmem = 0;
+  // programmatic dependent launch: the set-up above overlapped the previous kernel's tail; from here on this
+  // kernel reads / writes memory that kernel may have produced
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
 
   // single-thread roles are entered through elect.sync (not `lane == 0`): the compiler then knows exactly one
   // thread is active and issues the uniform-datapath TMA / tcgen05 instructions without a per-thread ELECT loop
@@ -527,7 +531,7 @@ int gemm_nt_tc(const NtTcSeg* segs, int nseg, int N, float* out, int ld_out, con
             h[5] / 1e3 / grid, h[6] / 1e3 / grid, h[7] / 1e3, h[8] / 1e3);
     return WNB_OK;
   }
-  gemm_nt_tc_kernel<false><<<grid, kThreadsN, smem, st>>>(p);
+  if (launch_pdl(gemm_nt_tc_kernel<false>, grid, kThreadsN, smem, st, p) != cudaSuccess) { /* reported below */ }
   WNB_CHECK_LAUNCH("gemm_nt_tc");
   return WNB_OK;
 }

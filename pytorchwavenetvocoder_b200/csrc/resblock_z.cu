@@ -92,6 +92,10 @@ resblock_fwd_z_kernel(const __grid_constant__ Maps maps, const float* __restrict
   ptx::tc_fence_after();
   ptx::tmem_base_must_be_zero(*tmem_slot);
   constexpr uint32_t tmem = 0;
+  // programmatic dependent launch: the set-up above overlapped the previous kernel's tail; from here on this
+  // kernel reads / writes memory that kernel may have produced
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
 
   if (warp == 0) {
     // =============================== TMA producer: activation tiles ===============================
@@ -357,7 +361,8 @@ int resblock_fwd_z(const float* xin, const float* haux, const float* w1, const f
   }
   const int ntiles = B * ((T + kTM - 1) / kTM);
   const int grid = ntiles < sms ? ntiles : sms;
-  resblock_fwd_z_kernel<<<grid, kThreadsZ, kSmemBytes, st>>>(maps, b1, b2res ? b2res : b1, B, T, d, xout ? 1 : 0, zcol0);
+  if (launch_pdl(resblock_fwd_z_kernel, grid, kThreadsZ, kSmemBytes, st, maps, b1, b2res ? b2res : b1, B, T, d,
+                 xout ? 1 : 0, zcol0) != cudaSuccess) { /* reported below */ }
   WNB_CHECK_LAUNCH("resblock_fwd_z");
   return WNB_OK;
 }

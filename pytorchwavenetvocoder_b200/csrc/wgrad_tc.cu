@@ -119,6 +119,10 @@ __global__ void __launch_bounds__(kThreadsW, 1) wgrad_tc_kernel(const __grid_con
   ptx::tc_fence_after();
   ptx::tmem_base_must_be_zero(*tmem_slot);
   constexpr uint32_t tmem = 0;
+  // programmatic dependent launch: the set-up above overlapped the previous kernel's tail; from here on this
+  // kernel reads / writes memory that kernel may have produced
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
 
   // single-thread roles are entered through elect.sync (not `lane == 0`): the compiler then knows exactly one
   // thread is active and issues the uniform-datapath TMA / tcgen05 instructions without a per-thread ELECT loop
@@ -352,7 +356,7 @@ int wgrad_tc_blocks(const WgBlock* blocks, int nblocks, const WgOperand* b_ops, 
             h[0] / 1e3 / grid, h[1] / 1e3 / grid, h[2] / 1e3 / grid, h[3] / 1e3 / grid, h[4] / 1e3, h[5] / 1e3);
     return WNB_OK;
   }
-  wgrad_tc_kernel<false><<<grid, kThreadsW, smem, st>>>(p);
+  if (launch_pdl(wgrad_tc_kernel<false>, grid, kThreadsW, smem, st, p) != cudaSuccess) { /* reported below */ }
   WNB_CHECK_LAUNCH("wgrad_tc");
   return WNB_OK;
 }
