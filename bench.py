@@ -259,8 +259,9 @@ def run_ours(args):
             # fp32 channels-last tensors, each streamed once; weights (<= 4 MB) not counted
             bt4, Ap, LR = float(Bq) * T * 4, net.n_aux_pad, L * R
             alg = {"fwd_block": bt4 * (3 * R + Ap), "skip_gemm": bt4 * (LR + S), "dzall_gemm": bt4 * (S + LR),
-                   "gate_bwd": bt4 * (5 * R + Ap), "dx_gemm": bt4 * (4 * R + 2 * Ap), "dw1": bt4 * (3 * R + Ap),
-                   "dw2res": bt4 * 2 * R, "dwskip": bt4 * (S + LR)}
+                   "gate_bwd": bt4 * (5 * R + Ap), "dx_gemm": bt4 * (4 * R + 2 * Ap),
+                   # every block's dW1 / dW2res in ONE segmented launch each (dpre_l, x_l, aux | dout_l, z_l)
+                   "dw1": L * bt4 * (3 * R + Ap), "dw2res": (L - 1) * bt4 * 2 * R, "dwskip": bt4 * (S + LR)}
             roof_all = []
             for name, tot, n in kinds:
                 if n == 0:

@@ -9,8 +9,8 @@
 //   forward    z_l -> Z_all[:, :, l*R:(l+1)*R]     (resblock_z.cu writes the slice)
 //              skip  = Z_all Wskip^T + bskip        one NT GEMM, K = L*R          (Wskip[s][l*R+c] = W2_l[R+s][c])
 //   backward   dZ_all = dskip Wskip                  one NT GEMM, N = L*R in column blocks (A tile shared via L2)
-//              per block: gate recompute + dz_l = dZ_all[l] + dout W2res_l + gate backward (one GEMM) ; dx ; dW1 ;
-//              dW2res_l
+//              per block: gate recompute + dz_l = dZ_all[l] + dout W2res_l + gate backward (one GEMM) ; dx
+//              dW1_l, dW2res_l of ALL blocks: one segmented weight-gradient launch each (dpre_l, dx_l are kept)
 //              dWskip = dskip^T Z_all                one weight-gradient GEMM, column groups of Z_all across CTAs
 //
 // Z_all is written once and read twice per step (it replaces the z recompute output of the per-block backward).
@@ -91,11 +91,14 @@ WNB_API int wnb_stack_fwd(float* xs, int nxs, const float* haux, const float* w1
   return wnb_skip_gemm(zall, wskip, bskip, skip, B, T, ldz, S, skip_relu, stream);
 }
 
-// workspace: dZ_all (B,T,L*R) [+ one row of slack] | dpre (B,T,2R) | two (B,T,R) gradient buffers
+// workspace: dZ_all (B,T,L*R) [+ one row of slack] | dpre of every block (L,B,T,2R) | dx of every block (L,B,T,R).
+// dpre / dx of ALL blocks are kept so that the weight gradients dW1_l, dW2res_l of the whole stack are two launches at
+// the end instead of 2L small ones inside the block loop (each of those spent a third of its time on launch, set-up
+// and the atomic flush).
 WNB_API size_t wnb_stack_bwd_workspace(int L, int B, int T, int R, int S, int Ap, int ks) {
   (void)S; (void)Ap; (void)ks;
   const size_t bt = (size_t)B * T;
-  return sizeof(float) * (bt * L * R + (size_t)L * R + bt * 2 * R + 2 * bt * R);
+  return sizeof(float) * (bt * L * R + (size_t)L * R + (size_t)L * bt * 2 * R + (size_t)L * bt * R);
 }
 
 WNB_API int wnb_stack_bwd(const float* xs, const float* haux, const float* zall, const float* dskip, const float* w1,
@@ -115,8 +118,9 @@ WNB_API int wnb_stack_bwd(const float* xs, const float* haux, const float* zall,
   const size_t bt = (size_t)B * T, xsz = bt * R;
   const int K1 = ks * R + Ap, ldz = L * R;
   float* dzall = (float*)workspace;
-  float* dpre = dzall + bt * ldz + ldz;
-  float* dbuf[2] = {dpre + bt * 2 * R, dpre + bt * 2 * R + xsz};
+  float* dpre_all = dzall + bt * ldz + ldz;                 // (L, B, T, 2R)
+  float* dx_all = dpre_all + (size_t)L * bt * 2 * R;        // (L, B, T, R); slot 0 unused (block 0 writes dx0)
+  WNB_REQUIRE(L <= 64, "stack_bwd: at most 64 blocks");
   int rc;
 
   {  // dZ_all = dskip Wskip   (wskip_t: rows n = l*R + c, K = S contiguous)
@@ -137,7 +141,8 @@ WNB_API int wnb_stack_bwd(const float* xs, const float* haux, const float* zall,
     const float* xin = xs + (size_t)l * xsz;
     const float* w1tl = w1t + (size_t)l * K1 * 2 * R;
     float* dzl = dzall + (size_t)l * R;          // (B,T,R) view with row pitch ldz
-    float* dxin = (l == 0) ? dx0 : dbuf[l & 1];
+    float* dxin = (l == 0) ? dx0 : dx_all + (size_t)l * xsz;
+    float* dpre = dpre_all + (size_t)l * bt * 2 * R;
     {  // gate recompute (pre = W1 [x(t-d) | x(t) | aux]) and dz_l = dZ_all[l] + dout W2res_l in ONE GEMM over the block
        // matrix wgate_l = [[W1, 0], [0, W2res^T]] (3R x (K1+R)): accumulator columns 0..2R-1 are the gate
        // pre-activations, columns 2R..3R-1 the residual part of dz; the epilogue turns both into dpre.
@@ -163,25 +168,32 @@ WNB_API int wnb_stack_bwd(const float* xs, const float* haux, const float* zall,
       const NtTcSeg sx[2] = {{dpre, 2 * R, d, 2 * R, w1tl, K1, 2 * R, 0, 0}, {dpre, 2 * R, 0, 2 * R, w1tl, K1, 2 * R, 0, R}};
       if ((rc = gemm_nt_tc(sx, 2, R, dxin, R, nullptr, nullptr, 0, dout, R, 0, 0, B, T, st)) != WNB_OK) return rc;
     }
-    {  // dW1 (128 x 160) += dpre^T [x(t-d) | x(t) | aux(t)],  db1 = column sums of dpre
-      const WgOperand a[1] = {{dpre, 2 * R, 0, 4, 0}};
-      const WgOperand b[3] = {{xin, R, 0, 2, -d}, {xin, R, 0, 2, 0}, {haux, Ap, 0, 1, 0}};
-      ProfScope ps(WNB_PROF_DW1, st);
-      if ((rc = wgrad_tc(a, 1, b, 3, dw1 + (size_t)l * 2 * R * K1, K1, 128, db1 + (size_t)l * 2 * R, B, T, st)) != WNB_OK)
-        return rc;
-    }
-    if (dout) {  // dW2res_l (R x R) += dout^T z_l, db2res_l = column sums of dout (rows 64..127 of the block: zero fill)
-      WgBlock blk;
-      blk.nops = 1;
-      blk.ops[0] = WgOperand{dout, R, 0, 4, 0};
-      blk.c = dw2res + (size_t)l * R * R;
-      blk.m_valid = R;
-      blk.db = db2res + (size_t)l * R;
-      const WgOperand bz[1] = {{zall, ldz, l * R, R / 32, 0}};
-      ProfScope ps(WNB_PROF_DW2RES, st);
-      if ((rc = wgrad_tc_blocks(&blk, 1, bz, 1, R, B, T, st)) != WNB_OK) return rc;
-    }
     dout = dxin;
+  }
+
+  int seg_shift[64];
+  for (int l = 0; l < L; l++) seg_shift[l] = -dilations[l];
+  {  // every block's dW1 (128 x 160) += dpre_l^T [x_l(t-d_l) | x_l(t) | aux(t)], db1 = column sums of dpre_l: one launch
+    WgBlock blk;
+    blk.nops = 1;
+    blk.ops[0] = WgOperand{dpre_all, 2 * R, 0, 4, 0, WG_LAYERED, 0};
+    blk.c = dw1; blk.m_valid = 128; blk.db = db1;
+    const WgOperand b[3] = {{xs, R, 0, 2, 0, WG_LAYERED | WG_SEG_SHIFT, 0}, {xs, R, 0, 2, 0, WG_LAYERED, 0},
+                            {haux, Ap, 0, 1, 0, 0, 0}};
+    const WgOpts o{1, L, seg_shift, 2 * R * K1, 2 * R};
+    ProfScope ps(WNB_PROF_DW1, st);
+    if ((rc = wgrad_tc_blocks(&blk, 1, b, 3, K1, B, T, st, &o)) != WNB_OK) return rc;
+  }
+  if (L > 1) {  // every block's dW2res (R x R) += dout_l^T z_l with dout_l = dx_{l+1} (rows 64..127 of the M-block: TMA
+                // zero fill), db2res = column sums of dout_l; the last block has no residual output, hence L-1 segments
+    WgBlock blk;
+    blk.nops = 1;
+    blk.ops[0] = WgOperand{dx_all + xsz, R, 0, 4, 0, WG_LAYERED, 0};
+    blk.c = dw2res; blk.m_valid = R; blk.db = db2res;
+    const WgOperand bz[1] = {{zall, ldz, 0, R / 32, 0, 0, R}};
+    const WgOpts o{1, L - 1, seg_shift, R * R, R};
+    ProfScope ps(WNB_PROF_DW2RES, st);
+    if ((rc = wgrad_tc_blocks(&blk, 1, bz, 1, R, B, T, st, &o)) != WNB_OK) return rc;
   }
 
   {  // dWskip (S x L*R) += dskip^T Z_all, dbskip = column sums of dskip

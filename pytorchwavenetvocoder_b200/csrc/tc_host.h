@@ -6,13 +6,19 @@ namespace wnb {
 
 // ---- weight gradients (wgrad_tc.cu):  C_i[128 x N] += A_i^T B  over all (b, t) --------------------------------
 // One operand = a channels-last tensor (B,T,C); `groups` 32-channel groups starting at channel c0, shifted in time.
-struct WgOperand { const float* base; int C; int c0; int groups; int shift; };
+enum { WG_LAYERED = 1,     // segment mode: the tensor is (nseg*B, T, C); segment i reads batches i*B ..
+       WG_SEG_SHIFT = 2 }; // segment mode: time shift = WgOpts::seg_shift[i] instead of `shift`
+struct WgOperand { const float* base; int C; int c0; int groups; int shift; int flags; int seg_cstride; };
+// (seg_cstride: segment mode, channel offset added per segment -- a block's slice of a concatenated tensor)
 // One M-block: 128 output rows = 4 groups taken from up to 2 operands (TMA zero fill past a tensor's channels).
 struct WgBlock { WgOperand ops[2]; int nops; float* c; int m_valid; float* db; };
 // n_split > 1: the B operand holds n_split consecutive column groups of 32*sum(groups_b) channels each; CTA
 // (g, s) = (blockIdx % n_split, blockIdx / n_split) accumulates column group g over time split s, so that the A
 // operand (read by every group) is shared through L2.  Bias gradients are flushed by group 0 only.
-struct WgOpts { int n_split; };
+// nseg > 1: nseg independent problems of identical structure in one launch (every residual block's dW1, say):
+// operands pick their per-segment batch / shift / channel offsets with the WG_* flags, block i's C and db are at
+// c + i*c_seg_stride, db + i*db_seg_stride; CTAs split the flattened (segment, time tile) space evenly.
+struct WgOpts { int n_split; int nseg; const int* seg_shift; int c_seg_stride; int db_seg_stride; };
 int wgrad_tc_blocks(const WgBlock* blocks, int nblocks, const WgOperand* b_ops, int nb_ops, int ldc, int B, int T,
                     cudaStream_t st, const WgOpts* opts = nullptr);
 int wgrad_tc(const WgOperand* a_ops, int na_ops, const WgOperand* b_ops, int nb_ops, float* c, int ldc, int m_valid,

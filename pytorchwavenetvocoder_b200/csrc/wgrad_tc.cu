@@ -25,14 +25,18 @@ namespace wnb {
 namespace wg {
 
 constexpr int kMaxMB = 5;                    // M-blocks (128 rows each) sharing one B operand per launch
-constexpr int kMaxA = 4 * kMaxMB, kMaxB = 8, kMaxMaps = 4;
+constexpr int kMaxB = 8, kMaxMaps = 6, kMaxOps = 2 * kMaxMB + 8;
 constexpr int kThreadsW = 192;
+constexpr int kMaxSeg = 64;
 
-struct Sub { int map; int c0; int shift; };
+// One TMA load per operand and stage: the tensor (B,T,C) is mapped 4-D as {32 ch, T, C/32 groups, B} with a box of
+// {32, tk, groups, 1}, which lands in shared memory as `groups` consecutive [tk x 32] swizzled sub-tiles -- exactly
+// the per-group layout the MMA descriptors expect.  (The producer is ONE thread: with a load per 32-channel group
+// its issue time, not HBM, bounded the wide launches.)
+struct Op { int map; int cgrp0; int shift; int flags; int seg_cgrp_stride; int dst_group; };   // flags: WG_* of tc_host.h
 struct alignas(64) Params {
   CUtensorMap maps[kMaxMaps];
-  Sub a[kMaxA];                  // 4 groups per M-block
-  Sub b[kMaxB];
+  Op ops[kMaxOps]; int nops;     // A operands of every M-block (4 groups each), then the B operands
   int nMB, nB, use_ones;         // nB excludes the ones group
   float* c[kMaxMB]; int ldc;     // per block: C rows m (0..127), columns n (0..32*nB-1)
   int m_valid[kMaxMB];           // rows >= m_valid are padding (not written)
@@ -41,6 +45,10 @@ struct alignas(64) Params {
   int tk;                        // time rows per stage (K of one stage): 64, 32 or 16
   int vec4;                      // C blocks are 16-byte aligned with ldc % 4 == 0: flush with red.v4
   int n_split;                   // column groups of the B operand handled by different CTAs (WgOpts)
+  // segments (WgOpts::nseg > 1): nseg independent problems of identical structure (one per residual block) in one
+  // launch; the CTAs split the flattened (segment, time tile) space, accumulator sets alternate between segments
+  int nseg, c_seg_stride, db_seg_stride;
+  int seg_shift[kMaxSeg];
 };
 
 __device__ __forceinline__ uint64_t smem_desc_mn_sw128(uint32_t saddr, uint32_t lbo_bytes) {
@@ -82,8 +90,9 @@ __global__ void __launch_bounds__(kThreadsW, 1) wgrad_tc_kernel(const __grid_con
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.nstages * stage_bytes);
   uint64_t* full = bars;
   uint64_t* empty = bars + p.nstages;
-  uint64_t* done = bars + 2 * p.nstages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+  uint64_t* done = bars + 2 * p.nstages;        // [2]: accumulator set s holds a finished segment
+  uint64_t* accfree = done + 2;                 // [2]: the epilogue has flushed accumulator set s
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accfree + 2);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int N = 32 * nsubB;
 
@@ -92,9 +101,11 @@ __global__ void __launch_bounds__(kThreadsW, 1) wgrad_tc_kernel(const __grid_con
   // same time range (A operand shared through L2) for different 32*nB-channel groups of the B operand
   const int ng = blockIdx.x % p.n_split, tsplit = blockIdx.x / p.n_split, ntsplit = gridDim.x / p.n_split;
   const int bcol0 = ng * 32 * p.nB;
-  const int per = (p.ntiles + ntsplit - 1) / ntsplit;
+  const int total_tiles = p.ntiles * p.nseg;    // flattened (segment, tile) index f = seg * ntiles + tile
+  const int per = (total_tiles + ntsplit - 1) / ntsplit;
   const int tile_begin = tsplit * per;
-  const int tile_end = min(p.ntiles, tile_begin + per);
+  const int tile_end = min(total_tiles, tile_begin + per);
+  const uint32_t acc_cols = (uint32_t)p.nMB * (32u * nsubB);   // TMEM columns of one accumulator set
   const int my_tiles = max(0, tile_end - tile_begin);
 
   if (threadIdx.x == 0) {
@@ -102,7 +113,7 @@ __global__ void __launch_bounds__(kThreadsW, 1) wgrad_tc_kernel(const __grid_con
       ptx::mbar_init(&full[i], 1);
       ptx::mbar_init(&empty[i], 1);
     }
-    ptx::mbar_init(done, 1);
+    for (int i = 0; i < 2; i++) { ptx::mbar_init(&done[i], 1); ptx::mbar_init(&accfree[i], 128); }
     ptx::fence_barrier_init();
   }
   if (p.use_ones) {
@@ -130,16 +141,27 @@ __global__ void __launch_bounds__(kThreadsW, 1) wgrad_tc_kernel(const __grid_con
     if (my_tiles > 0 && ptx::elect_one()) {
       for (int i = 0; i < kMaxMaps; i++) ptx::prefetch_tmap(&p.maps[i]);
       uint32_t s = 0, ph = 0;
-      for (int tile = tile_begin; tile < tile_end; tile++) {
-        const int b = tile / p.tiles_per_b, t0 = (tile - b * p.tiles_per_b) * p.tk;
+      // (segment, batch, tile-in-batch) advance incrementally: this thread's instruction count per stage is what
+      // bounds the wide launches, so no divisions in the loop
+      int seg = tile_begin / p.ntiles, b = (tile_begin - seg * p.ntiles) / p.tiles_per_b;
+      int tb = tile_begin - seg * p.ntiles - b * p.tiles_per_b;
+      for (int f = tile_begin; f < tile_end; f++) {
+        const int t0 = tb * p.tk;
         wait(&empty[s], ph ^ 1, WP_P_EMPTY);
         ptx::mbar_arrive_expect_tx(&full[s], (nA + p.nB) * kSubBytes);
         unsigned char* st = smem + (size_t)s * stage_bytes;
-        for (int g = 0; g < nA; g++)
-          ptx::tma_load_3d(st + g * kSubBytes, &p.maps[p.a[g].map], &full[s], p.a[g].c0, t0 + p.a[g].shift, b);
-        for (int g = 0; g < p.nB; g++)
-          ptx::tma_load_3d(st + (nA + g) * kSubBytes, &p.maps[p.b[g].map], &full[s], p.b[g].c0 + bcol0, t0 + p.b[g].shift, b);
+        for (int i = 0; i < p.nops; i++) {
+          const Op o = p.ops[i];
+          const int cg = o.cgrp0 + (o.dst_group >= nA ? bcol0 >> 5 : 0) + seg * o.seg_cgrp_stride;
+          const int t = t0 + ((o.flags & WG_SEG_SHIFT) ? p.seg_shift[seg] : o.shift);
+          ptx::tma_load_4d(st + o.dst_group * kSubBytes, &p.maps[o.map], &full[s], 0, t, cg,
+                           (o.flags & WG_LAYERED) ? seg * p.B + b : b);
+        }
         if (++s == (uint32_t)p.nstages) { s = 0; ph ^= 1; }
+        if (++tb == p.tiles_per_b) {
+          tb = 0;
+          if (++b == p.B) { b = 0; seg++; }
+        }
       }
     }
   } else if (warp == 1) {
@@ -151,57 +173,78 @@ __global__ void __launch_bounds__(kThreadsW, 1) wgrad_tc_kernel(const __grid_con
       constexpr uint32_t hi = ptx::kDescHiMnSw128B32;
       const uint32_t stage_step = (uint32_t)stage_bytes >> 4, sub_step = (uint32_t)kSubBytes >> 4;
       const int ksteps = p.tk / 8;
-      uint32_t s = 0, ph = 0, it = 0;
-      for (int tile = tile_begin; tile < tile_end; tile++, it++) {
+      uint32_t s = 0, ph = 0, it = 0, nsegs_done = 0;
+      int next_boundary = (tile_begin / p.ntiles + 1) * p.ntiles;   // first flattened index of the next segment
+      for (int f = tile_begin; f < tile_end; f++, it++) {
+        if (f == next_boundary) {   // segment boundary inside this CTA's range: hand the finished set to the epilogue
+          ptx::tc_commit(&done[nsegs_done & 1]);
+          nsegs_done++;
+          next_boundary += p.ntiles;
+          it = 0;
+          if (nsegs_done >= 2) {   // the set about to be reused was handed over two segments ago
+            ptx::mbar_wait(&accfree[nsegs_done & 1], ((nsegs_done >> 1) - 1) & 1);
+            ptx::tc_fence_after();
+          }
+        }
+        const uint32_t dcol = (nsegs_done & 1) * acc_cols;
         wait(&full[s], ph, WP_M_FULL);
         ptx::tc_fence_after();
         const uint32_t a_lo = s_lo0 + s * stage_step, b_lo = a_lo + nA * sub_step;
         for (int mb = 0; mb < p.nMB; mb++) {
           const uint32_t am_lo = a_lo + mb * 4 * sub_step;
           for (int k = 0; k < ksteps; k++)
-            ptx::mma_tf32_ss(tmem + mb * N, ptx::desc64(am_lo + k * 64, hi), ptx::desc64(b_lo + k * 64, hi), idesc,
+            ptx::mma_tf32_ss(tmem + dcol + mb * N, ptx::desc64(am_lo + k * 64, hi), ptx::desc64(b_lo + k * 64, hi), idesc,
                              (it | k) != 0);
         }
         ptx::tc_commit(&empty[s]);
         if (++s == (uint32_t)p.nstages) { s = 0; ph ^= 1; }
       }
-      ptx::tc_commit(done);
+      ptx::tc_commit(&done[nsegs_done & 1]);
       if constexpr (PROF) acc[WP_M_TOTAL] = clock64() - t_begin;
     }
   } else if (my_tiles > 0) {
-    // epilogue: flush the accumulator once
+    // epilogue: flush each finished accumulator set once (one per segment of this CTA's range)
     const int q = warp & 3;
     const int row = q * 32 + lane;
-    ptx::mbar_wait(done, 0);
-    ptx::tc_fence_after();
-    const long long t_flush = PROF ? clock64() : 0;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     const int nchunk = N / 16;
-    for (int mb = 0; mb < p.nMB; mb++) {
-      for (int ci = 0; ci < nchunk; ci++) {
-        // every CTA flushes the same addresses: start at a CTA-dependent chunk so the atomics spread out
-        const int c0 = ((ci + blockIdx.x) % nchunk) * 16;
-        float v[16];
-        ptx::tmem_ld16(tmem + lane_base + mb * N + c0, v);
-        ptx::tc_wait_ld();
-        if (row < p.m_valid[mb]) {
-          if (c0 < 32 * p.nB) {
-            float* dst = p.c[mb] + (size_t)row * p.ldc + bcol0 + c0;
-            if (p.vec4) {   // 16-byte vector reductions: a quarter of the L2 atomic operations
+    const int first_seg = tile_begin / p.ntiles, last_seg = (tile_end - 1) / p.ntiles;
+    long long t_flush = 0;
+    for (int k = 0; k <= last_seg - first_seg; k++) {
+      const int seg = first_seg + k, aset = k & 1;
+      ptx::mbar_wait(&done[aset], (k >> 1) & 1);
+      ptx::tc_fence_after();
+      if (PROF && k == 0) t_flush = clock64();
+      const uint32_t dcol = aset * acc_cols;
+      for (int mb = 0; mb < p.nMB; mb++) {
+        float* cbase = p.c[mb] + (size_t)seg * p.c_seg_stride;
+        for (int ci = 0; ci < nchunk; ci++) {
+          // every CTA flushes the same addresses: start at a CTA-dependent chunk so the atomics spread out
+          const int c0 = ((ci + blockIdx.x) % nchunk) * 16;
+          float v[16];
+          ptx::tmem_ld16(tmem + lane_base + dcol + mb * N + c0, v);
+          ptx::tc_wait_ld();
+          if (row < p.m_valid[mb]) {
+            if (c0 < 32 * p.nB) {
+              float* dst = cbase + (size_t)row * p.ldc + bcol0 + c0;
+              if (p.vec4) {   // 16-byte vector reductions: a quarter of the L2 atomic operations
 #pragma unroll
-              for (int i = 0; i < 16; i += 4)
-                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + i), "f"(v[i]), "f"(v[i + 1]),
-                             "f"(v[i + 2]), "f"(v[i + 3])
-                             : "memory");
-            } else {
+                for (int i = 0; i < 16; i += 4)
+                  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + i), "f"(v[i]), "f"(v[i + 1]),
+                               "f"(v[i + 2]), "f"(v[i + 3])
+                               : "memory");
+              } else {
 #pragma unroll
-              for (int i = 0; i < 16; i++) atomicAdd(dst + i, v[i]);
+                for (int i = 0; i < 16; i++) atomicAdd(dst + i, v[i]);
+              }
+            } else if (c0 == 32 * p.nB && p.db[mb] && ng == 0) {
+              atomicAdd(p.db[mb] + (size_t)seg * p.db_seg_stride + row, v[0]);
             }
-          } else if (c0 == 32 * p.nB && p.db[mb] && ng == 0) {
-            atomicAdd(p.db[mb] + row, v[0]);
           }
         }
       }
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&accfree[aset]);
     }
     if constexpr (PROF) {
       if (warp == 2) {
@@ -238,14 +281,15 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
-// (B, T, C) fp32 channels-last tensor, box [32 ch x 64 rows x 1]
-static bool make_act_map(CUtensorMap* m, const float* base, int C, int T, int B, int tk) {
+// (B, T, C) fp32 channels-last tensor seen as {32 ch, T, C/32 groups, B} (the group axis OUTSIDE time, so that the box
+// {32, tk, groups, 1} lands in shared memory group-major: `groups` consecutive [tk x 32] sub-tiles)
+static bool make_act_map(CUtensorMap* m, const float* base, int C, int T, int B, int tk, int groups) {
   EncodeTiledFn enc = get_encode();
-  if (!enc) return false;
-  cuuint64_t gdim[3] = {(cuuint64_t)C, (cuuint64_t)T, (cuuint64_t)B};
-  cuuint64_t gstr[2] = {(cuuint64_t)C * 4, (cuuint64_t)C * 4 * (cuuint64_t)T};
-  cuuint32_t box[3] = {32, (cuuint32_t)tk, 1}, es[3] = {1, 1, 1};
-  return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), gdim, gstr, box, es,
+  if (!enc || C % 32 != 0) return false;
+  cuuint64_t gdim[4] = {32, (cuuint64_t)T, (cuuint64_t)(C / 32), (cuuint64_t)B};
+  cuuint64_t gstr[3] = {(cuuint64_t)C * 4, 128, (cuuint64_t)C * 4 * (cuuint64_t)T};
+  cuuint32_t box[4] = {32, (cuuint32_t)tk, (cuuint32_t)groups, 1}, es[4] = {1, 1, 1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), gdim, gstr, box, es,
              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
@@ -285,45 +329,59 @@ int wgrad_tc_blocks(const WgBlock* blocks, int nblocks, const WgOperand* b_ops, 
 
   int nmaps = 0;
   const float* map_base[kMaxMaps];
-  int map_c[kMaxMaps];
+  int map_c[kMaxMaps], map_g[kMaxMaps];
   auto map_of = [&](const WgOperand& o) -> int {
     for (int i = 0; i < nmaps; i++)
-      if (map_base[i] == o.base && map_c[i] == o.C) return i;
+      if (map_base[i] == o.base && map_c[i] == o.C && map_g[i] == o.groups) return i;
     if (nmaps >= kMaxMaps) return -1;
-    if (!make_act_map(&p.maps[nmaps], o.base, o.C, T, B, tk)) return -1;
-    map_base[nmaps] = o.base; map_c[nmaps] = o.C;
+    const int nseg_map = (opts && opts->nseg > 1 && (o.flags & WG_LAYERED)) ? opts->nseg : 1;
+    if (!make_act_map(&p.maps[nmaps], o.base, o.C, T, B * nseg_map, tk, o.groups)) return -1;
+    map_base[nmaps] = o.base; map_c[nmaps] = o.C; map_g[nmaps] = o.groups;
     return nmaps++;
+  };
+  auto add_op = [&](const WgOperand& o, int dst_group) -> bool {
+    if (o.c0 % 32 != 0 || o.seg_cstride % 32 != 0 || o.groups < 1 || p.nops >= kMaxOps) return false;
+    const int m = map_of(o);
+    if (m < 0) return false;
+    p.ops[p.nops++] = Op{m, o.c0 / 32, o.shift, o.flags, o.seg_cstride / 32, dst_group};
+    return true;
   };
   for (int bi = 0; bi < nblocks; bi++) {
     int ng = 0;
     for (int i = 0; i < blocks[bi].nops; i++) {
       const WgOperand& o = blocks[bi].ops[i];
-      const int m = map_of(o);
-      if (m < 0) { set_error("wgrad_tc: tensor map creation failed (A)"); return WNB_ERR_CUDA; }
-      for (int g = 0; g < o.groups; g++) {
-        if (ng >= 4) { set_error("wgrad_tc: more than 4 groups in an M-block"); return WNB_ERR_INVALID; }
-        p.a[bi * 4 + ng++] = Sub{m, o.c0 + 32 * g, o.shift};
-      }
+      if (ng + o.groups > 4) { set_error("wgrad_tc: more than 4 groups in an M-block"); return WNB_ERR_INVALID; }
+      if (!add_op(o, bi * 4 + ng)) { set_error("wgrad_tc: tensor map creation failed (A)"); return WNB_ERR_CUDA; }
+      ng += o.groups;
     }
     if (ng != 4) { set_error("wgrad_tc: an M-block needs exactly 4 groups"); return WNB_ERR_INVALID; }
     p.c[bi] = blocks[bi].c; p.m_valid[bi] = blocks[bi].m_valid; p.db[bi] = blocks[bi].db;
   }
   int nb = 0;
   for (int i = 0; i < nb_ops; i++) {
-    const int m = map_of(b_ops[i]);
-    if (m < 0) { set_error("wgrad_tc: tensor map creation failed (B)"); return WNB_ERR_CUDA; }
-    for (int g = 0; g < b_ops[i].groups; g++) p.b[nb++] = Sub{m, b_ops[i].c0 + 32 * g, b_ops[i].shift};
+    if (!add_op(b_ops[i], 4 * nblocks + nb)) { set_error("wgrad_tc: tensor map creation failed (B)"); return WNB_ERR_CUDA; }
+    nb += b_ops[i].groups;
   }
   for (int i = nmaps; i < kMaxMaps; i++) p.maps[i] = p.maps[0];
   p.ldc = ldc;
   p.n_split = (opts && opts->n_split > 1) ? opts->n_split : 1;
+  p.nseg = (opts && opts->nseg > 1) ? opts->nseg : 1;
+  if (p.nseg > 1) {
+    if (p.nseg > kMaxSeg || p.n_split > 1 || 2 * N * nblocks > 512 || !opts->seg_shift) {
+      set_error("wgrad_tc: bad segment configuration (nseg=%d, %d accumulator columns)", p.nseg, N * nblocks);
+      return WNB_ERR_INVALID;
+    }
+    for (int i = 0; i < p.nseg; i++) p.seg_shift[i] = opts->seg_shift[i];
+    p.c_seg_stride = opts->c_seg_stride;
+    p.db_seg_stride = opts->db_seg_stride;
+  }
   p.vec4 = (ldc % 4 == 0) ? 1 : 0;
   for (int i = 0; i < nblocks; i++)
     if (reinterpret_cast<uintptr_t>(blocks[i].c) & 15) p.vec4 = 0;
   p.T = T; p.B = B;
   p.tiles_per_b = (T + tk - 1) / tk;
   p.ntiles = B * p.tiles_per_b;
-  const size_t smem = (size_t)nst * stage_bytes + 1024 + 256;
+  const size_t smem = (size_t)nst * stage_bytes + 1024 + 256;   // barriers: 2*nst + 4 (+ TMEM slot) <= 21 words
   static size_t configured = 0;
   if (smem > configured) {
     WNB_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
