@@ -261,7 +261,8 @@ def run_ours(args):
             alg = {"fwd_block": bt4 * (3 * R + Ap), "skip_gemm": bt4 * (LR + S), "dzall_gemm": bt4 * (S + LR),
                    "gate_bwd": bt4 * (5 * R + Ap), "dx_gemm": bt4 * (4 * R + 2 * Ap),
                    # every block's dW1 / dW2res in ONE segmented launch each (dpre_l, x_l, aux | dout_l, z_l)
-                   "dw1": L * bt4 * (3 * R + Ap), "dw2res": (L - 1) * bt4 * 2 * R, "dwskip": bt4 * (S + LR)}
+                   # (aux is shared by all blocks and stays in L2: counted once)
+                   "dw1": L * bt4 * 3 * R + bt4 * Ap, "dw2res": (L - 1) * bt4 * 2 * R, "dwskip": bt4 * (S + LR)}
             roof_all = []
             for name, tot, n in kinds:
                 if n == 0:
@@ -321,7 +322,9 @@ def run_ours(args):
 TRAFFIC_NCU = {"fp32": None, "tf32": 814.14e6}
 # kernel kinds timed by wnb_profile_read (WNB_PROF_* order) and their ncu DRAM bytes per launch (None = not captured)
 STACK_KINDS = ["fwd_block", "skip_gemm", "dzall_gemm", "gate_bwd", "dx_gemm", "dw1", "dw2res", "dwskip"]
-TRAFFIC_NCU_STACK = {}
+# profiles/r1_ncu_gate_bwd_summary.txt: gate backward 118.2 MB read + 52.2 MB written (dout and half of dpre stay in
+# L2 between kernels), dx 118.1 + 31.1 MB
+TRAFFIC_NCU_STACK = {"gate_bwd": 170.34e6, "dx_gemm": 149.16e6}
 
 
 def run_decode(args, dev, rank, world, dist):

@@ -54,7 +54,12 @@ struct alignas(64) Params {
 enum { NP_P_EMPTY = 0, NP_M_DEMPTY, NP_M_FULL, NP_M_TOTAL, NP_E_DFULL, NP_E_BULK, NP_E_TOTAL, NP_MIN, NP_MAX, NP_COUNT };
 __device__ unsigned long long g_nt_prof[NP_COUNT];
 
-template <bool PROF>
+// EPI selects the epilogue at compile time so that each variant gets its own register allocation (the kernel runs
+// 320 threads = 168 registers per thread): 0 plain (bias / add / ReLU / mask / split output), 1 gate forward and
+// gate backward with z output, 2 gate backward without z (the stack path, two 16-channel passes).
+enum { EPI_PLAIN = 0, EPI_GATE = 1, EPI_GATE_BWD_NOZ = 2 };
+
+template <bool PROF, int EPI>
 __global__ void __launch_bounds__(kThreadsN, 1) gemm_nt_tc_kernel(const __grid_constant__ Params p) {
   long long acc[NP_COUNT] = {};
   auto wait = [&](uint64_t* bar, uint32_t parity, int k) {
@@ -184,8 +189,8 @@ __global__ void __launch_bounds__(kThreadsN, 1) gemm_nt_tc_kernel(const __grid_c
       // operands of the epilogue that do not depend on the accumulator are requested before waiting for it, so
       // their DRAM latency overlaps the mainloop of this tile: dz of the gate backward, `add` of the first chunk
       float4 pre[8];
-      const bool pre_dz = p.gate_mode >= 2 && row_ok && hf * 32 < 64;
-      const bool pre_add = !p.gate_mode && p.add && row_ok && hf * 32 < N && !(p.out2_col0 > 0 && hf * 32 >= p.out2_col0);
+      const bool pre_dz = EPI != EPI_PLAIN && p.gate_mode >= 2 && row_ok && hf * 32 < 64;
+      const bool pre_add = EPI == EPI_PLAIN && p.add && row_ok && hf * 32 < N && !(p.out2_col0 > 0 && hf * 32 >= p.out2_col0);
       if (pre_dz) {
         const float4* dr = reinterpret_cast<const float4*>(p.gate_dz + grow * p.gate_ld_dz + p.gate_c0 + hf * 32);
 #pragma unroll
@@ -197,7 +202,66 @@ __global__ void __launch_bounds__(kThreadsN, 1) gemm_nt_tc_kernel(const __grid_c
       }
       wait(&dfull[buf], use & 1, NP_E_DFULL);
       ptx::tc_fence_after();
-      if (p.gate_mode) {
+      if constexpr (EPI == EPI_GATE_BWD_NOZ) {
+        // ---- gate backward without the z output (the stack path): two passes of 16 gate channels keep the live
+        //      registers under the 168 this kernel gets (the 32-channel form below spilled); the two dpre boxes of
+        //      this warp (d pre-sigmoid, d pre-tanh) are filled side by side and stored with one bulk group ----
+        const int c0 = hf * 32;
+        {
+          const long long tb = PROF ? clock64() : 0;
+          if (lane == 0) ptx::bulk_wait_read<0>();
+          __syncwarp();
+          if constexpr (PROF) acc[NP_E_BULK] += clock64() - tb;
+        }
+        const uint32_t sb0 = ptx::smem_u32(stg + lane * 128), sb1 = sb0 + kStg;
+        const float4* bsv = reinterpret_cast<const float4*>(p.bias + c0);
+        const float4* btv = reinterpret_cast<const float4*>(p.bias2 + c0);
+#pragma unroll
+        for (int h2 = 0; h2 < 2; h2++) {
+          const int cc = c0 + h2 * 16;
+          float a[16], g[16], dzp[16];
+          ptx::tmem_ld16(tmem + lane_base + buf * N + cc, a);
+          ptx::tmem_ld16(tmem + lane_base + buf * N + 64 + cc, g);
+          if (p.gate_mode == 3) ptx::tmem_ld16(tmem + lane_base + buf * N + 128 + cc, dzp);
+          float4 bs[4], bt[4];
+#pragma unroll
+          for (int i = 0; i < 4; i++) { bs[i] = __ldg(bsv + h2 * 4 + i); bt[i] = __ldg(btv + h2 * 4 + i); }
+          ptx::tc_wait_ld();
+          if (h2 == 1) {
+            ptx::tc_fence_before();
+            ptx::mbar_arrive(&dempty[buf]);   // this warp's share of the accumulator is in registers
+          }
+#pragma unroll
+          for (int jj = 0; jj < 4; jj++) {
+            const float4 d4 = pre[h2 * 4 + jj];   // dz slice, requested before the accumulator wait
+            const float dzs[4] = {d4.x, d4.y, d4.z, d4.w};
+            const float bsa[4] = {bs[jj].x, bs[jj].y, bs[jj].z, bs[jj].w}, bta[4] = {bt[jj].x, bt[jj].y, bt[jj].z, bt[jj].w};
+            float da[4], dg[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+              const int i = 4 * jj + k;
+              float dz = row_ok ? dzs[k] : 0.f;
+              if (p.gate_mode == 3) dz += dzp[i];
+              const float sg = 0.5f * ptx::tanh_approx(0.5f * (a[i] + bsa[k])) + 0.5f;
+              const float th = ptx::tanh_approx(g[i] + bta[k]);
+              da[k] = dz * th * sg * (1.f - sg);      // d pre-sigmoid
+              dg[k] = dz * sg * (1.f - th * th);      // d pre-tanh
+            }
+            const uint32_t off = (uint32_t)(((h2 * 4 + jj) ^ (lane & 7)) << 4);
+            ptx::st_shared_v4(sb0 + off, da[0], da[1], da[2], da[3]);
+            ptx::st_shared_v4(sb1 + off, dg[0], dg[1], dg[2], dg[3]);
+          }
+        }
+        ptx::fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          ptx::tma_store_3d(&p.maps[9], stg, p.gate_c0 + c0, t0 + q * 32, b);
+          ptx::tma_store_3d(&p.maps[9], stg + kStg, p.gate_R + p.gate_c0 + c0, t0 + q * 32, b);
+          ptx::bulk_commit();
+        }
+        continue;
+      }
+      if constexpr (EPI == EPI_GATE) {
         // ---- gate epilogues: pair sigmoid column c with tanh column 64 + c ----
         for (int c0 = hf * 32; c0 < 64; c0 += 64) {
           float a[32], g[32];
@@ -303,6 +367,7 @@ __global__ void __launch_bounds__(kThreadsN, 1) gemm_nt_tc_kernel(const __grid_c
         }
         continue;
       }
+      if constexpr (EPI == EPI_PLAIN) {
       if (hf * 32 >= N) {  // N == 32: the second warp of the pair has no chunk
         ptx::tc_fence_before();
         ptx::mbar_arrive(&dempty[buf]);
@@ -369,6 +434,7 @@ __global__ void __launch_bounds__(kThreadsN, 1) gemm_nt_tc_kernel(const __grid_c
         }
         nstore++;
       }
+      }  // EPI_PLAIN
     }
     if (lane == 0) ptx::bulk_wait<0>();
     if constexpr (PROF) {
@@ -456,6 +522,7 @@ int gemm_nt_tc(const NtTcSeg* segs, int nseg, int N, float* out, int ld_out, con
       set_error("gemm_nt_tc: bad gate-backward configuration");
       return WNB_ERR_INVALID;
     }
+    if (reinterpret_cast<uintptr_t>(bias) & 15) { set_error("gemm_nt_tc: gate bias must be 16-byte aligned"); return WNB_ERR_INVALID; }
     p.gate_dz = gate_dz; p.bias = bias; p.bias2 = bias + 64; p.gate_mode = fused_dz ? 3 : 2; p.gate_c0 = 0; p.gate_R = 64;
   }
   if (gate) {      // general form: 64 gate channels [c0, c0+64) of R; W rows c0.. (sigmoid) and R+c0.. (tanh)
@@ -501,8 +568,12 @@ int gemm_nt_tc(const NtTcSeg* segs, int nseg, int N, float* out, int ld_out, con
   const size_t smem = (size_t)nst * stage_bytes + kEpiWarpsN * 2 * kStg + 512 + 1024;
   static size_t configured = 0;
   if (smem > configured) {
-    WNB_CUDA(cudaFuncSetAttribute(gemm_nt_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    WNB_CUDA(cudaFuncSetAttribute(gemm_nt_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    WNB_CUDA(cudaFuncSetAttribute(gemm_nt_tc_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    WNB_CUDA(cudaFuncSetAttribute(gemm_nt_tc_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    WNB_CUDA(cudaFuncSetAttribute(gemm_nt_tc_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    WNB_CUDA(cudaFuncSetAttribute(gemm_nt_tc_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    WNB_CUDA(cudaFuncSetAttribute(gemm_nt_tc_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    WNB_CUDA(cudaFuncSetAttribute(gemm_nt_tc_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
   static int sms = 0;
@@ -513,13 +584,16 @@ int gemm_nt_tc(const NtTcSeg* segs, int nseg, int N, float* out, int ld_out, con
   }
   const int ntiles = B * ((T + kTM - 1) / kTM) * p.nblk;
   const int grid = ntiles < sms ? ntiles : sms;
+  const int epi = !p.gate_mode ? EPI_PLAIN : ((p.gate_mode >= 2 && p.gate_skip_z) ? EPI_GATE_BWD_NOZ : EPI_GATE);
   static int prof = -1;
   if (prof < 0) { const char* e = getenv("WNB_PROF"); prof = (e && e[0] == '1') ? 1 : 0; }
   if (prof) {
     unsigned long long zero[NP_COUNT] = {}, h[NP_COUNT];
     zero[NP_MIN] = ~0ull;
     WNB_CUDA(cudaMemcpyToSymbol(g_nt_prof, zero, sizeof(zero)));
-    gemm_nt_tc_kernel<true><<<grid, kThreadsN, smem, st>>>(p);
+    if (epi == EPI_PLAIN) gemm_nt_tc_kernel<true, 0><<<grid, kThreadsN, smem, st>>>(p);
+    else if (epi == EPI_GATE) gemm_nt_tc_kernel<true, 1><<<grid, kThreadsN, smem, st>>>(p);
+    else gemm_nt_tc_kernel<true, 2><<<grid, kThreadsN, smem, st>>>(p);
     WNB_CHECK_LAUNCH("gemm_nt_tc");
     WNB_CUDA(cudaStreamSynchronize(st));
     WNB_CUDA(cudaMemcpyFromSymbol(h, g_nt_prof, sizeof(h)));
@@ -531,7 +605,11 @@ int gemm_nt_tc(const NtTcSeg* segs, int nseg, int N, float* out, int ld_out, con
             h[5] / 1e3 / grid, h[6] / 1e3 / grid, h[7] / 1e3, h[8] / 1e3);
     return WNB_OK;
   }
-  if (launch_pdl(gemm_nt_tc_kernel<false>, grid, kThreadsN, smem, st, p) != cudaSuccess) { /* reported below */ }
+  cudaError_t le;
+  if (epi == EPI_PLAIN) le = launch_pdl(gemm_nt_tc_kernel<false, 0>, grid, kThreadsN, smem, st, p);
+  else if (epi == EPI_GATE) le = launch_pdl(gemm_nt_tc_kernel<false, 1>, grid, kThreadsN, smem, st, p);
+  else le = launch_pdl(gemm_nt_tc_kernel<false, 2>, grid, kThreadsN, smem, st, p);
+  (void)le;   // reported by WNB_CHECK_LAUNCH below
   WNB_CHECK_LAUNCH("gemm_nt_tc");
   return WNB_OK;
 }

@@ -117,6 +117,18 @@ resblock_fwd_z_kernel(const __grid_constant__ Maps maps, const float* __restrict
         ptx::tma_load_3d(sA + 4 * kSubBytes, &maps.haux, &bars[B_AFULL], 0, t0, b);
         tile = (int)(atomicAdd(&g_tile_next, 1u) + gridDim.x);
         if (tile >= ntiles) tile = -1;
+        if (tile >= 0) {
+          // there is room for only one A stage, so the next tile cannot be loaded yet -- but it can be pulled into
+          // L2 now, which turns the exposed DRAM latency of its load into an L2 hit
+          const int nb = tile / tiles_per_b, nt0 = (tile - nb * tiles_per_b) * kTM;
+          ptx::tma_prefetch_3d(&maps.x, 0, nt0, nb);
+          ptx::tma_prefetch_3d(&maps.x, 32, nt0, nb);
+          ptx::tma_prefetch_3d(&maps.haux, 0, nt0, nb);
+          if (d >= kTM) {   // (for d < 128 most of x(t-d) is the previous tile of the same row: already in L2)
+            ptx::tma_prefetch_3d(&maps.x, 0, nt0 - d, nb);
+            ptx::tma_prefetch_3d(&maps.x, 32, nt0 - d, nb);
+          }
+        }
       }
     }
   } else if (warp == 2) {
