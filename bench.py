@@ -225,15 +225,43 @@ def run_ours(args):
             _lib.check(lib.wnb_profile_enable(0), "profile_enable")
         clocks = sampler.stop() if rank == 0 else None
         # --- end-to-end timing: pinned host -> device every step, loss read back every step ---
-        for _ in range(2):
-            float(step(xh.to(dev, non_blocking=True), hh.to(dev, non_blocking=True), th.to(dev, non_blocking=True)).detach())
+        # The public-API loop a trainer runs (bin/train.py): the next batch's host->device copy is issued on a copy
+        # stream before the current loss is read back (what the reference's background batch generator does with
+        # its prefetch thread), so each step's copy overlaps the previous step's kernels; every step still copies its
+        # own inputs from pinned memory and reads its own loss inside the timed region.
+        copy_stream = torch.cuda.Stream(device=dev)
+
+        def fetch():
+            with torch.cuda.stream(copy_stream):
+                tens = (xh.to(dev, non_blocking=True), hh.to(dev, non_blocking=True), th.to(dev, non_blocking=True))
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+            return tens, ev
+
+        def e2e_loop(n):
+            # every step's loss is read back to the host inside the loop, one step late (the usual logging lag of a
+            # training loop: the host stays one step ahead of the device instead of draining it every iteration)
+            last_loss, pending = 0.0, None
+            nxt = fetch()
+            for i in range(n):
+                (xb, hb, tb), ev = nxt
+                cur = torch.cuda.current_stream()
+                cur.wait_event(ev)
+                for tns in (xb, hb, tb):
+                    tns.record_stream(cur)
+                loss_i = step(xb, hb, tb)
+                if i + 1 < n:
+                    nxt = fetch()
+                if pending is not None:
+                    last_loss = float(pending)
+                pending = loss_i.detach()
+            return float(pending)
+
+        e2e_loop(2)
         barrier()
         e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e2.record()
-        last = 0.0
-        for _ in range(args.steps):
-            last = float(step(xh.to(dev, non_blocking=True), hh.to(dev, non_blocking=True),
-                              th.to(dev, non_blocking=True)).detach())
+        last = e2e_loop(args.steps)
         e3.record()
         barrier()
         ms_e2e = e2.elapsed_time(e3)
@@ -294,7 +322,9 @@ def run_ours(args):
                        "l2": "per-step working set ~10 GB >> 126 MB L2 (no explicit flush needed)"},
             "e2e": {"value": samples / (ms_e2e / args.steps * 1e-3), "unit": "samples/s",
                     "h2d_bytes_per_step": int(xh.numel() * 8 + th.numel() * 8 + hh.numel() * 4),
-                    "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps, "last_loss": last},
+                    "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps, "last_loss": last,
+                    "loop": "next batch copied H2D on a copy stream while the step runs; each step's loss read back "
+                            "one step later (all %d reads inside the timed region)" % args.steps},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": roof,

@@ -16,10 +16,11 @@
 //   out     xout = D2 + b2res + x(t)   (x(t) was copied from the A stage into registers when the tile landed, so
 //           the single A stage is released as soon as GEMM-1 has read it and the next tile's TMA load overlaps the
 //           gate / GEMM-2 / epilogue of this one)
-// Roles (352 threads): warp 0 TMA producer (dynamic tile scheduler), warp 1 MMA issuer, warp 2 loads the weights
+// Roles (352 threads): warp 0 TMA producer (dynamic tile scheduler), warp 1 MMA issuer (GEMM-1 of the next tile and
+// GEMM-2 of this one in whichever order their inputs arrive; D1 is double-buffered), warp 2 loads the weights
 // once, warps 3-10 epilogue (TMEM lane quarter x column half).  fp32 storage, tf32 multiplies, fp32 accumulate.
 //
-// Shared memory: W1 80 KB | W2res 16 KB | A stage 80 KB | staging 8 x 4 KB.   TMEM: D1 128 | z 64 | D2 64 columns.
+// Shared memory: W1 80 KB | W2res 16 KB | A stage 80 KB | staging 8 x 4 KB.   TMEM: D1 2 x 128 | z 64 | D2 64 columns.
 #include <cuda.h>
 
 #include <cstdio>
@@ -48,13 +49,13 @@ constexpr int kOffStg = kOffA + kNSubA * kSubBytes;
 constexpr int kOffBar = kOffStg + kEpiWarps * kStgBytes;
 constexpr int kSmemBytes = kOffBar + 256 + 1024;
 constexpr int kThreadsZ = 32 * (3 + kEpiWarps);
-constexpr uint32_t kColD1 = 0, kColZ = 128, kColD2 = 192;
+constexpr uint32_t kColD1 = 0 /* two buffers of 128 */, kColZ = 256, kColD2 = 320;
 
 struct alignas(64) Maps {
   CUtensorMap x, haux, w1, w2, xout, z;
 };
 
-enum { B_W = 0, B_AFULL, B_AEMPTY, B_D1F, B_D1E, B_ZF, B_D2F, B_D2E, B_TILE0, B_TILE1, B_COUNT };
+enum { B_W = 0, B_AFULL, B_AEMPTY, B_D1F0, B_D1F1, B_D1E0, B_D1E1, B_ZF, B_D2F, B_D2E, B_TILE0, B_TILE1, B_COUNT };
 static_assert(8 * B_COUNT + 16 <= 256, "barrier block");
 
 // dynamic tile scheduler state (see resblock_tc.cu): launches must be stream-ordered
@@ -77,8 +78,8 @@ resblock_fwd_z_kernel(const __grid_constant__ Maps maps, const float* __restrict
     ptx::mbar_init(&bars[B_W], 1);
     ptx::mbar_init(&bars[B_AFULL], 1);
     ptx::mbar_init(&bars[B_AEMPTY], kEpiThreads + 1);   // every epilogue thread (x copied) + GEMM-1 commit
-    ptx::mbar_init(&bars[B_D1F], 1);
-    ptx::mbar_init(&bars[B_D1E], kEpiThreads);
+    ptx::mbar_init(&bars[B_D1F0], 1); ptx::mbar_init(&bars[B_D1F1], 1);
+    ptx::mbar_init(&bars[B_D1E0], kEpiThreads); ptx::mbar_init(&bars[B_D1E1], kEpiThreads);
     ptx::mbar_init(&bars[B_ZF], kEpiThreads);
     ptx::mbar_init(&bars[B_D2F], 1);
     ptx::mbar_init(&bars[B_D2E], kEpiThreads);
@@ -152,31 +153,57 @@ resblock_fwd_z_kernel(const __grid_constant__ Maps maps, const float* __restrict
       const uint32_t w2_lo0 = ptx::desc_lo(ptx::smem_u32(smem + kOffW2), 16);
       constexpr uint32_t hi = ptx::kDescHiKSw128;
       ptx::mbar_wait(&bars[B_W], 0);
-      for (uint32_t it = 0;; it++) {
-        ptx::mbar_wait(&bars[B_TILE0 + (it & 1)], (it >> 1) & 1);
-        if (tile_ring[it & 1] < 0) break;
-        ptx::mbar_wait(&bars[B_AFULL], it & 1);
-        ptx::mbar_wait(&bars[B_D1E], (it & 1) ^ 1);
+      // GEMM-1 of tile it+1 (into the other D1 buffer) and GEMM-2 of tile it are issued in whichever order their
+      // inputs become ready -- the next A stage landing, or the gate of tile it finishing -- so the tensor pipe
+      // works on the next tile while the epilogue warps are still in the gate of this one.
+      auto gemm1 = [&](uint32_t it) {
         ptx::tc_fence_after();
 #pragma unroll
         for (int j = 0; j < kNSubA; j++)
 #pragma unroll
           for (int k = 0; k < 4; k++)
-            ptx::mma_tf32_ss(tmem + kColD1, ptx::desc64(a_lo0 + j * (kSubBytes >> 4) + 2 * k, hi),
+            ptx::mma_tf32_ss(tmem + kColD1 + (it & 1) * 128, ptx::desc64(a_lo0 + j * (kSubBytes >> 4) + 2 * k, hi),
                              ptx::desc64(w1_lo0 + j * (kSubBytes >> 4) + 2 * k, hi), idesc1, (j | k) != 0);
-        ptx::tc_commit(&bars[B_D1F]);
+        ptx::tc_commit(&bars[B_D1F0 + (it & 1)]);
         ptx::tc_commit(&bars[B_AEMPTY]);   // GEMM-1 has read the A stage
-        if (has_xout) {
-          ptx::mbar_wait(&bars[B_ZF], it & 1);
-          ptx::mbar_wait(&bars[B_D2E], (it & 1) ^ 1);
-          ptx::tc_fence_after();
+      };
+      ptx::mbar_wait(&bars[B_TILE0], 0);
+      if (tile_ring[0] >= 0) {
+        ptx::mbar_wait(&bars[B_AFULL], 0);
+        gemm1(0);
+        for (uint32_t it = 0;; it++) {
+          const uint32_t nx = it + 1;
+          ptx::mbar_wait(&bars[B_TILE0 + (nx & 1)], (nx >> 1) & 1);
+          bool need1 = tile_ring[nx & 1] >= 0;
+          const bool has_next = need1;
+          bool need2 = has_xout != 0;
+          uint32_t spins = 0;
+          while (need1 || need2) {
+            if (need2 && ptx::mbar_try_wait(&bars[B_ZF], it & 1) && ptx::mbar_try_wait(&bars[B_D2E], (it & 1) ^ 1)) {
+              ptx::tc_fence_after();
 #pragma unroll
-          for (int kk = 0; kk < 2; kk++)
+              for (int kk = 0; kk < 2; kk++)
 #pragma unroll
-            for (int k = 0; k < 4; k++)
-              ptx::mma_tf32_ts(tmem + kColD2, tmem + kColZ + kk * 32 + k * 8,
-                               ptx::desc64(w2_lo0 + kk * (kW2SubBytes >> 4) + 2 * k, hi), idesc2, (kk | k) != 0);
-          ptx::tc_commit(&bars[B_D2F]);
+                for (int k = 0; k < 4; k++)
+                  ptx::mma_tf32_ts(tmem + kColD2, tmem + kColZ + kk * 32 + k * 8,
+                                   ptx::desc64(w2_lo0 + kk * (kW2SubBytes >> 4) + 2 * k, hi), idesc2, (kk | k) != 0);
+              ptx::tc_commit(&bars[B_D2F]);
+              need2 = false;
+              continue;
+            }
+            // D1 buffer nx & 1 was last read by the gate of tile nx - 2
+            if (need1 && ptx::mbar_try_wait(&bars[B_AFULL], nx & 1) &&
+                ptx::mbar_try_wait(&bars[B_D1E0 + (nx & 1)], ((nx >> 1) & 1) ^ 1)) {
+              gemm1(nx);
+              need1 = false;
+              continue;
+            }
+            if (++spins > (1u << 24)) {
+              printf("wnb200: resblock_fwd_z MMA issuer timed out (block %d)\n", blockIdx.x);
+              __trap();
+            }
+          }
+          if (!has_next) break;
         }
       }
     }
@@ -210,15 +237,16 @@ resblock_fwd_z_kernel(const __grid_constant__ Maps maps, const float* __restrict
       }
       ptx::mbar_arrive(&bars[B_AEMPTY]);
       // ---- gate: z = sigmoid(a) * tanh(g), 16 channels at a time, TMEM -> regs -> TMEM (+ kept for the store) ----
-      ptx::mbar_wait(&bars[B_D1F], it & 1);
+      ptx::mbar_wait(&bars[B_D1F0 + (it & 1)], (it >> 1) & 1);
       ptx::tc_fence_after();
+      const uint32_t d1col = kColD1 + (it & 1) * 128;
       float zr[32];
 #pragma unroll
       for (int gg = 0; gg < 2; gg++) {
         const int g = hf * 2 + gg;
         float a[16], t[16], z[16];
-        ptx::tmem_ld16(tmem + lane_base + kColD1 + g * 16, a);
-        ptx::tmem_ld16(tmem + lane_base + kColD1 + 64 + g * 16, t);
+        ptx::tmem_ld16(tmem + lane_base + d1col + g * 16, a);
+        ptx::tmem_ld16(tmem + lane_base + d1col + 64 + g * 16, t);
         float4 ba[4], bt[4];
 #pragma unroll
         for (int i = 0; i < 4; i++) { ba[i] = __ldg(b1v + g * 4 + i); bt[i] = __ldg(b1v + 16 + g * 4 + i); }
@@ -238,7 +266,7 @@ resblock_fwd_z_kernel(const __grid_constant__ Maps maps, const float* __restrict
       if (has_xout) ptx::tc_wait_st();
       ptx::tc_fence_before();
       ptx::mbar_arrive(&bars[B_ZF]);
-      ptx::mbar_arrive(&bars[B_D1E]);
+      ptx::mbar_arrive(&bars[B_D1E0 + (it & 1)]);
       // ---- z -> Z_all slice ----
       if (lane == 0) ptx::bulk_wait_read<0>();
       __syncwarp();

@@ -293,25 +293,31 @@ def test_block_z_and_skip_gemm_vs_fp32_block(d, T, last):
     assert (skip - ref_skip).abs().max().item() <= 4e-3 * ref_skip.abs().max().item()
 
 
-def test_deferred_skip_stack_matches_per_block_training_step():
+@pytest.mark.parametrize("S,depth,repeat,B,T", [
+    (512, 5, 2, 3, 1040),     # T not a multiple of the 128-row tile; CTAs of the segmented dW launches span two blocks
+    (256, 7, 1, 2, 700),      # L*R = 448: dZ_all in 64-column blocks, dWskip in 7 column groups
+    (96, 3, 1, 1, 333),       # S not a multiple of 128: zero-filled rows in the dWskip M-block
+    (512, 3, 2, 1, 100),      # 2 time tiles per block: every CTA of the segmented dW1 / dW2res launch walks through
+                              # all six blocks and recycles both accumulator sets
+])
+def test_deferred_skip_stack_matches_per_block_training_step(S, depth, repeat, B, T):
     """Same model, same batch: WaveNet.forward/backward through the deferred-skip stack (one ABI call per
     direction) vs the per-block tf32 path.  Both are tf32; they differ only in summation order, so logits agree to
     2e-3 abs and every gradient to 3 % (relative Frobenius norm; bias gradients 5 %) -- the gradients at the bottom
     of the stack carry the tf32 rounding of every block above them in both runs."""
     from pytorchwavenetvocoder_b200.nets import cross_entropy
-    cfg = O.Config(256, 28, 64, 512, 5, 2, 2, 16)
+    cfg = O.Config(256, 28, 64, S, depth, repeat, 2, 0)
     p = O.make_params(cfg, 21)
     rng = np.random.RandomState(4)
-    B, T = 3, 1040                       # not a multiple of the 128-row tile
     x = torch.from_numpy(rng.randint(0, 256, size=(B, T)).astype(np.int64)).cuda()
     t = torch.from_numpy(rng.randint(0, 256, size=(B, T)).astype(np.int64)).cuda()
-    h = torch.from_numpy(rng.standard_normal((B, 28, T // 16)).astype(np.float32)).cuda()
+    h = torch.from_numpy(rng.standard_normal((B, 28, T)).astype(np.float32)).cuda()
     res = {}
     for deferred in (False, True):
         net = our_model(cfg, p, math_mode="tf32").train()
         net.deferred_skip = deferred
         y = net(x, h)
-        loss = cross_entropy(y, t, 32)
+        loss = cross_entropy(y, t, min(32, T // 4))
         loss.backward()
         res[deferred] = (y.detach().clone(), loss.item(),
                          {k: (None if v.grad is None else v.grad.clone()) for k, v in net.named_parameters()})
