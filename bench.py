@@ -352,9 +352,9 @@ def run_ours(args):
 TRAFFIC_NCU = {"fp32": None, "tf32": 814.14e6}
 # kernel kinds timed by wnb_profile_read (WNB_PROF_* order) and their ncu DRAM bytes per launch (None = not captured)
 STACK_KINDS = ["fwd_block", "skip_gemm", "dzall_gemm", "gate_bwd", "dx_gemm", "dw1", "dw2res", "dwskip"]
-# profiles/r1_ncu_gate_bwd_summary.txt: gate backward 118.2 MB read + 52.2 MB written (dout and half of dpre stay in
-# L2 between kernels), dx 118.1 + 31.1 MB
-TRAFFIC_NCU_STACK = {"gate_bwd": 170.34e6, "dx_gemm": 149.16e6}
+# profiles/r1_ncu_gate_bwd_summary.txt: gate backward 165.4 MB read + 56.2 MB written (part of dout / dpre stays in
+# L2 between kernels), dx 165.3 + 39.5 MB
+TRAFFIC_NCU_STACK = {"gate_bwd": 221.58e6, "dx_gemm": 204.85e6}
 
 
 def run_decode(args, dev, rank, world, dist):

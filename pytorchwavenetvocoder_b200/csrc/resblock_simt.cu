@@ -12,6 +12,8 @@
 //
 // All activations are channels-last (B,T,C).  Everything here is fp32 FFMA: this is the parity path and
 // the fallback for shapes the tcgen05 path (resblock_tc.cu) does not cover.
+#include <stdlib.h>
+
 #include "gemm_simt.cuh"
 #include "tc_host.h"
 
@@ -347,6 +349,14 @@ static int pick_tchunk(int B, int T, int tiles) {
   chunk = ((chunk + 15) / 16) * 16;
   if (chunk < 64) chunk = 64;
   return chunk;
+}
+
+// N == 512 GEMMs of the post network run as two 256-column blocks: the accumulators are then double-buffered and the
+// epilogue of one tile overlaps the mainloop of the next (-0.2 ms on the 10 ms step); WNB_POST_SPLIT=0 switches it off
+static bool post_split(int S) {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("WNB_POST_SPLIT"); on = (e && e[0] == '0') ? 0 : 1; }
+  return on == 1 && S == 512;
 }
 
 static bool nt_tc_n_ok(int N) { return N % 32 == 0 && N >= 32 && (N <= 256 || N == 512); }
@@ -723,7 +733,12 @@ WNB_API int wnb_post_fwd(float* skip, const float* wp1, const float* bp1, const 
       WNB_CHECK_LAUNCH("relu_inplace");
     }
     const NtTcSeg s1[1] = {{skip, S, 0, S, wp1, S, S, 0, 0}};
-    if ((rc = gemm_nt_tc(s1, 1, S, r1, S, bp1, nullptr, 0, nullptr, 0, 1, 0, B, T, st)) != WNB_OK) return rc;
+    if (post_split(S)) {   // two 256-column blocks: double-buffered accumulators, epilogue overlapped with the next tile
+      const NtTcOpts o{2, 0, 0, 0};
+      if ((rc = gemm_nt_tc(s1, 1, S / 2, r1, S, bp1, nullptr, 0, nullptr, 0, 1, 0, B, T, st, nullptr, nullptr, nullptr, 0, 0,
+                           nullptr, &o)) != WNB_OK)
+        return rc;
+    } else if ((rc = gemm_nt_tc(s1, 1, S, r1, S, bp1, nullptr, 0, nullptr, 0, 1, 0, B, T, st)) != WNB_OK) return rc;
     const NtTcSeg s2[1] = {{r1, S, 0, S, wp2, Q, S, 0, 0}};
     return gemm_nt_tc(s2, 1, Q, logits, Q, bp2, nullptr, 0, nullptr, 0, 0, 0, B, T, st);
   }
@@ -755,9 +770,19 @@ WNB_API int wnb_post_bwd(const float* skip, const float* r1, const float* dlogit
   if (math_mode == WNB_MATH_TF32 && nt_tc_n_ok(S) && nt_tc_n_ok(Q)) {
     // (skip was rectified in place by the tf32 forward, so it doubles as relu(skip) and as the sign mask)
     const NtTcSeg s1[1] = {{dlogits, Q, 0, Q, wp2t, S, Q, 0, 0}};
-    if ((rc = gemm_nt_tc(s1, 1, S, dh1, S, nullptr, r1, S, nullptr, 0, 0, 0, B, T, st)) != WNB_OK) return rc;
     const NtTcSeg s2[1] = {{dh1, S, 0, S, wp1t, S, S, 0, 0}};
-    if ((rc = gemm_nt_tc(s2, 1, S, dskip, S, nullptr, skip, S, nullptr, 0, 0, 0, B, T, st)) != WNB_OK) return rc;
+    if (post_split(S)) {
+      const NtTcOpts o{2, 0, 0, 0};
+      if ((rc = gemm_nt_tc(s1, 1, S / 2, dh1, S, nullptr, r1, S, nullptr, 0, 0, 0, B, T, st, nullptr, nullptr, nullptr, 0, 0,
+                           nullptr, &o)) != WNB_OK)
+        return rc;
+      if ((rc = gemm_nt_tc(s2, 1, S / 2, dskip, S, nullptr, skip, S, nullptr, 0, 0, 0, B, T, st, nullptr, nullptr, nullptr, 0,
+                           0, nullptr, &o)) != WNB_OK)
+        return rc;
+    } else {
+      if ((rc = gemm_nt_tc(s1, 1, S, dh1, S, nullptr, r1, S, nullptr, 0, 0, 0, B, T, st)) != WNB_OK) return rc;
+      if ((rc = gemm_nt_tc(s2, 1, S, dskip, S, nullptr, skip, S, nullptr, 0, 0, 0, B, T, st)) != WNB_OK) return rc;
+    }
     if ((rc = wgrad_tc_split(dlogits, Q, Q, r1, S, S, dwp2, S, dbp2, B, T, st)) != WNB_OK) return rc;
     return wgrad_tc_split(dh1, S, S, skip, S, S, dwp1, S, dbp1, B, T, st);
   }
