@@ -3,10 +3,14 @@
 // A rows are time steps (K-major operand straight from the (B,T,C) tensor, TMA zero fill outside [0,T) =
 // causal / anti-causal padding), W is a row-major [N][K] weight matrix (K-major operand).  tcgen05.mma
 // kind::tf32, fp32 accumulate in TMEM (whole 128 x N tile; double buffered when N <= 256).
-// Epilogue (4 warps, one TMEM lane quarter each): + bias, ReLU, * (mask > 0), + residual, then a swizzled
-// per-warp staging box and a TMA store or TMA reduce-add (.add.f32) into the (B,T,N) output.
-// Used for: the post network forward (wavenet.py:518-523) and backward, the residual-stream data
-// gradient dX (two time-shifted segments) and the aux gradient dhaux (reduce-add).
+// Epilogue (8 warps = TMEM lane quarter x alternate 32-column chunks, two per SM sub-partition): + bias, ReLU,
+// * (mask > 0), + residual (operands that do not depend on the accumulator are requested before waiting for it), then
+// a swizzled per-warp staging box and a TMA store or TMA reduce-add (.add.f32) into the (B,T,N) output; gate forward /
+// backward epilogues for the residual blocks.  The kernel is instantiated per epilogue kind (EPI_*) so each variant
+// gets its own register allocation.  Options: column blocks (tiles ordered block-fastest so the A tile is shared
+// through L2), split output, programmatic dependent launch.
+// Used for: the post network forward (wavenet.py:518-523) and backward, the hoisted skip GEMMs, the gate backward,
+// the residual-stream data gradient dX (two time-shifted segments) with the aux gradient dhaux (reduce-add).
 #include <cuda.h>
 #include <stdio.h>
 #include <stdlib.h>

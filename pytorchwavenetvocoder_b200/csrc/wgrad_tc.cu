@@ -6,7 +6,10 @@
 // gradient tensors with no transpose, and tcgen05.mma kind::tf32 (a_major = b_major = MN) contracts
 // 8 time steps per instruction into a [128 x N] fp32 accumulator that stays resident in TMEM for ALL
 // time tiles a CTA owns.  One persistent CTA per SM, 3 warp roles (TMA producer, MMA issuer, epilogue);
-// at the end the accumulator is flushed once with fp32 atomics (red.global.add).
+// at the end the accumulator is flushed once with fp32 vector reductions (red.global.add.v4.f32).
+// Launch shapes: up to 5 M-blocks sharing one B operand; column groups of B across CTAs (n_split, A shared through
+// L2); segments = many independent problems of one structure (every residual block's dW1) in one launch, the CTAs
+// splitting the flattened (segment, time tile) space with two alternating accumulator sets.
 //
 // Generic over "sub-tile lists": A = 4 groups of 32 channels (M = 128), B = up to 7 groups (N <= 224),
 // each group = (tensor map, channel offset, time shift); dilated taps are just shifted groups, zero filled

@@ -36,6 +36,30 @@ def test_argument_validation_without_gpu():
     assert rc == -1
 
 
+def test_stack_entry_points_host_logic_without_gpu():
+    """Shape coverage, workspace arithmetic and argument checks of the deferred-skip stack ABI (no kernels run)."""
+    import ctypes
+    from pytorchwavenetvocoder_b200 import _lib
+    lib = _lib.load()
+    TF32, FP32 = _lib.MATH_TF32, _lib.MATH_FP32
+    assert lib.wnb_stack_supported(64, 512, 32, 2, 30, TF32) == 1        # BASELINE family
+    assert lib.wnb_stack_supported(64, 256, 32, 2, 7, TF32) == 1
+    assert lib.wnb_stack_supported(64, 512, 32, 2, 30, FP32) == 0        # fp32 mode: per-block FFMA path
+    assert lib.wnb_stack_supported(512, 256, 96, 3, 30, TF32) == 0       # recipe shape: composed per-block path
+    assert lib.wnb_stack_supported(64, 384, 32, 2, 30, TF32) == 0        # skip GEMM needs S <= 256 or S == 512
+    L, B, T, R = 30, 8, 23040, 64
+    bt = B * T
+    assert lib.wnb_stack_bwd_workspace(L, B, T, R, 512, 32, 2) == 4 * (bt * L * R + L * R + L * bt * 2 * R + L * bt * R)
+    rc = lib.wnb_stack_fwd(None, 2, None, None, None, None, None, None, None, None, None, None, 30, 8, 100, 64, 512,
+                           32, 2, 1, None)
+    assert rc == -1 and b"null pointer" in lib.wnb_last_error()
+    rc = lib.wnb_resblock_fwd_z(None, None, None, None, None, None, None, None, 64, 0, 0, 0, 64, 32, 2, 1, None)
+    assert rc == -1 and b"bad shape" in lib.wnb_last_error()
+    tot, n = ctypes.c_double(0.0), ctypes.c_int(0)
+    assert lib.wnb_profile_read(99, ctypes.byref(tot), ctypes.byref(n)) == -1
+    assert lib.wnb_profile_enable(0) == 0 and lib.wnb_profile_read(0, ctypes.byref(tot), ctypes.byref(n)) == 0 and n.value == 0
+
+
 def test_no_cpu_fallback():
     import torch
     from pytorchwavenetvocoder_b200 import _lib
