@@ -15,6 +15,7 @@
 //
 // Z_all is written once and read twice per step (it replaces the z recompute output of the per-block backward).
 #include <cuda_runtime.h>
+#include <stdlib.h>
 
 #include "../../include/wnb200.h"
 #include "common.cuh"
@@ -196,15 +197,27 @@ WNB_API int wnb_stack_bwd(const float* xs, const float* haux, const float* zall,
     if ((rc = wgrad_tc_blocks(&blk, 1, bz, 1, R, B, T, st, &o)) != WNB_OK) return rc;
   }
 
-  {  // dWskip (S x L*R) += dskip^T Z_all, dbskip = column sums of dskip
+  {  // dWskip (S x L*R) += dskip^T Z_all, dbskip = column sums of dskip.  M-blocks per launch x columns per CTA is a
+     // trade: fewer M-blocks leave TMEM for wider column groups (fewer CTAs re-reading the same dskip tile through L2,
+     // fewer wasted bias columns per MMA) at the price of one launch per group of M-blocks.  Measured at the bench
+     // shape: 4 M-blocks x 96 columns = one 827 us launch, 2 M-blocks x 192 columns = two 313 us launches.
+     // WNB_DWSKIP_MB overrides (1..4).
+    static int mb_per_launch = 0;
+    if (!mb_per_launch) {
+      const char* e = getenv("WNB_DWSKIP_MB");
+      mb_per_launch = e ? atoi(e) : 2;
+      if (mb_per_launch < 1 || mb_per_launch > 4) mb_per_launch = 2;
+    }
     const int groups = ldz / 32;
+    const int nmb = (S + 127) / 128 < mb_per_launch ? (S + 127) / 128 : mb_per_launch;
     int nB = 0;
-    for (int c = 3; c >= 1 && !nB; c--)
-      if (groups % c == 0) nB = c;
-    for (int r0 = 0; r0 < S; r0 += 512) {
+    for (int c = 512 / nmb / 32 - 1 < 7 ? 512 / nmb / 32 - 1 : 7; c >= 1 && !nB; c--)
+      if (groups % c == 0 && groups / c <= 128) nB = c;
+    WNB_REQUIRE(nB > 0, "stack_bwd: cannot split L*R into column groups");
+    for (int r0 = 0; r0 < S; r0 += 128 * nmb) {
       WgBlock blk[4];
       int nblk = 0;
-      for (int r = r0; r < S && nblk < 4; r += 128, nblk++) {
+      for (int r = r0; r < S && nblk < nmb; r += 128, nblk++) {
         blk[nblk].nops = 1;
         blk[nblk].ops[0] = WgOperand{dskip, S, r, 4, 0};
         blk[nblk].c = dwskip + (size_t)r * ldz;
