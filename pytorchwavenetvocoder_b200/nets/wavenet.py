@@ -511,6 +511,17 @@ class WaveNet(nn.Module):
         Wp2 = self.conv_post_2.weight[..., 0].contiguous()
         return wf, bf, W1, b1, W2, b2, Wp1, self.conv_post_1.bias, Wp2, self.conv_post_2.bias
 
+    def _pack_stack(self, packed):
+        """Operands of the deferred-skip stack (csrc/stack.cu) from ``_pack()``'s: W2 / b2 split into the residual part
+        ``W2res (L,R,R)``, ``b2res (L,R)`` and the skip GEMM operand over the concatenated gate outputs
+        ``Wskip (S, L*R)`` with ``Wskip[s][l*R + c] = skip_1x1[l].weight[s][c]``, ``bskip (S) = sum_l skip_1x1[l].bias``."""
+        wf, bf, W1, b1, W2, b2, Wp1, bp1, Wp2, bp2 = packed
+        R, S, L = self.n_resch, self.n_skipch, len(self.dilations)
+        W2res, b2res = W2[:, :R].contiguous(), b2[:, :R].contiguous()
+        Wskip = W2[:, R:].permute(1, 0, 2).reshape(S, L * R).contiguous()
+        bskip = b2[:, R:].sum(0)
+        return wf, bf, W1, b1, W2res, b2res, Wskip, bskip, Wp1, bp1, Wp2, bp2
+
     def _aux(self, h, upsample=True):
         """(B, A, T or T/U) -> channels-last (B, T, Ap) with the up-sampling layer applied."""
         if h.size(1) != self.n_aux:
@@ -530,13 +541,7 @@ class WaveNet(nn.Module):
                 tuple(self.dilations), self._math())
         if getattr(self, "deferred_skip", True) and _lib.load().wnb_stack_supported(self.n_resch, self.n_skipch, self.n_aux_pad, self.kernel_size,
                                            len(self.dilations), self._math()):
-            # deferred-skip form: split W2 / b2 into the residual part and the concatenated skip GEMM operand
-            wf, bf, W1, b1, W2, b2, Wp1, bp1, Wp2, bp2 = packed
-            R, S, L = self.n_resch, self.n_skipch, len(self.dilations)
-            W2res, b2res = W2[:, :R].contiguous(), b2[:, :R].contiguous()
-            Wskip = W2[:, R:].permute(1, 0, 2).reshape(S, L * R).contiguous()      # [s][l*R + c]
-            bskip = b2[:, R:].sum(0)
-            return _WaveNetStackFn.apply(x, haux, wf, bf, W1, b1, W2res, b2res, Wskip, bskip, Wp1, bp1, Wp2, bp2, meta)
+            return _WaveNetStackFn.apply(x, haux, *self._pack_stack(packed), meta)
         return _WaveNetFn.apply(x, haux, *packed, meta)
 
     def forward(self, x, h):

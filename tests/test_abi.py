@@ -78,3 +78,31 @@ def test_product_does_not_import_oracle():
             if fn.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dp, fn)).read()
                 assert "import oracle" not in txt and "from oracle" not in txt, fn
+
+
+def test_stack_weight_packing_on_cpu():
+    """WaveNet._pack_stack (pure torch ops, no kernels): layouts documented in include/wnb200.h, and gradients flow
+    back to the reference-shaped parameters (the last block's res_1x1 stays out of the graph, like the reference)."""
+    import numpy as np
+    import torch
+    from pytorchwavenetvocoder_b200.nets import WaveNet
+    torch.manual_seed(0)
+    net = WaveNet(256, 28, 64, 96, 3, 2, 2, 0)
+    for prm in net.parameters():
+        torch.nn.init.normal_(prm, std=0.1)
+    wf, bf, W1, b1, W2res, b2res, Wskip, bskip, Wp1, bp1, Wp2, bp2 = net._pack_stack(net._pack())
+    L, R, S = 6, 64, 96
+    assert W1.shape == (L, 2 * R, 2 * R + 32) and W2res.shape == (L, R, R) and Wskip.shape == (S, L * R)
+    sd = {k: v.detach().numpy() for k, v in net.state_dict().items()}
+    for l in range(L):
+        assert np.array_equal(Wskip[:, l * R:(l + 1) * R].detach().numpy(), sd["skip_1x1.%d.weight" % l][:, :, 0])
+        assert np.array_equal(W2res[l].detach().numpy(), sd["res_1x1.%d.weight" % l][:, :, 0])
+        # W1 rows: sigmoid branch then tanh branch; columns: tap 0 (oldest), tap 1, aux (zero padded to 32)
+        assert np.array_equal(W1[l, :R, :R].detach().numpy(), sd["dil_sigmoid.%d.conv.weight" % l][:, :, 0])
+        assert np.array_equal(W1[l, R:, R:2 * R].detach().numpy(), sd["dil_tanh.%d.conv.weight" % l][:, :, 1])
+        assert np.array_equal(W1[l, :R, 2 * R:2 * R + 28].detach().numpy(), sd["aux_1x1_sigmoid.%d.weight" % l][:, :, 0])
+        assert np.all(W1[l, :, 2 * R + 28:].detach().numpy() == 0)
+    assert np.allclose(bskip.detach().numpy(), sum(sd["skip_1x1.%d.bias" % l] for l in range(L)), atol=1e-6)
+    (Wskip.sum() + W2res.sum() + b2res.sum() + bskip.sum()).backward()
+    assert net.skip_1x1[0].weight.grad is not None and net.res_1x1[0].weight.grad is not None
+    assert net.res_1x1[L - 1].weight.grad is None and net.res_1x1[L - 1].bias.grad is None
