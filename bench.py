@@ -421,13 +421,122 @@ def run_decode(args, dev, rank, world, dist):
     }
 
 
+def _ref_nets():
+    """The UNMODIFIED reference ``wavenet_vocoder.nets.wavenet`` from git-ignored baseline/_ref (installed by
+    baseline/install_ref.py in the build container; it travels to the GPU box).  None if it is not there."""
+    try:
+        from baseline.install_ref import import_ref
+        return import_ref()
+    except Exception:
+        return None
+
+
+def _ref_model(R, seed=20260924):
+    torch.manual_seed(seed)
+    m = R.WaveNet(*CFG)
+    m.apply(R.initialize)
+    with torch.no_grad():
+        for name, prm in m.named_parameters():
+            if name.endswith("bias"):
+                prm.add_(0.05 * torch.randn_like(prm))
+    return m
+
+
+def _thread_candidates():
+    n = os.cpu_count() or 1
+    return [c for c in (4, 8, 16, 32, 64) if c <= n] or [n]
+
+
 def cpu_baseline(args, workload, decode=False, steps=None):
-    """The reference's op sequence on the host cores (oracle/torch_port.py), bounded sample."""
+    """The reference's own code on the host cores: baseline/_ref (kind "reference") when it travelled with the
+    snapshot, else oracle/torch_port.py (kind "port").  Bounded sample; the thread count is the best of a short
+    sweep (torch's CPU conv path collapses when oversubscribed: 183 s/step with 128 threads on the GPU host vs
+    1.2 s with 16), `cores` reports the threads actually used and `thread_sweep` the sweep."""
+    R = _ref_nets()
+    cfg = _Cfg(CFG)
+    rf = cfg.receptive_field
+    if R is None:
+        return _cpu_baseline_port(args, decode, steps)
+    Q = cfg.n_quantize
+    if decode:
+        m = _ref_model(R).eval()
+        B = 8
+        g = torch.Generator().manual_seed(1)
+        x = torch.full((B, 1), Q // 2, dtype=torch.int64)
+
+        def run(n):
+            h = torch.randn(B, cfg.n_aux, (n + 1 + cfg.upsampling_factor - 1) // cfg.upsampling_factor, generator=g)
+            t0 = time.time()
+            with torch.no_grad():
+                m.batch_fast_generate(x, h, [n] * B, None, "argmax")
+            return time.time() - t0
+        sweep = {}
+        run(4)                         # one-time initialisations out of the way
+        for c in _thread_candidates():
+            torch.set_num_threads(c)
+            run(4)
+            a, b = run(8), run(48)
+            sweep[c] = B * 40 / (b - a) if b - a > 1e-3 else 0.0
+            if c >= 16 and sweep[c] < 0.5 * max(sweep.values()):
+                break
+        cores = max(sweep, key=sweep.get)
+        torch.set_num_threads(cores)
+        a, b = run(20), run(100)      # differencing removes the receptive-field warm-up (BASELINE.md section 2)
+        v = B * 80 / max(b - a, 1e-9)
+        return {"value": v, "unit": "samples/s", "cores": cores, "kind": "reference",
+                "sample": "reference batch_fast_generate B=8 argmax, 100 vs 20 samples differenced, torch CPU fp32",
+                "thread_sweep": {str(k): v_ for k, v_ in sweep.items()}}
+    m = _ref_model(R).train()
+    crit = torch.nn.CrossEntropyLoss()
+    opt = torch.optim.Adam(m.parameters(), lr=1e-4)
+
+    def step(x, h, t):
+        y = m(x, h)
+        loss = crit(y[:, rf:].contiguous().view(-1, Q), t[:, rf:].contiguous().view(-1))   # reference train.py:534-536
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        return float(loss.detach())
+
+    # thread sweep on a short window (rf + 130 samples -> 3200), one warm-up + one timed step each
+    U = cfg.upsampling_factor
+    gs = torch.Generator().manual_seed(7)
+    Ts = ((rf + 130 + U - 1) // U) * U
+    xs_ = torch.randint(0, Q, (1, Ts + 1), generator=gs)
+    hs_ = torch.randn(1, cfg.n_aux, Ts // U, generator=gs)
+    sweep = {}
+    for c in _thread_candidates():
+        torch.set_num_threads(c)
+        step(xs_[:, :-1], hs_, xs_[:, 1:])
+        t0 = time.time()
+        step(xs_[:, :-1], hs_, xs_[:, 1:])
+        sweep[c] = time.time() - t0
+        if c >= 16 and sweep[c] > 2.0 * min(sweep.values()):
+            break      # oversubscription cliff: do not go further up
+    cores = min(sweep, key=sweep.get)
+    torch.set_num_threads(cores)
+    x, h, t = synth_batch(cfg, 0, 1, pinned=False)
+    t0 = time.time()
+    step(x, h, t)
+    warm = time.time() - t0
+    k = steps or 2
+    if warm > 15.0:       # keep the whole baseline leg bounded: count the warm-up step itself
+        k, dt = 1, warm
+    else:
+        t0 = time.time()
+        for _ in range(k):
+            step(x, h, t)
+        dt = (time.time() - t0) / k
+    return {"value": BATCH_LENGTH / dt, "unit": "samples/s", "cores": cores, "kind": "reference",
+            "sample": "%d step(s) of 1 x %d-sample window (fwd+CE+bwd+Adam) through the unmodified reference "
+                      "wavenet_vocoder.nets.WaveNet (baseline/_ref), torch CPU fp32, after 1 warm-up" % (k, x.shape[1]),
+            "sec_per_step": dt, "thread_sweep_sec_short_window": {str(k_): v_ for k_, v_ in sweep.items()}}
+
+
+def _cpu_baseline_port(args, decode=False, steps=None):
+    """Fallback when baseline/_ref did not travel: the reference's op sequence restated on torch CPU ops."""
     from oracle import torch_port as TP
     from oracle import wavenet_oracle as O
-    # torch's CPU conv path collapses when oversubscribed (measured on the 128-core GPU host: 183 s/step
-    # with 128 threads vs 2.5 s with 8 on the build container), so the port runs on at most 16 threads:
-    # `cores` reports the threads actually used.
     cores = min(os.cpu_count() or 1, 16)
     torch.set_num_threads(cores)
     cfg = O.Config(*CFG)
@@ -442,7 +551,7 @@ def cpu_baseline(args, workload, decode=False, steps=None):
             t0 = time.time()
             TP.batch_fast_generate(cfg, p, x, h, [n] * B, "argmax")
             return time.time() - t0
-        a, b = run(20), run(60)       # differencing removes the receptive-field warm-up
+        a, b = run(20), run(60)
         v = B * 40 / max(b - a, 1e-9)
         return {"value": v, "unit": "samples/s", "cores": cores, "kind": "port",
                 "sample": "batch_fast_generate B=8, 60 vs 20 samples differenced, torch CPU fp32"}
@@ -453,7 +562,7 @@ def cpu_baseline(args, workload, decode=False, steps=None):
     TP.train_step(cfg, p, opt, x, h, t)
     warm = time.time() - t0
     k = steps or 2
-    if warm > 15.0:       # keep the whole baseline leg bounded: count the warm-up step itself
+    if warm > 15.0:
         k, dt = 1, warm
     else:
         t0 = time.time()
@@ -469,8 +578,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
-    from oracle import wavenet_oracle as O
-    cfg = O.Config(*CFG)
+    cfg = _Cfg(CFG)
     decode = args.workload == "decode"
     k = max(1, min(args.steps, 3))
     cb = cpu_baseline(args, "", decode=decode, steps=k)

@@ -121,13 +121,13 @@ def causal_conv(x, W, b, d=1):
     for k in range(ks):
         s = (ks - 1 - k) * d
         if s < T:
-            y[:, :, s:] += np.einsum("oc,bct->bot", W[:, :, k], x[:, :, :T - s])
+            y[:, :, s:] += np.matmul(W[:, :, k], x[:, :, :T - s])   # (O,C) @ (B,C,T') -> (B,O,T'), BLAS
     return y
 
 
 def conv1x1(x, W, b):
     """nn.Conv1d(C, O, 1), wavenet.py:203-210."""
-    return np.einsum("oc,bct->bot", W[:, :, 0], x) + b[None, :, None]
+    return np.matmul(W[:, :, 0], x) + b[None, :, None]
 
 
 def front_embed(x, W, b):
@@ -219,9 +219,9 @@ def cross_entropy(logits, target, start):
 # manual backward (what autograd does for bin/train.py:537-538); returns grads by key
 # --------------------------------------------------------------------------------------
 def _conv1x1_bwd(x, W, dy):
-    dW = np.einsum("bot,bct->oc", dy, x)[:, :, None]
+    dW = np.matmul(dy, np.transpose(x, (0, 2, 1))).sum(axis=0)[:, :, None]   # sum_b dy[b] x[b]^T
     db = dy.sum(axis=(0, 2))
-    dx = np.einsum("oc,bot->bct", W[:, :, 0], dy)
+    dx = np.matmul(W[:, :, 0].T, dy)
     return dx, dW, db
 
 
@@ -233,8 +233,8 @@ def _causal_conv_bwd(x, W, dy, d):
     for k in range(ks):
         s = (ks - 1 - k) * d
         if s < T:
-            dW[:, :, k] = np.einsum("bot,bct->oc", dy[:, :, s:], x[:, :, :T - s])
-            dx[:, :, :T - s] += np.einsum("oc,bot->bct", W[:, :, k], dy[:, :, s:])
+            dW[:, :, k] = np.matmul(dy[:, :, s:], np.transpose(x[:, :, :T - s], (0, 2, 1))).sum(axis=0)
+            dx[:, :, :T - s] += np.matmul(W[:, :, k].T, dy[:, :, s:])
     return dx, dW, dy.sum(axis=(0, 2))
 
 

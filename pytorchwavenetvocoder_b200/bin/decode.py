@@ -121,6 +121,10 @@ def get_parser():
 
 def gpu_decode(feat_list, gpu, args, config):
     """One process per GPU (reference decode.py:274-327)."""
+    # spawned workers do not inherit main()'s RNG state (the reference forks after seeding, decode.py:242):
+    # re-seed here so that --seed controls the Philox stream of every GPU (distinct per GPU, reproducible)
+    np.random.seed(args.seed + gpu)
+    torch.manual_seed(args.seed + gpu)
     with torch.cuda.device(gpu):
         with torch.no_grad():
             upsampling_factor = config.upsampling_factor if config.use_upsampling_layer else 0

@@ -5,9 +5,9 @@
 Same command line (reference train.py:337-394), same ``model.conf`` / ``checkpoint-*.pkl`` formats
 (:315-332, :429, :564-568), same batching arithmetic (``train_generator`` :67-312), same loop (:530-561).
 What changes underneath: ``WaveNet`` is the sm_100a kernel build, the loss is the fused CE kernel, and
-``--n_gpus N`` means N *processes* (launch with ``torchrun --nproc-per-node N``; one rank per GPU, a
-single flat NCCL all-reduce of the gradients per step) instead of single-process ``nn.DataParallel``
-(:449-454).  Extra, optional flags: ``--math_mode {tf32,fp32}``.
+``--n_gpus N`` means N *processes* (the command re-launches itself under ``torch.distributed.run``; one rank per
+GPU, a single flat NCCL all-reduce of the gradients per step) instead of single-process ``nn.DataParallel``
+(:449-454).  ``--batch_size`` stays the GLOBAL batch: every rank trains on ``batch_size / n_gpus`` windows of it.  Extra, optional flags: ``--math_mode {tf32,fp32}``.
 """
 from __future__ import division
 
@@ -236,9 +236,24 @@ def main():
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
+    if args.n_gpus > 1 and "WORLD_SIZE" not in os.environ:
+        # the recipes call `train.py --n_gpus N` as ONE process (reference nn.DataParallel, train.py:449-454); the
+        # B200 build runs one process per GPU, so re-launch this command line under torch.distributed.run
+        import socket
+        with socket.socket() as s_:
+            s_.bind(("127.0.0.1", 0))
+            port = s_.getsockname()[1]
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.n_gpus),
+               "--master-addr", "127.0.0.1", "--master-port", str(port), "-m", "pytorchwavenetvocoder_b200.bin.train"]
+        logging.info("re-launching with one process per GPU: %s" % " ".join(cmd))
+        os.execv(sys.executable, cmd + sys.argv[1:])
     if args.n_gpus > 1 and world != args.n_gpus:
-        logging.error("--n_gpus %d needs `torchrun --nproc-per-node %d` (one process per GPU) in the B200 build."
-                      % (args.n_gpus, args.n_gpus))
+        logging.error("--n_gpus %d but WORLD_SIZE is %d (launch with `torchrun --nproc-per-node %d`)."
+                      % (args.n_gpus, world, args.n_gpus))
+        sys.exit(1)
+    if args.batch_length > 0 and args.batch_size % world != 0:
+        # --batch_size stays the GLOBAL batch (the reference scatters one batch over the GPUs, train.py:449-454)
+        logging.error("--batch_size %d is not divisible by the number of GPUs %d." % (args.batch_size, world))
         sys.exit(1)
     if not torch.cuda.is_available():
         logging.error("gpu is not available. please check the setting.")   # reference train.py:523-525
@@ -250,7 +265,9 @@ def main():
     if rank == 0 and not os.path.exists(args.expdir):
         os.makedirs(args.expdir)
     os.environ['PYTHONHASHSEED'] = str(args.seed)
-    np.random.seed(args.seed + rank)
+    # every rank draws the SAME shuffles and therefore sees the same sequence of global batches; rank r trains on
+    # rows [r*B/world, (r+1)*B/world) of each (torch.chunk order, like DataParallel's scatter)
+    np.random.seed(args.seed)
     torch.manual_seed(args.seed)
     if rank == 0:
         torch.save(args, args.expdir + "/model.conf")
@@ -274,7 +291,8 @@ def main():
     model.math_mode = args.math_mode if (args.math_mode == "fp32" or tc_supported(cfg_t)) else "fp32"
     logging.info("math_mode = %s" % model.math_mode)
 
-    optimizer = torch.optim.Adam(model.parameters(), lr=args.lr, weight_decay=args.weight_decay)
+    model.cuda()   # before the optimizer: the fused (single multi-tensor kernel) Adam needs CUDA parameters
+    optimizer = torch.optim.Adam(model.parameters(), lr=args.lr, weight_decay=args.weight_decay, fused=True)
 
     scaler = StandardScaler()
     scaler.mean_ = read_hdf5(args.stats, "/" + args.feature_type + "/mean")
@@ -317,7 +335,6 @@ def main():
     else:
         iterations = 0
 
-    model.cuda()
     for state in optimizer.state.values():
         for key, value in state.items():
             if torch.is_tensor(value):
@@ -327,11 +344,15 @@ def main():
         from pytorchwavenetvocoder_b200.parallel import GradAllReduce
         sync = GradAllReduce(model)
 
-    loss = 0
+    loss = torch.zeros((), device="cuda")    # summed on the device: no host sync per step (reference :540 syncs)
     total = 0
+    debug = logging.getLogger().isEnabledFor(logging.DEBUG)
     for i in range(iterations, args.iters):
         start = time.time()
         (batch_x, batch_h), batch_t = generator.next()
+        if world > 1 and batch_x.size(0) > 1:
+            per = batch_x.size(0) // world
+            batch_x, batch_h, batch_t = (v[rank * per:(rank + 1) * per].contiguous() for v in (batch_x, batch_h, batch_t))
         batch_output = model(batch_x, batch_h)
         batch_loss = cross_entropy(batch_output, batch_t, model.receptive_field)   # CE on [:, receptive_field:]
         optimizer.zero_grad()
@@ -339,18 +360,23 @@ def main():
         if sync is not None:
             sync.allreduce()
         optimizer.step()
-        loss_value = batch_loss.item()
-        loss += loss_value
+        loss += batch_loss.detach()
         total += time.time() - start
-        logging.debug("batch loss = %.3f (%.3f sec / batch)" % (loss_value, time.time() - start))
+        if debug:
+            logging.debug("batch loss = %.3f (%.3f sec / batch)" % (batch_loss.item(), time.time() - start))
 
         if (i + 1) % args.intervals == 0:
+            loss_sum = float(loss)
+            if world > 1:   # equal per-rank batches: the global mean is the mean of the rank means
+                lt = loss.clone()
+                torch.distributed.all_reduce(lt)
+                loss_sum = float(lt) / world
+            loss.zero_()
             logging.info("(iter:%d) average loss = %.6f (%.3f sec / batch)" % (
-                i + 1, loss / args.intervals, total / args.intervals))
+                i + 1, loss_sum / args.intervals, total / args.intervals))
             remain = int((args.iters - (i + 1)) * (total / args.intervals))
             logging.info("estimated required time = %02d:%02d:%02d:%02d" % (
                 remain // 86400, remain % 86400 // 3600, remain % 3600 // 60, remain % 60))
-            loss = 0
             total = 0
 
         if (i + 1) % args.checkpoint_interval == 0 and rank == 0:

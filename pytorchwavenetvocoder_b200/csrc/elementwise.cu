@@ -262,6 +262,10 @@ __global__ void cross_entropy_kernel(const float* __restrict__ logits, const int
     s = warp_sum(s);
     const float lse = m + logf(s);
     int64_t tg = target[row];
+    if (tg < 0 || tg >= Q) {   // torch's CrossEntropyLoss asserts here; flag it loudly instead of reading out of bounds
+      if (lane == 0) local += (double)NAN;
+      tg = 0;
+    }
     if (lane == 0) local += (double)(lse - lg[tg]);
     if (dl) {
       const float inv_s = 1.0f / s;

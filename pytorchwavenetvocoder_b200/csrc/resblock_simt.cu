@@ -742,7 +742,7 @@ WNB_API int wnb_post_fwd(float* skip, const float* wp1, const float* bp1, const 
     const NtTcSeg s2[1] = {{r1, S, 0, S, wp2, Q, S, 0, 0}};
     return gemm_nt_tc(s2, 1, Q, logits, Q, bp2, nullptr, 0, nullptr, 0, 0, 0, B, T, st);
   }
-  WNB_REQUIRE(!skip_rectified, "post_fwd: skip_rectified is a tf32-path option");
+  // (skip_rectified: the FFMA GEMM below applies ReLU to its B operand anyway, and ReLU is idempotent)
   {  // r1 = relu(wp1 * relu(skip) + bp1)
     NtParams p{};
     p.nseg = 1; p.seg[0] = NtSeg{wp1, S, skip, S, 0, S};

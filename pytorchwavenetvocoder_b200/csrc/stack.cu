@@ -31,7 +31,8 @@ static int pick_block(int total, const int* cands, int n) {
 
 static bool stack_supported(int R, int S, int Ap, int ks, int L) {
   if (!resblock_fwd_z_supported(R, Ap, ks)) return false;
-  if (L < 1 || S % 32 != 0 || S < 32 || (S > 256 && S != 512)) return false;
+  if (L < 1 || L > 64 /* wnb_stack_bwd's segment table, wgrad kMaxSeg */) return false;
+  if (S % 32 != 0 || S < 32 || (S > 256 && S != 512)) return false;
   return true;
 }
 

@@ -138,6 +138,9 @@ class _CrossEntropyFn(torch.autograd.Function):
         logits = logits.contiguous()
         target = target.contiguous()
         B, T, Q = logits.shape
+        if target.dtype != torch.int64 or tuple(target.shape) != (B, T) or target.device != logits.device:
+            raise ValueError("cross_entropy: target should be an int64 (B, T) = %s tensor on %s, got %s %s on %s"
+                             % ((B, T), logits.device, target.dtype, tuple(target.shape), target.device))
         loss = torch.zeros(1, device=logits.device, dtype=torch.float64)
         need = ctx.needs_input_grad[0]
         dl = torch.empty_like(logits) if need else None
@@ -374,7 +377,10 @@ class CausalConv1d(nn.Module):
         Inside ``WaveNet`` the convolution runs in the fused block kernels; this standalone form exists for API
         compatibility and goes through ``wnb_causal_conv1d_fwd`` (no autograd)."""
         if torch.is_grad_enabled() and (x.requires_grad or self.conv.weight.requires_grad):
-            x = x.detach()   # forward only: gradients flow through WaveNet.forward, not through this helper
+            # the reference module is a differentiable Conv1d; this standalone helper has no backward kernel, and a
+            # silently detached result would train nothing -- say so instead
+            raise RuntimeError("CausalConv1d.forward is inference-only in the B200 build (no standalone backward): "
+                               "call it under torch.no_grad(); training goes through WaveNet.forward")
         lib = _lib.load()
         if not x.is_cuda:
             raise _lib.WnbError("CausalConv1d.forward needs CUDA tensors: the B200 build has no CPU fallback")

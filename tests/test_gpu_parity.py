@@ -290,7 +290,10 @@ def test_causal_conv1d_standalone():
     for cin, cout, ks, d in ((5, 7, 2, 1), (32, 16, 3, 4), (64, 64, 2, 16)):
         m = CausalConv1d(cin, cout, ks, d).cuda()
         x = torch.randn(2, cin, 70).cuda()
-        y = m(x)
+        with pytest.raises(RuntimeError):     # no standalone backward: refuses to hand out a detached tensor silently
+            m(x)
+        with torch.no_grad():
+            y = m(x)
         assert tuple(y.shape) == (2, cout, 70)
         ref = O.causal_conv(x.cpu().numpy().astype(np.float64), m.conv.weight.detach().cpu().numpy().astype(np.float64),
                             m.conv.bias.detach().cpu().numpy().astype(np.float64), d)
