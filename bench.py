@@ -162,8 +162,7 @@ def run_ours(args):
         rf = cfg.receptive_field
 
         def step(x, h, t):
-            y = net(x, h)
-            loss = cross_entropy(y, t, rf)
+            loss = net.forward_loss(x, h, t, rf)     # = cross_entropy(net(x, h), t, rf) as one autograd node
             opt.zero_grad(set_to_none=True)
             loss.backward()
             if sync is not None:

@@ -99,6 +99,30 @@ WNB_API int wnb_resblock_fwd_supported(int R, int S, int Ap, int ks, int math_mo
 WNB_API int wnb_causal_conv1d_fwd(const float* x, const float* w, const float* bias, float* out, int B, int T,
                                   int Cin, int Cout, int ks, int dilation, void* stream);
 
+/* ---- pack_weights: state_dict layout <-> kernel layout as one launch per direction ----------
+ * A table of strided 3-D copies dst[i0*ds0 + i1*ds1 + i2*ds2] = scale * f(src[i0*ss0 + i1*ss1 + i2*ss2]) executed by
+ * one kernel (one block row per entry).  `src` / `src2` are absolute device pointers (WNB_PACK_SRC_ABS: the
+ * reference-shaped nn.Parameters of wavenet.py:188-210) or element offsets from `src_base`; `dst` is an element
+ * offset from `dst_base`.  Ops: COPY; ADD2 = src + src2 (dilated-conv bias + aux bias, wavenet.py:527-532);
+ * SUMPTR = sum over a device table (at `src`) of `nsum` equally shaped tensors (the summed skip biases).
+ * Forward: parameters -> packed buffer (layouts above, plus the transposes the backward wants).  Backward: packed
+ * gradient buffer -> one flat buffer holding every parameter's .grad, scaled by the device scalar `scale` (NULL = 1). */
+#define WNB_PACK_COPY 0
+#define WNB_PACK_ADD2 1
+#define WNB_PACK_SUMPTR 2
+#define WNB_PACK_SRC_ABS 1
+typedef struct WnbPackDesc {
+  int64_t src, src2, dst;
+  int32_t n0, n1, n2;
+  int32_t ss0, ss1, ss2;
+  int32_t ds0, ds1, ds2;
+  int32_t op, flags, nsum;
+} WnbPackDesc;
+WNB_API int wnb_pack_weights(const WnbPackDesc* descs /*device*/, int ndesc, const float* src_base, float* dst_base,
+                             const float* scale /*device scalar or NULL*/, void* stream);
+/* cudaMemsetAsync(p, 0, bytes) on `stream`: gradient accumulators the kernels add into */
+WNB_API int wnb_zero(void* p, size_t bytes, void* stream);
+
 /* ---- per-launch timing of the stack kernels (measurement aid for bench.py's roofline block) ----
  * While enabled, wnb_stack_fwd / wnb_stack_bwd bracket every kernel launch with CUDA events on the launching stream;
  * wnb_profile_read() waits for them and returns the summed duration and launch count of one kind since the last

@@ -238,15 +238,20 @@ def _causal_conv_bwd(x, W, dy, d):
     return dx, dW, dy.sum(axis=(0, 2))
 
 
-def backward(cfg, p, cache, dlogits):
-    """Gradients of every parameter given d(loss)/d(logits) (B,T,Q)."""
+def backward(cfg, p, cache, dlogits, relu_masks=None):
+    """Gradients of every parameter given d(loss)/d(logits) (B,T,Q).
+
+    ``relu_masks`` (test aid): {"h1": bool (B,S,T), "skip": bool (B,S,T)} replaces the two ReLU sign patterns of the
+    post network (wavenet.py:518-523) by the ones another forward produced, so that a reduced-precision run can be
+    compared on its arithmetic alone (a pre-activation within rounding distance of zero flips its mask, and every
+    flipped element passes / blocks its whole gradient: chaotic, not an arithmetic error of the backward)."""
     g = {}
     r0, h1, r1 = cache["post"]
     dy = np.transpose(dlogits, (0, 2, 1))
     dr1, g["conv_post_2.weight"], g["conv_post_2.bias"] = _conv1x1_bwd(r1, p["conv_post_2.weight"], dy)
-    dh1 = dr1 * (h1 > 0)
+    dh1 = dr1 * ((h1 > 0) if relu_masks is None else relu_masks["h1"])
     dr0, g["conv_post_1.weight"], g["conv_post_1.bias"] = _conv1x1_bwd(r0, p["conv_post_1.weight"], dh1)
-    dskip = dr0 * (cache["skip_sum"] > 0)
+    dskip = dr0 * ((cache["skip_sum"] > 0) if relu_masks is None else relu_masks["skip"])
     h = cache["h"]
     dh = np.zeros_like(h)
     dout = np.zeros_like(cache["xs"][0])

@@ -60,6 +60,8 @@ SIGNATURES = {
     "wnb_decode_warp_supported": (_I, [_I] * 6),
     "wnb_decode_warp": (_I, [_P] * 11 + [_P, _I] + [_P] * 4 + [_I] * 8 + [_c.c_uint64, _I, _P]),
     "wnb_decode_warp_plan": (_I, [_I]),
+    "wnb_pack_weights": (_I, [_P, _I, _P, _P, _P, _P]),
+    "wnb_zero": (_I, [_P, _c.c_size_t, _P]),
 }
 
 _lib = None

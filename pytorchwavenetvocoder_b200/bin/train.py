@@ -22,7 +22,6 @@ import torch
 
 from sklearn.preprocessing import StandardScaler
 
-from pytorchwavenetvocoder_b200.nets import cross_entropy
 from pytorchwavenetvocoder_b200.nets import encode_mu_law
 from pytorchwavenetvocoder_b200.nets import initialize
 from pytorchwavenetvocoder_b200.nets import WaveNet
@@ -353,8 +352,8 @@ def main():
         if world > 1 and batch_x.size(0) > 1:
             per = batch_x.size(0) // world
             batch_x, batch_h, batch_t = (v[rank * per:(rank + 1) * per].contiguous() for v in (batch_x, batch_h, batch_t))
-        batch_output = model(batch_x, batch_h)
-        batch_loss = cross_entropy(batch_output, batch_t, model.receptive_field)   # CE on [:, receptive_field:]
+        # = cross_entropy(model(batch_x, batch_h), batch_t, rf): CE on [:, receptive_field:] (reference :533-536)
+        batch_loss = model.forward_loss(batch_x, batch_h, batch_t, model.receptive_field)
         optimizer.zero_grad()
         batch_loss.backward()
         if sync is not None:

@@ -239,8 +239,10 @@ __global__ void aux_upsample_bwd_kernel(const float* __restrict__ h, const float
 // ------------------------------------------------------------------------------------------------
 // cross entropy (mean over B*(T-start) rows) + gradient; one warp per (b,t) row of Q logits
 // ------------------------------------------------------------------------------------------------
-__global__ void cross_entropy_kernel(const float* __restrict__ logits, const int64_t* __restrict__ target,
-                                     double* __restrict__ loss_sum, float* __restrict__ dlogits, int B, int T, int Q,
+// dlogits may alias logits (in-place: the fused training entry never keeps the logits): every lane finishes reading
+// a row -- including the target logit -- before any lane overwrites it.
+__global__ void cross_entropy_kernel(const float* logits, const int64_t* __restrict__ target,
+                                     double* __restrict__ loss_sum, float* dlogits, int B, int T, int Q,
                                      int start, float inv_n) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int64_t nrows = (int64_t)B * T;
@@ -266,9 +268,11 @@ __global__ void cross_entropy_kernel(const float* __restrict__ logits, const int
       if (lane == 0) local += (double)NAN;
       tg = 0;
     }
-    if (lane == 0) local += (double)(lse - lg[tg]);
+    const float ltg = lg[tg];
+    if (lane == 0) local += (double)(lse - ltg);
     if (dl) {
       const float inv_s = 1.0f / s;
+      __syncwarp();
       for (int q = lane; q < Q; q += 32) {
         float p = expf(lg[q] - m) * inv_s;
         if (q == tg) p -= 1.0f;

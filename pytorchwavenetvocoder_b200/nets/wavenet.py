@@ -335,6 +335,119 @@ class _WaveNetStackFn(torch.autograd.Function):
         return (None, dhaux, dwf, dbf, dW1, db1, dW2res, db2res, dWskip, dbskip, dWp1, dbp1, dWp2, dbp2, None)
 
 
+class _StackTrainFn(torch.autograd.Function):
+    """WaveNet.forward (reference wavenet.py:212-241) [+ the cross entropy of bin/train.py:534-536] on the deferred-skip
+    stack, with NO torch arithmetic in between: parameters are packed by ``wnb_pack_weights`` (one launch), the packed
+    gradients are scattered into one flat buffer by the same kernel (one launch) and handed to autograd as views, so
+    ``p.grad`` of every parameter aliases one contiguous tensor (``module._wnb_flat_grad``: what the data-parallel
+    all-reduce sends).  ``target is None``: returns the (B,T,Q) logits; otherwise the mean CE over ``[:, start:]``."""
+
+    @staticmethod
+    def forward(ctx, net, plan, x, h, target, start, *params):
+        lib = _lib.load()
+        d = plan.dims
+        R, S, Q, ks, A, Ap, L, U = d["R"], d["S"], d["Q"], d["ks"], d["A"], d["Ap"], d["L"], d["U"]
+        dev = x.device
+        st = stream()
+        x = x.contiguous()
+        h = h.contiguous().float()
+        B, T = x.shape
+        Tf = h.size(2)
+        if h.size(1) != A:
+            raise ValueError("aux feature has %d dims, expected %d" % (h.size(1), A))
+        if (Tf * U if U > 0 else Tf) != T:
+            raise ValueError("aux length %d does not match waveform length %d" % (Tf * max(U, 1), T))
+        need_grad = any(ctx.needs_input_grad)
+        plan.pack(st)
+        P = plan.p
+        f32 = dict(device=dev, dtype=torch.float32)
+        haux = torch.empty(B, T, Ap, **f32)
+        upw = net.upsampling.conv.weight if U > 0 else None
+        upb = net.upsampling.conv.bias if U > 0 else None
+        check(lib.wnb_aux_upsample_fwd(ptr(h), ptr(upw), ptr(upb), ptr(haux), B, A, Ap, Tf, U, st), "aux_upsample_fwd")
+        nbuf = L if need_grad else min(L, 2)
+        xs = torch.empty(nbuf, B, T, R, **f32)
+        check(lib.wnb_front_embed_fwd(ptr(x), ptr(P("wf")), ptr(P("bf")), ptr(xs[0]), B, T, Q, R, ks, st), "front_embed_fwd")
+        zall = torch.empty(B, T, L * R, **f32)
+        skip = torch.empty(B, T, S, **f32)
+        dil = (ctypes.c_int * L)(*[int(v) for v in net.dilations])
+        check(lib.wnb_stack_fwd(ptr(xs), nbuf, ptr(haux), ptr(P("W1")), ptr(P("b1")), ptr(P("W2res")), ptr(P("b2res")),
+                                ptr(P("Wskip")), ptr(P("bskip")), ptr(zall), ptr(skip), dil, L, B, T, R, S, Ap, ks, 1, st),
+              "stack_fwd")
+        r1 = torch.empty(B, T, S, **f32)
+        logits = torch.empty(B, T, Q, **f32)
+        check(lib.wnb_post_fwd(ptr(skip), ptr(P("Wp1")), ptr(P("bp1")), ptr(P("Wp2")), ptr(P("bp2")), ptr(r1), ptr(logits),
+                               B, T, S, Q, MATH_TF32, 1, st), "post_fwd")
+        dbg = getattr(net, "_wnb_debug", None)
+        if dbg is not None:     # test aid: the ReLU sign patterns of the post network (tests/test_gpu_oracle_direct.py)
+            dbg["skip_mask"], dbg["r1_mask"] = skip > 0, r1 > 0
+        out = logits
+        dl = None
+        if target is not None:
+            target = target.contiguous()
+            if target.dtype != torch.int64 or tuple(target.shape) != (B, T) or target.device != dev:
+                raise ValueError("target should be an int64 (B, T) tensor on the model's device")
+            loss = torch.empty(1, device=dev, dtype=torch.float64)
+            check(lib.wnb_zero(ptr(loss), 8, st), "zero")
+            dl = logits if need_grad else None     # dlogits overwrite the logits in place (each row is read, then written)
+            check(lib.wnb_cross_entropy(ptr(logits), ptr(target), ptr(loss), ptr(dl), B, T, Q, int(start), st),
+                  "cross_entropy")
+            out = loss.float().view(())
+        if need_grad:
+            ctx.save_for_backward(x, h, haux, xs, zall, skip, r1)
+            ctx.net, ctx.plan, ctx.dl, ctx.dil = net, plan, dl, dil
+            ctx.fused_loss = target is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib.load()
+        x, h, haux, xs, zall, skip, r1 = ctx.saved_tensors
+        net, plan, dil = ctx.net, ctx.plan, ctx.dil
+        d = plan.dims
+        R, S, Q, ks, A, Ap, L, U = d["R"], d["S"], d["Q"], d["ks"], d["A"], d["Ap"], d["L"], d["U"]
+        B, T = x.shape
+        Tf = h.size(2)
+        dev = x.device
+        st = stream()
+        f32 = dict(device=dev, dtype=torch.float32)
+        if ctx.fused_loss:
+            dlogits, scale = ctx.dl, g.contiguous().float()   # d loss / d logits from the CE kernel; g scales the result
+            ctx.dl = None
+        else:
+            dlogits, scale = g.contiguous(), None
+        P = plan.p
+        gbuf = torch.empty(plan.G.size, **f32)
+        check(lib.wnb_zero(ptr(gbuf), gbuf.numel() * 4, st), "zero")
+        G = lambda name: plan.G.view(gbuf, name)  # noqa: E731
+        dskip = torch.empty(B, T, S, **f32)
+        ws_post = torch.empty(B, T, S, **f32)
+        check(lib.wnb_post_bwd(ptr(skip), ptr(r1), ptr(dlogits), ptr(P("wp1t")), ptr(P("wp2t")), ptr(dskip), ptr(G("Wp1")),
+                               ptr(G("bp1")), ptr(G("Wp2")), ptr(G("bp2")), ptr(ws_post), B, T, S, Q, MATH_TF32, st),
+              "post_bwd")
+        del ws_post, dlogits
+        dhaux = None
+        if U > 0:
+            dhaux = torch.empty(B, T, Ap, **f32)
+            check(lib.wnb_zero(ptr(dhaux), dhaux.numel() * 4, st), "zero")
+        nbytes = lib.wnb_stack_bwd_workspace(L, B, T, R, S, Ap, ks)
+        ws = torch.empty(nbytes // 4, **f32)
+        dx0 = torch.empty(B, T, R, **f32)
+        check(lib.wnb_stack_bwd(ptr(xs), ptr(haux), ptr(zall), ptr(dskip), ptr(P("W1")), ptr(P("b1")), ptr(P("w1t")),
+                                ptr(P("wgate")), ptr(P("wskt")), ptr(dx0), ptr(dhaux), ptr(G("W1")), ptr(G("b1")),
+                                ptr(G("W2res")), ptr(G("b2res")), ptr(G("Wskip")), ptr(G("bskip")), ptr(ws), dil, L, B, T,
+                                R, S, Ap, ks, st), "stack_bwd")
+        del ws
+        check(lib.wnb_front_embed_bwd(ptr(x), ptr(dx0), ptr(G("wf")), ptr(G("bf")), B, T, Q, R, ks, st), "front_embed_bwd")
+        if U > 0:
+            check(lib.wnb_aux_upsample_bwd(ptr(h), ptr(dhaux), ptr(G("upw")), ptr(G("upb")), B, A, Ap, Tf, U, st),
+                  "aux_upsample_bwd")
+        flat = torch.empty(plan.grad_size, **f32)
+        plan.unpack(gbuf, flat, scale, st)
+        net._wnb_flat_grad = flat
+        return (None, None, None, None, None, None) + tuple(plan.grad_views(flat))
+
+
 # ------------------------------------------------------------------------------------------
 # modules (same names / parameters / state_dict keys as the reference)
 # ------------------------------------------------------------------------------------------
@@ -536,9 +649,41 @@ class WaveNet(nn.Module):
             return _UpsampleFn.apply(h, self.upsampling.conv.weight, self.upsampling.conv.bias, self.n_aux_pad)
         return _UpsampleFn.apply(h, None, None, self.n_aux_pad)
 
+    def _stack_plan(self, device):
+        """Copy tables + packed buffers of the one-launch weight packing (nets/packing.py); None when the deferred-skip
+        stack does not cover this model."""
+        if not getattr(self, "deferred_skip", True) or self.math_mode != "tf32":
+            return None
+        if not _lib.load().wnb_stack_supported(self.n_resch, self.n_skipch, self.n_aux_pad, self.kernel_size,
+                                               len(self.dilations), MATH_TF32):
+            return None
+        plan = self.__dict__.get("_wnb_plan")
+        if plan is None or plan.device != device or plan.stale():
+            from .packing import StackPlan
+            plan = StackPlan(self, device)
+            self.__dict__["_wnb_plan"] = plan
+        return plan
+
+    def forward_loss(self, x, h, t, start=None):
+        """Training entry of the B200 build: mean cross entropy of ``forward(x, h)[:, start:]`` against ``t[:, start:]``
+        (reference bin/train.py:533-536 with ``start = receptive_field``) as ONE autograd node -- the post network's
+        logits never make a round trip through a separate loss kernel's gradient multiply.  Same value and gradients as
+        ``cross_entropy(self(x, h), t, start)``."""
+        start = self.receptive_field if start is None else int(start)
+        if not x.is_cuda:
+            raise _lib.WnbError("WaveNet.forward_loss needs CUDA tensors: the B200 build has no CPU fallback")
+        plan = self._stack_plan(x.device)
+        if plan is None:
+            return cross_entropy(self._forward_impl(x, h), t, start)
+        return _StackTrainFn.apply(self, plan, x, h, t, start, *[p for _, p in plan.params])
+
     def _forward_impl(self, x, h, upsample=True):
         if not x.is_cuda:
             raise _lib.WnbError("WaveNet.forward needs CUDA tensors: the B200 build has no CPU fallback")
+        if upsample and PROFILE_EVENTS is None:
+            plan = self._stack_plan(x.device)
+            if plan is not None:
+                return _StackTrainFn.apply(self, plan, x, h, None, 0, *[p for _, p in plan.params])
         haux = self._aux(h, upsample)
         if haux.size(1) != x.size(1):
             raise ValueError("aux length %d does not match waveform length %d" % (haux.size(1), x.size(1)))

@@ -17,6 +17,7 @@ class GradAllReduce(object):
     """Average ``.grad`` of every parameter across ranks with a single flat all-reduce."""
 
     def __init__(self, module, group=None):
+        self.module = module
         self.params = [p for p in module.parameters() if p.requires_grad]
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -30,6 +31,14 @@ class GradAllReduce(object):
         if self.world == 1:
             return
         live = [p for p in self.params if p.grad is not None]
+        flat = getattr(self.module, "_wnb_flat_grad", None)
+        if flat is not None and live:
+            # the stack path hands autograd views of ONE flat buffer (nets/wavenet.py _StackTrainFn): when every .grad
+            # still aliases it, that buffer is the all-reduce message -- no pack / unpack copies, no separate divide
+            lo, hi = flat.data_ptr(), flat.data_ptr() + flat.numel() * flat.element_size()
+            if all(lo <= p.grad.data_ptr() < hi for p in live):
+                dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=self.group)
+                return
         n = sum(p.grad.numel() for p in live)
         if self._flat is None or self._flat.numel() != n or self._flat.device != live[0].grad.device:
             self._flat = torch.empty(n, dtype=live[0].grad.dtype, device=live[0].grad.device)

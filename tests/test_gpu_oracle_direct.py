@@ -63,6 +63,7 @@ def _train_step_vs_oracle(cfg, seed, B, T, start, math_mode, expect_stack):
         sup = bool(lib.wnb_stack_supported(cfg.n_resch, cfg.n_skipch, net.n_aux_pad, cfg.kernel_size,
                                            len(cfg.dilations), net._math()))
         assert sup == expect_stack
+    net._wnb_debug = {}
     rng = np.random.RandomState(seed + 100)
     U = max(cfg.upsampling_factor, 1)
     x = rng.randint(0, cfg.n_quantize, size=(B, T)).astype(np.int64)
@@ -78,6 +79,16 @@ def _train_step_vs_oracle(cfg, seed, B, T, start, math_mode, expect_stack):
     g = O.backward(cfg, p64, cache, dl)
     yv = y.detach().cpu().numpy().astype(np.float64)
     rows = _grad_errors(net, g)
+    rows_same_masks, flips = None, None
+    if "skip_mask" in net._wnb_debug:
+        # the same comparison with the oracle's two post-network ReLU masks replaced by the sign patterns of OUR forward:
+        # isolates the arithmetic error of the backward kernels from mask flips at pre-activations within rounding
+        # distance of zero (each flip passes / blocks a whole gradient element)
+        ms = net._wnb_debug["skip_mask"].cpu().numpy().transpose(0, 2, 1)
+        m1 = net._wnb_debug["r1_mask"].cpu().numpy().transpose(0, 2, 1)
+        flips = {"skip": float((ms != (cache["skip_sum"] > 0))[:, :, start:].mean()),
+                 "h1": float((m1 != (cache["post"][1] > 0))[:, :, start:].mean())}
+        rows_same_masks = _grad_errors(net, O.backward(cfg, p64, cache, dl, relu_masks={"h1": m1, "skip": ms}))
     srt = np.sort(ref, axis=-1)
     margin = srt[..., -1] - srt[..., -2]
     agree = (yv.argmax(-1) == ref.argmax(-1))
@@ -86,7 +97,7 @@ def _train_step_vs_oracle(cfg, seed, B, T, start, math_mode, expect_stack):
            "logits_max_abs_err": float(np.abs(yv - ref).max()), "logits_max_ref": float(np.abs(ref).max()),
            "argmax_agree_all": float(agree.mean()),
            "argmax_agree_margin_gt_0.05": float(agree[margin > 0.05].mean()) if (margin > 0.05).any() else None,
-           "grads": rows}
+           "grads": rows, "grads_same_relu_masks": rows_same_masks, "relu_mask_flip_fraction": flips}
     return rep
 
 
@@ -108,6 +119,9 @@ def _summarise(rep):
     rows = rep["grads"]
     rep["worst_weight"] = _worst(rows, _is_weight)
     rep["worst_bias"] = _worst(rows, _is_bias)
+    if rep.get("grads_same_relu_masks"):
+        rep["worst_weight_same_masks"] = _worst(rep["grads_same_relu_masks"], _is_weight)
+        rep["worst_bias_same_masks"] = _worst(rep["grads_same_relu_masks"], _is_bias)
     per_kind = {}
     for k, v in rows.items():
         if v is None:
@@ -131,17 +145,21 @@ def test_tf32_stack_every_gradient_vs_fp64_oracle_arctic30():
     print("tf32 stack vs fp64 oracle: loss err %.2e, logits max err %.2e, worst weight %s %.3e, worst bias %s %.3e"
           % (rep["loss_abs_err"], rep["logits_max_abs_err"], rep["worst_weight"][0], rep["worst_weight"][1],
              rep["worst_bias"][0], rep["worst_bias"][1]))
+    print("   with the oracle's ReLU masks replaced by ours (flip fraction %s): worst weight %s %.3e, worst bias %s %.3e"
+          % (rep["relu_mask_flip_fraction"], rep["worst_weight_same_masks"][0], rep["worst_weight_same_masks"][1],
+             rep["worst_bias_same_masks"][0], rep["worst_bias_same_masks"][1]))
     assert rep["loss_abs_err"] < TOL_TF32["loss"], rep["loss_abs_err"]
     assert rep["logits_max_abs_err"] < TOL_TF32["logits"], rep["logits_max_abs_err"]
     none = [k for k, v in rep["grads"].items() if v is None]
     assert none == ["res_1x1.29.weight", "res_1x1.29.bias"], none   # reference: the last res_1x1 gets no gradient
-    for k, v in rep["grads"].items():
-        if v is None:
-            continue
-        if v["numel"] == 1:     # upsampling bias: one scalar = a sum with heavy cancellation -> absolute bound
-            continue
-        tol = TOL_TF32["weight"] if k.endswith("weight") else TOL_TF32["bias"]
-        assert v["rel_fro"] <= tol, (k, v)
+    for key, tols in (("grads", TOL_TF32), ("grads_same_relu_masks", TOL_TF32_SAME_MASKS)):
+        for k, v in rep[key].items():
+            if v is None:
+                continue
+            if v["numel"] == 1:     # upsampling bias: one scalar = a sum with heavy cancellation, no relative bound
+                continue
+            tol = tols["weight"] if k.endswith("weight") else tols["bias"]
+            assert v["rel_fro"] <= tol, (key, k, v)
 
 
 def test_fp32_path_every_gradient_vs_fp64_oracle_arctic30():
@@ -179,7 +197,12 @@ def test_composed_tf32_path_vs_fp64_oracle_ljspeech_melspc():
 
 
 # Asserted tolerances: ~2x the errors observed on B200 (see profiles/r2_parity_*.json for the per-tensor numbers)
-TOL_TF32 = {"loss": 2e-3, "logits": 5e-2, "weight": 0.05, "bias": 0.10}
+# Observed (B200, round 2): loss 1.1e-3, logits 1.4e-2 (max |logit| 3.2), every weight gradient 4.5-5.7 %, biases
+# 2.6-6.1 % -- UNIFORM over the 30 blocks and already 2.5 % at conv_post_1: it is not rounding accumulated through the
+# stack but the two ReLU masks of the post network flipping where a pre-activation is within tf32 rounding of zero.
+# With the masks shared the same gradients agree to the second set of bounds.
+TOL_TF32 = {"loss": 2.5e-3, "logits": 3e-2, "weight": 0.08, "bias": 0.09}
+TOL_TF32_SAME_MASKS = {"weight": 0.02, "bias": 0.03}
 TOL_COMPOSED = {"loss": 2e-3, "logits": 5e-2, "weight": 0.05, "bias": 0.10}
 
 
