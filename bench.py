@@ -264,10 +264,59 @@ def run_ours(args):
         e3.record()
         barrier()
         ms_e2e = e2.elapsed_time(e3)
+        # --- end-to-end through the CLI's data path (bin/train.py): DISTINCT batches every step from wav / feature
+        # FILES -> reader thread -> pinned memory -> async H2D into the device rings -> wnb_make_train_batch
+        # (windowing + mu-law + scaler on the device) -> step; loss read back one step late as above ---
+        loader_e2e = None
+        if args.loader_e2e and cfg.upsampling_factor > 0:
+            import shutil
+            import tempfile
+            from pytorchwavenetvocoder_b200.utils import write_hdf5, write_wav
+            from pytorchwavenetvocoder_b200.utils.device_loader import DeviceTrainGenerator
+            tmpd = tempfile.mkdtemp(prefix="wnb_bench_")
+            try:
+                rngc = np.random.RandomState(1000 + rank)
+                U, n_utt, n_frames = cfg.upsampling_factor, 24, 2000      # 24 utterances x 10 s @ 16 kHz
+                wl, fl = [], []
+                for i in range(n_utt):
+                    w, f = os.path.join(tmpd, "u%d.wav" % i), os.path.join(tmpd, "u%d.npz" % i)
+                    write_wav(w, 0.5 * np.tanh(rngc.standard_normal(n_frames * U)), 16000)
+                    write_hdf5(f, "/world", rngc.standard_normal((n_frames, cfg.n_aux)).astype(np.float32))
+                    wl.append(w)
+                    fl.append(f)
+                gen = DeviceTrainGenerator(wl, fl, rf, BATCH_LENGTH, BATCH, n_quantize=cfg.n_quantize,
+                                           mean=np.zeros(cfg.n_aux), scale=np.ones(cfg.n_aux), shuffle=True,
+                                           upsampling_factor=U, use_upsampling_layer=True, device=local)
+
+                def loader_loop(n):
+                    pending, last_ = None, 0.0
+                    for _ in range(n):
+                        (xb, hb), tb = gen.next()
+                        loss_i = step(xb, hb, tb)
+                        if pending is not None:
+                            last_ = float(pending)
+                        pending = loss_i.detach()
+                    return float(pending)
+                loader_loop(3)
+                barrier()
+                e4, e5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s0_ = gen.tail_s
+                e4.record()
+                last_l = loader_loop(args.steps)
+                e5.record()
+                barrier()
+                ms_l = e4.elapsed_time(e5)
+                up_bytes = (gen.tail_s - s0_) * (4 + cfg.n_aux * 4.0 / U)
+                loader_e2e = {"ms": ms_l, "last_loss": last_l, "h2d_bytes_per_step": int(up_bytes / args.steps),
+                              "T": gen.T}
+            finally:
+                shutil.rmtree(tmpd, ignore_errors=True)
         if dist is not None:
-            tt = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+            tt = torch.tensor([ms, ms_e2e, loader_e2e["ms"] if loader_e2e else 0.0], device=dev, dtype=torch.float64)
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             ms, ms_e2e = float(tt[0]), float(tt[1])
+            if loader_e2e:
+                loader_e2e["ms"] = float(tt[2])
         per_step = ms / args.steps
         samples = world * BATCH * BATCH_LENGTH
         hbm, how = _peaks()
@@ -328,6 +377,15 @@ def run_ours(args):
             "clocks": clocks,
             "roofline": roof,
         }
+        if loader_e2e:
+            out["e2e_data_loader"] = {
+                "value": samples / (loader_e2e["ms"] / args.steps * 1e-3), "unit": "samples/s",
+                "ms_per_step": loader_e2e["ms"] / args.steps, "h2d_bytes_per_step": loader_e2e["h2d_bytes_per_step"],
+                "d2h_bytes_per_step": 4, "last_loss": loader_e2e["last_loss"],
+                "loop": "bin/train.py's data path: distinct batches every step cut on the device "
+                        "(wnb_make_train_batch) from 24 synthetic 10 s wav + feature files read by the loader thread, "
+                        "uploaded once per utterance from pinned memory on a copy stream; window %d samples"
+                        % loader_e2e["T"]}
         if roof_all:
             out["roofline_kernels"] = roof_all
     if args.workload == "decode" or (args.workload == "train" and args.with_decode):
@@ -608,6 +666,7 @@ def main():
     ap.add_argument("--math", default=None, choices=["fp32", "tf32"])
     ap.add_argument("--with-decode", type=int, default=1, help="also report the decode workload (extra object)")
     ap.add_argument("--cpu-baseline", type=int, default=1)
+    ap.add_argument("--loader-e2e", type=int, default=1, help="also time the step fed by the on-device data loader")
     ap.add_argument("--cfg", default=None, help="override the WaveNet ctor tuple, e.g. 256,28,512,256,10,3,2,80 "
                                                 "(recipe shape); the default is BASELINE.json configs[1]")
     ap.add_argument("--batch", type=int, default=None, help="override the per-GPU batch (default 8)")

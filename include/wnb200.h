@@ -99,6 +99,20 @@ WNB_API int wnb_resblock_fwd_supported(int R, int S, int Ap, int ks, int math_mo
 WNB_API int wnb_causal_conv1d_fwd(const float* x, const float* w, const float* bias, float* out, int B, int T,
                                   int Cin, int Cout, int ks, int dilation, void* stream);
 
+/* ---- a18 / f1: train_generator on the device (bin/train.py:67-312) ------------------------------------------------
+ * One launch cuts a whole mini-batch out of device-resident RING buffers: `wave` (cap_s floats) = the concatenated
+ * float32 waveforms, `feat` (cap_f rows of D, float32 or float64 as read from the feature file) = the concatenated
+ * feature frames; positions are absolute stream positions, ring index = position mod capacity.  Window b starts at
+ * sample s0 + b*hop: x[b][i] = encode_mu_law(wave[..+i]), t[b][i] = encode_mu_law(wave[..+i+1]) (bit exact with
+ * wnb_mulaw_encode_f32); h[b][d][j] = float32 StandardScaler transform ((v - mean[d]) / scale[d] with sklearn's dtype
+ * behaviour; mean == NULL: none) of frame (s0 + b*hop)/U + j (up-sampling layer: Tf = T/U, frame_of_sample NULL) or of
+ * frame frame_of_sample[sample] (extend_time mode: Tf = T; an int32 ring parallel to `wave`).
+ * x, t (B,T) int64; h (B,D,Tf) fp32. */
+WNB_API int wnb_make_train_batch(const float* wave, const void* feat, const int32_t* frame_of_sample, int64_t s0,
+                                 int64_t hop, int U, int64_t cap_s, int64_t cap_f, const double* mean, const double* scale,
+                                 int64_t* x, int64_t* t, float* h, int B, int T, int Tf, int D, int feat_f64, int mu,
+                                 void* stream);
+
 /* ---- pack_weights: state_dict layout <-> kernel layout as one launch per direction ----------
  * A table of strided 3-D copies dst[i0*ds0 + i1*ds1 + i2*ds2] = scale * f(src[i0*ss0 + i1*ss1 + i2*ss2]) executed by
  * one kernel (one block row per entry).  `src` / `src2` are absolute device pointers (WNB_PACK_SRC_ABS: the

@@ -207,6 +207,8 @@ def get_parser():
     parser.add_argument("--verbose", default=1, type=int, help="log level")
     parser.add_argument("--math_mode", default="tf32", choices=["tf32", "fp32"], type=str,
                         help="(B200 build) contraction precision of the training kernels")
+    parser.add_argument("--host_loader", default=False, type=_strtobool,
+                        help="(B200 build) build the mini-batches on the host like the reference instead of on the GPU")
     return parser
 
 
@@ -311,19 +313,29 @@ def main():
         sys.exit(1)
     assert len(wav_list) == len(feat_list)
     logging.info("number of training data = %d." % len(wav_list))
-    generator = train_generator(
-        wav_list, feat_list,
-        receptive_field=model.receptive_field,
-        batch_length=args.batch_length if args.batch_length > 0 else None,
-        batch_size=args.batch_size,
-        feature_type=args.feature_type,
-        wav_transform=wav_transform,
-        feat_transform=feat_transform,
-        shuffle=True,
-        upsampling_factor=args.upsampling_factor,
-        use_upsampling_layer=args.use_upsampling_layer,
-        use_speaker_code=args.use_speaker_code,
-        device=local)
+    if args.batch_length > 0 and not args.host_loader:
+        # mini-batch modes: windowing + mu-law + scaler on the device, utterances uploaded once (utils/device_loader.py);
+        # same batches as train_generator below (tests/test_gpu_loader.py)
+        from pytorchwavenetvocoder_b200.utils.device_loader import DeviceTrainGenerator
+        generator = DeviceTrainGenerator(
+            wav_list, feat_list, model.receptive_field, args.batch_length, args.batch_size,
+            feature_type=args.feature_type, n_quantize=args.n_quantize, mean=scaler.mean_, scale=scaler.scale_,
+            shuffle=True, upsampling_factor=args.upsampling_factor, use_upsampling_layer=args.use_upsampling_layer,
+            use_speaker_code=args.use_speaker_code, device=local)
+    else:
+        generator = train_generator(
+            wav_list, feat_list,
+            receptive_field=model.receptive_field,
+            batch_length=args.batch_length if args.batch_length > 0 else None,
+            batch_size=args.batch_size,
+            feature_type=args.feature_type,
+            wav_transform=wav_transform,
+            feat_transform=feat_transform,
+            shuffle=True,
+            upsampling_factor=args.upsampling_factor,
+            use_upsampling_layer=args.use_upsampling_layer,
+            use_speaker_code=args.use_speaker_code,
+            device=local)
 
     if args.resume is not None and len(args.resume) != 0:
         checkpoint = torch.load(args.resume, map_location=lambda storage, loc: storage, weights_only=False)

@@ -39,6 +39,17 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), unsigned grid, unsigned 
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
+// ---- per-device / per-stream launch state (thread-safe; elementwise.cu) -------------------------------------------
+// SM count of the CURRENT device (cached per device).
+int device_sms();
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (device, kernel) -- function attributes are per device.
+cudaError_t ensure_dynamic_smem(const void* func, size_t bytes);
+// Two zero-initialised uint32 words of device memory owned by (current device, stream): the dynamic tile scheduler
+// of the block kernels (tile counter, CTAs-done counter; the last CTA re-arms them).  Launches on DIFFERENT streams
+// get different words and may run concurrently; launches on one stream are ordered.  A few bytes per stream, allocated
+// on first use and kept for the life of the process (library state, not a caller-visible buffer).
+unsigned int* sched_counters(cudaStream_t st);
+
 #define WNB_REQUIRE(cond, ...)            \
   do {                                    \
     if (!(cond)) {                        \

@@ -92,11 +92,11 @@ struct Ring {
   __device__ __forceinline__ const float* acquire() {
     const long long t0 = clock64();
     uint32_t seen;
-    uint32_t spins = 0;
+    ptx::SpinGuard guard;
     for (;;) {
       asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(seen) : "r"(ptx::smem_u32(ready)) : "memory");
       if ((int32_t)(seen - cidx) > 0) break;
-      if (++spins > (1u << 26)) { printf("wnb200: decode ring wait timed out\n"); __trap(); }
+      if (guard.expired()) { printf("wnb200: decode ring wait timed out after 20 s\n"); __trap(); }
     }
     waited += clock64() - t0;
     return reinterpret_cast<const float*>(base + (size_t)slot * slot_bytes);

@@ -6,6 +6,9 @@
 #include <stdlib.h>
 
 #include <atomic>
+#include <map>
+#include <mutex>
+#include <utility>
 #include <vector>
 
 #include "common.cuh"
@@ -26,6 +29,43 @@ bool pdl_enabled() {
   static int on = -1;
   if (on < 0) { const char* e = getenv("WNB_PDL"); on = (e && e[0] == '0') ? 0 : 1; }
   return on == 1;
+}
+
+// ---- per-device / per-stream launch state ----
+static std::mutex g_state_mu;
+int device_sms() {
+  static int sms[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  std::lock_guard<std::mutex> lk(g_state_mu);
+  if (!sms[dev] && cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms[dev] = 148;
+  return sms[dev];
+}
+cudaError_t ensure_dynamic_smem(const void* func, size_t bytes) {
+  static std::map<std::pair<int, const void*>, size_t> done;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  std::lock_guard<std::mutex> lk(g_state_mu);
+  size_t& have = done[std::make_pair(dev, func)];
+  if (bytes > have) {
+    e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return e;
+    have = bytes;
+  }
+  return cudaSuccess;
+}
+unsigned int* sched_counters(cudaStream_t st) {
+  static std::map<std::pair<int, cudaStream_t>, unsigned int*> slots;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+  std::lock_guard<std::mutex> lk(g_state_mu);
+  unsigned int*& p = slots[std::make_pair(dev, st)];
+  if (!p) {
+    if (cudaMalloc(&p, 256) != cudaSuccess) { p = nullptr; return nullptr; }
+    if (cudaMemset(p, 0, 256) != cudaSuccess) { cudaFree(p); p = nullptr; return nullptr; }
+  }
+  return p;
 }
 
 // ---- per-launch event timing (off by default; bench.py switches it on for the timed region) ----

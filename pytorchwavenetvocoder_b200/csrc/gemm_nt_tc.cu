@@ -50,6 +50,10 @@ struct alignas(64) Params {
   int out2_col0;
   // column blocks (NtTcOpts::n_blocks), dz row pitch and z suppression of the gate-backward epilogue
   int nblk, gate_ld_dz, gate_skip_z;
+  // mt == 2 (NtTcOpts::m_tiles): a CTA tile is TWO 128-row time tiles against ONE weight chunk per k-step -- the
+  // weight chunk is fetched from L2 once per 256 rows instead of once per 128 (the K >= 512 GEMMs are bound by the
+  // L2 -> SM path, not by HBM or the tensor pipe).  The two accumulators are the two TMEM buffers (N <= 256).
+  int mt, stg_boxes;
 };
 
 // barrier layout in smem: full[nstages] empty[nstages] dfull[2] dempty[2]
@@ -79,16 +83,18 @@ __global__ void __launch_bounds__(kThreadsN, 1) gemm_nt_tc_kernel(const __grid_c
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int N = p.N;
-  const int stage_bytes = kASub + N * 128;
+  const int a_bytes = p.mt * kASub;
+  const int stage_bytes = a_bytes + N * 128;
   unsigned char* stg_base = smem + (size_t)p.nstages * stage_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(stg_base + kEpiWarpsN * 2 * kStg);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stg_base + kEpiWarpsN * p.stg_boxes * kStg);
   uint64_t* full = bars;
   uint64_t* empty = bars + p.nstages;
   uint64_t* dfull = bars + 2 * p.nstages;
   uint64_t* dempty = dfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dempty + 2);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tiles_per_b = (p.T + kTM - 1) / kTM;
+  const int rows_per_tile = kTM * p.mt;
+  const int tiles_per_b = (p.T + rows_per_tile - 1) / rows_per_tile;
   const int ntiles = p.B * tiles_per_b * p.nblk;   // column block fastest: the blocks of one time tile share A via L2
   int kchunks = 0;
   for (int s = 0; s < p.nseg; s++) kchunks += p.seg[s].K / 32;
@@ -123,7 +129,7 @@ __global__ void __launch_bounds__(kThreadsN, 1) gemm_nt_tc_kernel(const __grid_c
       uint32_t st = 0, ph = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int tt = tile / p.nblk, ncol0 = (tile - tt * p.nblk) * N;
-        const int b = tt / tiles_per_b, t0 = (tt - b * tiles_per_b) * kTM;
+        const int b = tt / tiles_per_b, t0 = (tt - b * tiles_per_b) * rows_per_tile;
         for (int s = 0; s < p.nseg; s++) {
           const Seg sg = p.seg[s];
           for (int kc = 0; kc < sg.K / 32; kc++) {
@@ -131,12 +137,14 @@ __global__ void __launch_bounds__(kThreadsN, 1) gemm_nt_tc_kernel(const __grid_c
             ptx::mbar_arrive_expect_tx(&full[st], stage_bytes);
             unsigned char* dst = smem + (size_t)st * stage_bytes;
             ptx::tma_load_3d(dst, &p.maps[sg.amap], &full[st], kc * 32, t0 + sg.shift, b);
+            if (p.mt == 2)   // (rows past T are zero-filled by TMA, the matching stores are clipped)
+              ptx::tma_load_3d(dst + kASub, &p.maps[sg.amap], &full[st], kc * 32, t0 + kTM + sg.shift, b);
             if (sg.b_n1 >= 0) {   // N = two row ranges of N/2 each (sigmoid rows, tanh rows)
-              ptx::tma_load_2d(dst + kASub, &p.maps[sg.bmap], &full[st], sg.b_k0 + kc * 32, sg.b_n0);
-              ptx::tma_load_2d(dst + kASub + (N / 2) * 128, &p.maps[sg.bmap], &full[st], sg.b_k0 + kc * 32, sg.b_n1);
+              ptx::tma_load_2d(dst + a_bytes, &p.maps[sg.bmap], &full[st], sg.b_k0 + kc * 32, sg.b_n0);
+              ptx::tma_load_2d(dst + a_bytes + (N / 2) * 128, &p.maps[sg.bmap], &full[st], sg.b_k0 + kc * 32, sg.b_n1);
             } else {
               for (int n0 = 0; n0 < N; n0 += 256)
-                ptx::tma_load_2d(dst + kASub + n0 * 128, &p.maps[sg.bmap], &full[st], sg.b_k0 + kc * 32, sg.b_n0 + ncol0 + n0);
+                ptx::tma_load_2d(dst + a_bytes + n0 * 128, &p.maps[sg.bmap], &full[st], sg.b_k0 + kc * 32, sg.b_n0 + ncol0 + n0);
             }
             if (++st == (uint32_t)p.nstages) { st = 0; ph ^= 1; }
           }
@@ -152,6 +160,28 @@ __global__ void __launch_bounds__(kThreadsN, 1) gemm_nt_tc_kernel(const __grid_c
       const uint32_t stage_step = (uint32_t)stage_bytes >> 4;
       uint32_t st = 0, ph = 0, it = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
+        if (p.mt == 2) {
+          // two time tiles per weight chunk: accumulator h (TMEM columns h*N..) belongs to rows t0 + 128 h
+          wait(&dempty[0], (it & 1) ^ 1, NP_M_DEMPTY);
+          wait(&dempty[1], (it & 1) ^ 1, NP_M_DEMPTY);
+          ptx::tc_fence_after();
+          for (int kc = 0; kc < kchunks; kc++) {
+            wait(&full[st], ph, NP_M_FULL);
+            ptx::tc_fence_after();
+            const uint32_t a_lo = s_lo0 + st * stage_step, b_lo = a_lo + (2 * kASub >> 4);
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+              ptx::mma_tf32_ss(tmem, ptx::desc64(a_lo + 2 * k, hi), ptx::desc64(b_lo + 2 * k, hi), idesc, (kc | k) != 0);
+              ptx::mma_tf32_ss(tmem + N, ptx::desc64(a_lo + (kASub >> 4) + 2 * k, hi), ptx::desc64(b_lo + 2 * k, hi), idesc,
+                               (kc | k) != 0);
+            }
+            ptx::tc_commit(&empty[st]);
+            if (++st == (uint32_t)p.nstages) { st = 0; ph ^= 1; }
+          }
+          ptx::tc_commit(&dfull[0]);
+          ptx::tc_commit(&dfull[1]);
+          continue;
+        }
         const uint32_t buf = (p.nacc == 2) ? (it & 1) : 0;
         const uint32_t use = (p.nacc == 2) ? (it >> 1) : it;
         wait(&dempty[buf], (use & 1) ^ 1, NP_M_DEMPTY);
@@ -180,16 +210,18 @@ __global__ void __launch_bounds__(kThreadsN, 1) gemm_nt_tc_kernel(const __grid_c
     const int q = warp & 3;                 // TMEM lane quarter (hardware restriction: warp id % 4)
     const int hf = (warp - 2) >> 2;         // 0 / 1: this warp takes 32-column chunks hf, hf + 2, ...
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-    unsigned char* stg = stg_base + (warp - 2) * 2 * kStg;
+    unsigned char* stg = stg_base + (warp - 2) * p.stg_boxes * kStg;
+    const uint32_t box_mask = (uint32_t)p.stg_boxes - 1;   // 2 staging boxes per warp (alternating), 1 when mt == 2
     uint32_t it = 0, nstore = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
+     for (int mh = 0; mh < p.mt; mh++) {     // mt == 2: the two 128-row halves of the tile, accumulator mh each
       const int tt = tile / p.nblk, ncol0 = (tile - tt * p.nblk) * N;
-      const int b = tt / tiles_per_b, t0 = (tt - b * tiles_per_b) * kTM;
+      const int b = tt / tiles_per_b, t0 = (tt - b * tiles_per_b) * rows_per_tile + mh * kTM;
       const int t = t0 + q * 32 + lane;
       const bool row_ok = t < p.T;
       const size_t grow = (size_t)b * p.T + (row_ok ? t : 0);
-      const uint32_t buf = (p.nacc == 2) ? (it & 1) : 0;
-      const uint32_t use = (p.nacc == 2) ? (it >> 1) : it;
+      const uint32_t buf = (p.mt == 2) ? (uint32_t)mh : ((p.nacc == 2) ? (it & 1) : 0);
+      const uint32_t use = (p.mt == 2) ? it : ((p.nacc == 2) ? (it >> 1) : it);
       // operands of the epilogue that do not depend on the accumulator are requested before waiting for it, so
       // their DRAM latency overlaps the mainloop of this tile: dz of the gate backward, `add` of the first chunk
       float4 pre[8];
@@ -417,10 +449,12 @@ __global__ void __launch_bounds__(kThreadsN, 1) gemm_nt_tc_kernel(const __grid_c
             v[4 * j + 2] = m.z > 0.f ? v[4 * j + 2] : 0.f; v[4 * j + 3] = m.w > 0.f ? v[4 * j + 3] : 0.f;
           }
         }
-        unsigned char* sb = stg + (nstore & 1) * kStg;
+        unsigned char* sb = stg + (nstore & box_mask) * kStg;
         {
           const long long tb = PROF ? clock64() : 0;
-          if (lane == 0) ptx::bulk_wait_read<1>();
+          if (lane == 0) {
+            if (box_mask) ptx::bulk_wait_read<1>(); else ptx::bulk_wait_read<0>();
+          }
           __syncwarp();
           if constexpr (PROF) acc[NP_E_BULK] += clock64() - tb;
         }
@@ -439,6 +473,7 @@ __global__ void __launch_bounds__(kThreadsN, 1) gemm_nt_tc_kernel(const __grid_c
         nstore++;
       }
       }  // EPI_PLAIN
+     }  // mh
     }
     if (lane == 0) ptx::bulk_wait<0>();
     if constexpr (PROF) {
@@ -495,6 +530,12 @@ static bool map2(CUtensorMap* m, const float* base, int K, int Nrows, int box_ro
 }
 
 }  // namespace nt
+
+int nt_default_m_tiles() {
+  static int mt = 0;
+  if (!mt) { const char* e = getenv("WNB_NT_MT"); mt = (e && e[0] == '1') ? 1 : 2; }
+  return mt;
+}
 
 int gemm_nt_tc(const NtTcSeg* segs, int nseg, int N, float* out, int ld_out, const float* bias, const float* mask,
                int ldmask, const float* add, int ldadd, int relu_out, int accumulate, int B, int T, cudaStream_t st,
@@ -562,31 +603,28 @@ int gemm_nt_tc(const NtTcSeg* segs, int nseg, int N, float* out, int ld_out, con
   p.mask = mask; p.ldmask = ldmask; p.add = add; p.ldadd = ldadd;
   p.relu_out = relu_out; p.accumulate = accumulate;
   p.nacc = N <= 256 ? 2 : 1;
-  const int stage_bytes = kASub + N * 128;
-  int nst = (int)((227 * 1024 - 1024 - 512 - kEpiWarpsN * 2 * kStg) / stage_bytes);
+  p.mt = (opts && opts->m_tiles == 2) ? 2 : 1;
+  if (p.mt == 2 && (p.gate_mode || N > 256)) {
+    set_error("gemm_nt_tc: m_tiles = 2 is for plain epilogues with N <= 256");
+    return WNB_ERR_INVALID;
+  }
+  p.stg_boxes = p.mt == 2 ? 1 : 2;
+  const int stage_bytes = p.mt * kASub + N * 128;
+  int nst = (int)((227 * 1024 - 1024 - 512 - kEpiWarpsN * p.stg_boxes * kStg) / stage_bytes);
   static int max_stages = 0;
   if (!max_stages) { const char* e = getenv("WNB_NT_MAXSTAGES"); max_stages = e ? atoi(e) : 4; if (max_stages < 2) max_stages = 2; }
   if (nst > max_stages) nst = max_stages;
   if (nst < 2) { set_error("gemm_nt_tc: N too large"); return WNB_ERR_INVALID; }
   p.nstages = nst;
-  const size_t smem = (size_t)nst * stage_bytes + kEpiWarpsN * 2 * kStg + 512 + 1024;
-  static size_t configured = 0;
-  if (smem > configured) {
-    WNB_CUDA(cudaFuncSetAttribute(gemm_nt_tc_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    WNB_CUDA(cudaFuncSetAttribute(gemm_nt_tc_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    WNB_CUDA(cudaFuncSetAttribute(gemm_nt_tc_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    WNB_CUDA(cudaFuncSetAttribute(gemm_nt_tc_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    WNB_CUDA(cudaFuncSetAttribute(gemm_nt_tc_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    WNB_CUDA(cudaFuncSetAttribute(gemm_nt_tc_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
-  static int sms = 0;
-  if (!sms) {
-    int dev = 0;
-    WNB_CUDA(cudaGetDevice(&dev));
-    WNB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  }
-  const int ntiles = B * ((T + kTM - 1) / kTM) * p.nblk;
+  const size_t smem = (size_t)nst * stage_bytes + kEpiWarpsN * p.stg_boxes * kStg + 512 + 1024;
+  WNB_CUDA(ensure_dynamic_smem(reinterpret_cast<const void*>(gemm_nt_tc_kernel<false, 0>), smem));
+  WNB_CUDA(ensure_dynamic_smem(reinterpret_cast<const void*>(gemm_nt_tc_kernel<false, 1>), smem));
+  WNB_CUDA(ensure_dynamic_smem(reinterpret_cast<const void*>(gemm_nt_tc_kernel<false, 2>), smem));
+  WNB_CUDA(ensure_dynamic_smem(reinterpret_cast<const void*>(gemm_nt_tc_kernel<true, 0>), smem));
+  WNB_CUDA(ensure_dynamic_smem(reinterpret_cast<const void*>(gemm_nt_tc_kernel<true, 1>), smem));
+  WNB_CUDA(ensure_dynamic_smem(reinterpret_cast<const void*>(gemm_nt_tc_kernel<true, 2>), smem));
+  const int sms = device_sms();
+  const int ntiles = B * ((T + kTM * p.mt - 1) / (kTM * p.mt)) * p.nblk;
   const int grid = ntiles < sms ? ntiles : sms;
   const int epi = !p.gate_mode ? EPI_PLAIN : ((p.gate_mode >= 2 && p.gate_skip_z) ? EPI_GATE_BWD_NOZ : EPI_GATE);
   static int prof = -1;

@@ -50,7 +50,7 @@ extern "C" {
 WNB_API int wnb_pack_weights(const WnbPackDesc* descs, int ndesc, const float* src_base, float* dst_base,
                              const float* scale, void* stream) {
   WNB_REQUIRE(descs && ndesc > 0 && dst_base, "pack_weights: null pointer / empty table");
-  dim3 grid((unsigned)ndesc, 4);
+  dim3 grid((unsigned)ndesc, 8);
   pack_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(descs, src_base, dst_base, scale);
   WNB_CHECK_LAUNCH("pack_weights");
   return WNB_OK;

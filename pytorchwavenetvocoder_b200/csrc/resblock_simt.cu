@@ -511,11 +511,7 @@ WNB_API int wnb_resblock_fwd(const float* xin, const float* haux, const float* w
   WNB_REQUIRE(math_mode == WNB_MATH_FP32, "resblock_fwd: unknown math_mode %d", math_mode);
   const size_t smem = sizeof(TileSmem<8>) + (size_t)R * kBsLd * sizeof(float);
   WNB_REQUIRE(smem <= 227 * 1024, "resblock_fwd: n_resch=%d too large for the SIMT path", R);
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    WNB_CUDA(cudaFuncSetAttribute(resblock_fwd_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
+  if (smem > 48 * 1024) WNB_CUDA(ensure_dynamic_smem(reinterpret_cast<const void*>(resblock_fwd_simt_kernel), smem));
   dim3 grid(cdiv(T, kBN), B);
   resblock_fwd_simt_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(p);
   WNB_CHECK_LAUNCH("resblock_fwd_simt");
@@ -734,13 +730,15 @@ WNB_API int wnb_post_fwd(float* skip, const float* wp1, const float* bp1, const 
     }
     const NtTcSeg s1[1] = {{skip, S, 0, S, wp1, S, S, 0, 0}};
     if (post_split(S)) {   // two 256-column blocks: double-buffered accumulators, epilogue overlapped with the next tile
-      const NtTcOpts o{2, 0, 0, 0};
+      const NtTcOpts o{2, 0, 0, 0, nt_default_m_tiles()};
       if ((rc = gemm_nt_tc(s1, 1, S / 2, r1, S, bp1, nullptr, 0, nullptr, 0, 1, 0, B, T, st, nullptr, nullptr, nullptr, 0, 0,
                            nullptr, &o)) != WNB_OK)
         return rc;
     } else if ((rc = gemm_nt_tc(s1, 1, S, r1, S, bp1, nullptr, 0, nullptr, 0, 1, 0, B, T, st)) != WNB_OK) return rc;
     const NtTcSeg s2[1] = {{r1, S, 0, S, wp2, Q, S, 0, 0}};
-    return gemm_nt_tc(s2, 1, Q, logits, Q, bp2, nullptr, 0, nullptr, 0, 0, 0, B, T, st);
+    const NtTcOpts o2{1, 0, 0, 0, Q <= 256 ? nt_default_m_tiles() : 1};
+    return gemm_nt_tc(s2, 1, Q, logits, Q, bp2, nullptr, 0, nullptr, 0, 0, 0, B, T, st, nullptr, nullptr, nullptr, 0, 0,
+                      nullptr, &o2);
   }
   // (skip_rectified: the FFMA GEMM below applies ReLU to its B operand anyway, and ReLU is idempotent)
   {  // r1 = relu(wp1 * relu(skip) + bp1)
@@ -772,7 +770,7 @@ WNB_API int wnb_post_bwd(const float* skip, const float* r1, const float* dlogit
     const NtTcSeg s1[1] = {{dlogits, Q, 0, Q, wp2t, S, Q, 0, 0}};
     const NtTcSeg s2[1] = {{dh1, S, 0, S, wp1t, S, S, 0, 0}};
     if (post_split(S)) {
-      const NtTcOpts o{2, 0, 0, 0};
+      const NtTcOpts o{2, 0, 0, 0, nt_default_m_tiles()};
       if ((rc = gemm_nt_tc(s1, 1, S / 2, dh1, S, nullptr, r1, S, nullptr, 0, 0, 0, B, T, st, nullptr, nullptr, nullptr, 0, 0,
                            nullptr, &o)) != WNB_OK)
         return rc;

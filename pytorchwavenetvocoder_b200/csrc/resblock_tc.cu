@@ -79,13 +79,13 @@ __device__ unsigned long long g_fwd_prof[P_COUNT];
 // Dynamic tile scheduler: CTA c starts on tile c and then takes tiles from this counter, so SMs that get a
 // smaller share of the memory system simply process fewer tiles (with a static stride the slowest SM set the
 // kernel time: ncu showed SMs active for only 80 % of the elapsed cycles).  The last CTA to finish resets both
-// counters; launches of this kernel must therefore be stream-ordered (they are: one stream per process).
-__device__ unsigned int g_tile_next, g_cta_done;
+// counters.  They are two device words owned by the launching (device, stream) (common.cuh sched_counters), so launches
+// on different streams never share them.
 
 template <bool PROF>
 __global__ void __launch_bounds__(kThreadsTc, 1)
 resblock_fwd_tc_kernel(const __grid_constant__ Maps maps, const float* __restrict__ b1, const float* __restrict__ b2,
-                       int B, int T, int S, int d, int has_xout, int skip_init) {
+                       int B, int T, int S, int d, int has_xout, int skip_init, unsigned int* __restrict__ sched) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
@@ -149,7 +149,7 @@ resblock_fwd_tc_kernel(const __grid_constant__ Maps maps, const float* __restric
         ptx::tma_load_3d(sA + 2 * kSubBytes, &maps.x, &bars[B_AFULL], 0, t0, b);
         ptx::tma_load_3d(sA + 3 * kSubBytes, &maps.x, &bars[B_AFULL], 32, t0, b);
         ptx::tma_load_3d(sA + 4 * kSubBytes, &maps.haux, &bars[B_AFULL], 0, t0, b);
-        tile = (int)(atomicAdd(&g_tile_next, 1u) + gridDim.x);
+        tile = (int)(atomicAdd(&sched[0], 1u) + gridDim.x);
         if (tile >= ntiles) tile = -1;
       }
     }
@@ -351,9 +351,9 @@ resblock_fwd_tc_kernel(const __grid_constant__ Maps maps, const float* __restric
   if (warp == 1) ptx::tmem_dealloc<512>(tmem);
   if (threadIdx.x == 0) {
     __threadfence();
-    if (atomicAdd(&g_cta_done, 1u) == gridDim.x - 1) {  // last CTA out: re-arm the scheduler for the next launch
-      g_tile_next = 0;
-      g_cta_done = 0;
+    if (atomicAdd(&sched[1], 1u) == gridDim.x - 1) {  // last CTA out: re-arm the scheduler for the next launch
+      sched[0] = 0;
+      sched[1] = 0;
     }
   }
 }
@@ -424,23 +424,12 @@ int resblock_fwd_tc(const FwdParams& p, cudaStream_t st) {
     set_error("resblock_fwd_tc: cuTensorMapEncodeTiled failed or is unavailable");
     return WNB_ERR_CUDA;
   }
-  static bool configured = false;
-  static bool prof = false;
-  if (!configured) {
-    const char* e = getenv("WNB_FWD_PROF");
-    prof = e && e[0] == '1';
-    WNB_CUDA(cudaFuncSetAttribute(resblock_fwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  kSmemBytes));
-    WNB_CUDA(cudaFuncSetAttribute(resblock_fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  kSmemBytes));
-    configured = true;
-  }
-  static int sms = 0;
-  if (!sms) {
-    int dev = 0;
-    WNB_CUDA(cudaGetDevice(&dev));
-    WNB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  }
+  static const bool prof = [] { const char* e = getenv("WNB_FWD_PROF"); return e && e[0] == '1'; }();
+  WNB_CUDA(ensure_dynamic_smem(reinterpret_cast<const void*>(resblock_fwd_tc_kernel<false>), kSmemBytes));
+  WNB_CUDA(ensure_dynamic_smem(reinterpret_cast<const void*>(resblock_fwd_tc_kernel<true>), kSmemBytes));
+  const int sms = device_sms();
+  unsigned int* sched = sched_counters(st);
+  if (!sched) { set_error("resblock_fwd_tc: cannot allocate the scheduler words"); return WNB_ERR_CUDA; }
   const int ntiles = p.B * ((p.T + kTM - 1) / kTM);
   const int grid = ntiles < sms ? ntiles : sms;
   if (prof) {  // tuning aid: synchronous, prints where each role of the pipeline waited
@@ -448,7 +437,7 @@ int resblock_fwd_tc(const FwdParams& p, cudaStream_t st) {
     zero[P_E_MIN] = ~0ull;
     WNB_CUDA(cudaMemcpyToSymbol(g_fwd_prof, zero, sizeof(zero)));
     resblock_fwd_tc_kernel<true><<<grid, kThreadsTc, kSmemBytes, st>>>(maps, p.b1, p.b2, p.B, p.T, p.S, p.d,
-                                                                     p.xout ? 1 : 0, p.skip_init);
+                                                                     p.xout ? 1 : 0, p.skip_init, sched);
     WNB_CHECK_LAUNCH("resblock_fwd_tc");
     WNB_CUDA(cudaStreamSynchronize(st));
     WNB_CUDA(cudaMemcpyFromSymbol(h, g_fwd_prof, sizeof(h)));
@@ -460,7 +449,7 @@ int resblock_fwd_tc(const FwdParams& p, cudaStream_t st) {
     return WNB_OK;
   }
   resblock_fwd_tc_kernel<false><<<grid, kThreadsTc, kSmemBytes, st>>>(maps, p.b1, p.b2, p.B, p.T, p.S, p.d,
-                                                                    p.xout ? 1 : 0, p.skip_init);
+                                                                    p.xout ? 1 : 0, p.skip_init, sched);
   WNB_CHECK_LAUNCH("resblock_fwd_tc");
   return WNB_OK;
 }

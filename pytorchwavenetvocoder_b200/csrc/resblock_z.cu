@@ -58,12 +58,12 @@ struct alignas(64) Maps {
 enum { B_W = 0, B_AFULL, B_AEMPTY, B_D1F0, B_D1F1, B_D1E0, B_D1E1, B_ZF, B_D2F, B_D2E, B_TILE0, B_TILE1, B_COUNT };
 static_assert(8 * B_COUNT + 16 <= 256, "barrier block");
 
-// dynamic tile scheduler state (see resblock_tc.cu): launches must be stream-ordered
-__device__ unsigned int g_tile_next, g_cta_done;
+// dynamic tile scheduler: `sched` = {next tile, CTAs done}, two device words owned by the launching (device, stream)
+// (common.cuh sched_counters): launches on different streams never share them.
 
 __global__ void __launch_bounds__(kThreadsZ, 1)
 resblock_fwd_z_kernel(const __grid_constant__ Maps maps, const float* __restrict__ b1, const float* __restrict__ b2,
-                      int B, int T, int d, int has_xout, int zcol0) {
+                      int B, int T, int d, int has_xout, int zcol0, unsigned int* __restrict__ sched) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
@@ -116,7 +116,7 @@ resblock_fwd_z_kernel(const __grid_constant__ Maps maps, const float* __restrict
         ptx::tma_load_3d(sA + 2 * kSubBytes, &maps.x, &bars[B_AFULL], 0, t0, b);
         ptx::tma_load_3d(sA + 3 * kSubBytes, &maps.x, &bars[B_AFULL], 32, t0, b);
         ptx::tma_load_3d(sA + 4 * kSubBytes, &maps.haux, &bars[B_AFULL], 0, t0, b);
-        tile = (int)(atomicAdd(&g_tile_next, 1u) + gridDim.x);
+        tile = (int)(atomicAdd(&sched[0], 1u) + gridDim.x);
         if (tile >= ntiles) tile = -1;
         if (tile >= 0) {
           // there is room for only one A stage, so the next tile cannot be loaded yet -- but it can be pulled into
@@ -177,7 +177,7 @@ resblock_fwd_z_kernel(const __grid_constant__ Maps maps, const float* __restrict
           bool need1 = tile_ring[nx & 1] >= 0;
           const bool has_next = need1;
           bool need2 = has_xout != 0;
-          uint32_t spins = 0;
+          ptx::SpinGuard guard;
           while (need1 || need2) {
             if (need2 && ptx::mbar_try_wait(&bars[B_ZF], it & 1) && ptx::mbar_try_wait(&bars[B_D2E], (it & 1) ^ 1)) {
               ptx::tc_fence_after();
@@ -198,8 +198,8 @@ resblock_fwd_z_kernel(const __grid_constant__ Maps maps, const float* __restrict
               need1 = false;
               continue;
             }
-            if (++spins > (1u << 24)) {
-              printf("wnb200: resblock_fwd_z MMA issuer timed out (block %d)\n", blockIdx.x);
+            if (guard.expired()) {
+              printf("wnb200: resblock_fwd_z MMA issuer timed out after 20 s (block %d)\n", blockIdx.x);
               __trap();
             }
           }
@@ -321,9 +321,9 @@ resblock_fwd_z_kernel(const __grid_constant__ Maps maps, const float* __restrict
   if (warp == 1) ptx::tmem_dealloc<512>(tmem);
   if (threadIdx.x == 0) {
     __threadfence();
-    if (atomicAdd(&g_cta_done, 1u) == gridDim.x - 1) {  // last CTA out: re-arm the scheduler for the next launch
-      g_tile_next = 0;
-      g_cta_done = 0;
+    if (atomicAdd(&sched[1], 1u) == gridDim.x - 1) {  // last CTA out: re-arm the scheduler for the next launch
+      sched[0] = 0;
+      sched[1] = 0;
     }
   }
 }
@@ -388,21 +388,14 @@ int resblock_fwd_z(const float* xin, const float* haux, const float* w1, const f
     set_error("resblock_fwd_z: cuTensorMapEncodeTiled failed or is unavailable");
     return WNB_ERR_CUDA;
   }
-  static bool configured = false;
-  if (!configured) {
-    WNB_CUDA(cudaFuncSetAttribute(resblock_fwd_z_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    configured = true;
-  }
-  static int sms = 0;
-  if (!sms) {
-    int dev = 0;
-    WNB_CUDA(cudaGetDevice(&dev));
-    WNB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  }
+  WNB_CUDA(ensure_dynamic_smem(reinterpret_cast<const void*>(resblock_fwd_z_kernel), kSmemBytes));
+  const int sms = device_sms();
+  unsigned int* sched = sched_counters(st);
+  if (!sched) { set_error("resblock_fwd_z: cannot allocate the scheduler words"); return WNB_ERR_CUDA; }
   const int ntiles = B * ((T + kTM - 1) / kTM);
   const int grid = ntiles < sms ? ntiles : sms;
   if (launch_pdl(resblock_fwd_z_kernel, grid, kThreadsZ, kSmemBytes, st, maps, b1, b2res ? b2res : b1, B, T, d,
-                 xout ? 1 : 0, zcol0) != cudaSuccess) { /* reported below */ }
+                 xout ? 1 : 0, zcol0, sched) != cudaSuccess) { /* reported below */ }
   WNB_CHECK_LAUNCH("resblock_fwd_z");
   return WNB_OK;
 }

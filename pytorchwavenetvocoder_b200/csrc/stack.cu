@@ -62,7 +62,12 @@ WNB_API int wnb_skip_gemm(const float* zall, const float* wskip, const float* bs
   WNB_REQUIRE(zall && wskip && skip && B > 0 && T > 0 && K % 32 == 0 && S % 32 == 0 && (S <= 256 || S == 512),
               "skip_gemm: bad arguments");
   const NtTcSeg seg[1] = {{zall, K, 0, K, wskip, S, K, 0, 0}};
-  return gemm_nt_tc(seg, 1, S, skip, S, bskip, nullptr, 0, nullptr, 0, relu ? 1 : 0, 0, B, T, (cudaStream_t)stream);
+  // 256 rows x (<=256 columns) per CTA tile: every Wskip chunk is fetched from L2 once per 256 rows (K = L*R is long,
+  // the GEMM is bound by the L2 -> SM path: DESIGN.md section 3)
+  const int nblk = S > 256 ? S / 256 : 1;
+  const NtTcOpts o{nblk, 0, 0, 0, nt_default_m_tiles()};
+  return gemm_nt_tc(seg, 1, S / nblk, skip, S, bskip, nullptr, 0, nullptr, 0, relu ? 1 : 0, 0, B, T, (cudaStream_t)stream,
+                    nullptr, nullptr, nullptr, 0, 0, nullptr, &o);
 }
 
 WNB_API int wnb_stack_fwd(float* xs, int nxs, const float* haux, const float* w1, const float* b1, const float* w2res,
@@ -130,7 +135,7 @@ WNB_API int wnb_stack_bwd(const float* xs, const float* haux, const float* zall,
     const int nb = pick_block(ldz, cands, 5);
     WNB_REQUIRE(nb > 0, "stack_bwd: L*R must be a multiple of 32");
     const NtTcSeg seg[1] = {{dskip, S, 0, S, wskip_t, ldz, S, 0, 0}};
-    const NtTcOpts o{ldz / nb, 0, 0, 0};
+    const NtTcOpts o{ldz / nb, 0, 0, 0, nt_default_m_tiles()};
     ProfScope ps(WNB_PROF_DZALL_GEMM, st);
     if ((rc = gemm_nt_tc(seg, 1, nb, dzall, ldz, nullptr, nullptr, 0, nullptr, 0, 0, 0, B, T, st, nullptr, nullptr, nullptr,
                          0, 0, nullptr, &o)) != WNB_OK)
@@ -151,7 +156,7 @@ WNB_API int wnb_stack_bwd(const float* xs, const float* haux, const float* zall,
       const float* wg = wgate + (size_t)l * 3 * R * (K1 + R);
       const NtTcSeg sg[4] = {{xin, R, -d, R, wg, 3 * R, K1 + R, 0, 0}, {xin, R, 0, R, wg, 3 * R, K1 + R, R, 0},
                              {haux, Ap, 0, Ap, wg, 3 * R, K1 + R, 2 * R, 0}, {dout, R, 0, R, wg, 3 * R, K1 + R, K1, 0}};
-      const NtTcOpts o{1, ldz, 1, dout ? 1 : 0};
+      const NtTcOpts o{1, ldz, 1, dout ? 1 : 0, 1};
       ProfScope ps(WNB_PROF_GATE_BWD, st);
       if ((rc = gemm_nt_tc(sg, dout ? 4 : 3, dout ? 3 * R : 2 * R, dxin /* z output suppressed */, R,
                            b1 + (size_t)l * 2 * R, nullptr, 0, nullptr, 0, 0, 0, B, T, st, dzl, dpre, nullptr, 0, 0,

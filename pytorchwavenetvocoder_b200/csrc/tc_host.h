@@ -36,7 +36,11 @@ struct NtTcOpts {
   int gate_ld_dz;    // row pitch (floats) of the gate-backward dz input (0: gate_R)
   int gate_skip_z;   // gate-backward: do not write z
   int gate_fused_dz; // gate-backward shorthand with N == 192: accumulator columns 128..191 are added to dz
+  int m_tiles;       // 2: a CTA tile is two 128-row time tiles sharing every weight chunk (plain epilogue, N <= 256):
+                     //    halves the L2 -> SM weight traffic of the K >= 512 GEMMs (skip, dZ_all, post network)
 };
+// default of NtTcOpts::m_tiles for the K >= 512 GEMMs: 2, WNB_NT_MT=1 in the environment restores one tile per CTA
+int nt_default_m_tiles();
 int gemm_nt_tc(const NtTcSeg* segs, int nseg, int N, float* out, int ld_out, const float* bias, const float* mask,
                int ldmask, const float* add, int ldadd, int relu_out, int accumulate, int B, int T, cudaStream_t st,
                const float* gate_dz = nullptr, float* gate_dpre = nullptr, float* out2 = nullptr, int ld_out2 = 0,

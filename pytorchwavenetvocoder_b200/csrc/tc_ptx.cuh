@@ -57,13 +57,33 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug must trap (error returned to the host) instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  for (uint32_t it = 0; it < (1u << 22); ++it) {
-    if (mbar_try_wait(bar, parity)) return;
+// Bounded waits: a protocol bug must trap (error returned to the host) instead of hanging the GPU -- but the bound is
+// WALL-CLOCK time (20 s on %globaltimer, looked at every 64 K polls), not a poll count: under a profiler's kernel
+// replay, time slicing or preemption a healthy kernel can sit on a barrier for many millions of polls.
+__device__ __forceinline__ uint64_t globaltimer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+struct SpinGuard {
+  uint32_t polls = 0;
+  uint64_t t0 = 0;
+  __device__ __forceinline__ bool expired() {
+    if ((++polls & 0xFFFFu) != 0) return false;
+    const uint64_t now = globaltimer_ns();
+    if (t0 == 0) { t0 = now; return false; }
+    return now - t0 > 20000000000ull;
   }
-  printf("wnb200: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
-  __trap();
+};
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  SpinGuard guard;
+  while (!mbar_try_wait(bar, parity)) {
+    if (guard.expired()) {
+      printf("wnb200: mbarrier wait timed out after 20 s (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+      __trap();
+    }
+  }
 }
 
 // ---------------------------------------------------------------- TMA

@@ -385,18 +385,9 @@ int wgrad_tc_blocks(const WgBlock* blocks, int nblocks, const WgOperand* b_ops, 
   p.tiles_per_b = (T + tk - 1) / tk;
   p.ntiles = B * p.tiles_per_b;
   const size_t smem = (size_t)nst * stage_bytes + 1024 + 256;   // barriers: 2*nst + 4 (+ TMEM slot) <= 21 words
-  static size_t configured = 0;
-  if (smem > configured) {
-    WNB_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    WNB_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
-  static int sms = 0;
-  if (!sms) {
-    int dev = 0;
-    WNB_CUDA(cudaGetDevice(&dev));
-    WNB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  }
+  WNB_CUDA(ensure_dynamic_smem(reinterpret_cast<const void*>(wgrad_tc_kernel<false>), smem));
+  WNB_CUDA(ensure_dynamic_smem(reinterpret_cast<const void*>(wgrad_tc_kernel<true>), smem));
+  const int sms = device_sms();
   int grid = p.ntiles < sms ? p.ntiles : sms;
   if (p.n_split > 1) {
     if (p.n_split > sms) { set_error("wgrad_tc: n_split exceeds the SM count"); return WNB_ERR_INVALID; }

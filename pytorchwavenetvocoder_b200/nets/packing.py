@@ -91,7 +91,8 @@ class StackPlan(object):
             pk.append((src, src2, dst, n[0], n[1], n[2], ss[0], ss[1], ss[2], ds[0], ds[1], ds[2], op, flags, nsum))
 
         # ---- pack: parameters -> P ----
-        cp(ptr("causal.conv.weight"), P.off["wf"], (ks, Q, R), (1, ks, Q * ks), (Q * R, R, 1))
+        # (transposing entries iterate in SOURCE order: a strided read stalls its thread, a strided write does not)
+        cp(ptr("causal.conv.weight"), P.off["wf"], (R, Q, ks), (Q * ks, ks, 1), (1, R, Q * R))
         cp(ptr("causal.conv.bias"), P.off["bf"], (1, 1, R), (0, 0, 1), (0, 0, 1))
         Kg = K1 + R
         skip_bias_ptrs = []
@@ -103,32 +104,32 @@ class StackPlan(object):
                 dw = ptr("dil_%s.%d.conv.weight" % (nm, l))         # (R, R, ks)  [o][c][j]
                 aw = ptr("aux_1x1_%s.%d.weight" % (nm, l))          # (R, A, 1)   [o][a]
                 # W1[l][br*R + o][j*R + c]
-                cp(dw, w1 + br * R * K1, (R, ks, R), (R * ks, 1, ks), (K1, R, 1))
+                cp(dw, w1 + br * R * K1, (R, R, ks), (R * ks, ks, 1), (K1, 1, R))
                 cp(aw, w1 + br * R * K1 + ks * R, (1, R, A), (0, A, 1), (0, K1, 1))
                 # wgate[l][br*R + o][j*R + c]  (rows of pitch K1 + R)
-                cp(dw, wg + br * R * Kg, (R, ks, R), (R * ks, 1, ks), (Kg, R, 1))
+                cp(dw, wg + br * R * Kg, (R, R, ks), (R * ks, ks, 1), (Kg, 1, R))
                 cp(aw, wg + br * R * Kg + ks * R, (1, R, A), (0, A, 1), (0, Kg, 1))
                 # w1t[l][j*R + c][br*R + o]
-                cp(dw, w1t + br * R, (ks, R, R), (1, ks, R * ks), (R * 2 * R, 2 * R, 1))
-                cp(aw, w1t + ks * R * 2 * R + br * R, (1, A, R), (0, 1, A), (0, 2 * R, 1))
+                cp(dw, w1t + br * R, (R, R, ks), (R * ks, ks, 1), (1, 2 * R, R * 2 * R))
+                cp(aw, w1t + ks * R * 2 * R + br * R, (1, R, A), (0, A, 1), (0, 1, 2 * R))
                 cp(ptr("dil_%s.%d.conv.bias" % (nm, l)), P.off["b1"] + l * 2 * R + br * R, (1, 1, R), (0, 0, 1), (0, 0, 1),
                    op=ADD2, src2=ptr("aux_1x1_%s.%d.bias" % (nm, l)))
             rw = ptr("res_1x1.%d.weight" % l)                        # (R, R, 1) [o][c]
             cp(rw, P.off["W2res"] + l * R * R, (1, 1, R * R), (0, 0, 1), (0, 0, 1))
             cp(ptr("res_1x1.%d.bias" % l), P.off["b2res"] + l * R, (1, 1, R), (0, 0, 1), (0, 0, 1))
             # wgate[l][2R + c][K1 + o] = W2res[l][o][c]
-            cp(rw, wg + 2 * R * Kg + K1, (1, R, R), (0, 1, R), (0, Kg, 1))
+            cp(rw, wg + 2 * R * Kg + K1, (1, R, R), (0, R, 1), (0, 1, Kg))
             sw = ptr("skip_1x1.%d.weight" % l)                       # (S, R, 1) [s][c]
             cp(sw, P.off["Wskip"] + l * R, (1, S, R), (0, R, 1), (0, L * R, 1))
-            cp(sw, P.off["wskt"] + l * R * S, (1, R, S), (0, 1, R), (0, S, 1))
+            cp(sw, P.off["wskt"] + l * R * S, (1, S, R), (0, R, 1), (0, 1, S))
             skip_bias_ptrs.append(ptr("skip_1x1.%d.bias" % l))
         self.skip_bias_table = torch.tensor(skip_bias_ptrs, dtype=torch.int64, device=self.device)
         cp(self.skip_bias_table.data_ptr(), P.off["bskip"], (1, 1, S), (0, 0, 1), (0, 0, 1), op=SUMPTR, nsum=L)
         cp(ptr("conv_post_1.weight"), P.off["Wp1"], (1, 1, S * S), (0, 0, 1), (0, 0, 1))
-        cp(ptr("conv_post_1.weight"), P.off["wp1t"], (1, S, S), (0, 1, S), (0, S, 1))
+        cp(ptr("conv_post_1.weight"), P.off["wp1t"], (1, S, S), (0, S, 1), (0, 1, S))
         cp(ptr("conv_post_1.bias"), P.off["bp1"], (1, 1, S), (0, 0, 1), (0, 0, 1))
         cp(ptr("conv_post_2.weight"), P.off["Wp2"], (1, 1, Q * S), (0, 0, 1), (0, 0, 1))
-        cp(ptr("conv_post_2.weight"), P.off["wp2t"], (1, S, Q), (0, 1, S), (0, Q, 1))
+        cp(ptr("conv_post_2.weight"), P.off["wp2t"], (1, Q, S), (0, S, 1), (0, 1, Q))
         cp(ptr("conv_post_2.bias"), P.off["bp2"], (1, 1, Q), (0, 0, 1), (0, 0, 1))
         self.pack_table = self._upload(pk)
         self.n_pack = len(pk)
@@ -151,7 +152,7 @@ class StackPlan(object):
         def up(src, name, n, ss, ds):
             pk.append((src, 0, go[name], n[0], n[1], n[2], ss[0], ss[1], ss[2], ds[0], ds[1], ds[2], COPY, 0, 0))
 
-        up(G.off["wf"], "causal.conv.weight", (R, Q, ks), (1, R, Q * R), (Q * ks, ks, 1))
+        up(G.off["wf"], "causal.conv.weight", (ks, Q, R), (Q * R, R, 1), (1, ks, Q * ks))
         up(G.off["bf"], "causal.conv.bias", (1, 1, R), (0, 0, 1), (0, 0, 1))
         if U > 0:
             up(G.off["upw"], "upsampling.conv.weight", (1, 1, U), (0, 0, 1), (0, 0, 1))
@@ -159,7 +160,7 @@ class StackPlan(object):
         for l in range(L):
             w1 = G.off["W1"] + l * 2 * R * K1
             for br, nm in enumerate(("sigmoid", "tanh")):
-                up(w1 + br * R * K1, "dil_%s.%d.conv.weight" % (nm, l), (R, R, ks), (K1, 1, R), (R * ks, ks, 1))
+                up(w1 + br * R * K1, "dil_%s.%d.conv.weight" % (nm, l), (R, ks, R), (K1, R, 1), (R * ks, 1, ks))
                 up(w1 + br * R * K1 + ks * R, "aux_1x1_%s.%d.weight" % (nm, l), (1, R, A), (0, K1, 1), (0, A, 1))
                 for bn in ("dil_%s.%d.conv.bias", "aux_1x1_%s.%d.bias"):
                     up(G.off["b1"] + l * 2 * R + br * R, bn % (nm, l), (1, 1, R), (0, 0, 1), (0, 0, 1))

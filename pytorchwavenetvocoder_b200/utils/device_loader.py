@@ -1,0 +1,203 @@
+# -*- coding: utf-8 -*-
+"""``train_generator`` (reference bin/train.py:67-312, mini-batch modes) with the per-batch work on the GPU.
+
+The reference builds every batch on the host -- window slicing, mu-law over the whole window, StandardScaler,
+transpose, stack, three ``.cuda()`` copies per batch (train.py:157-185) -- in a Python prefetch thread.  At B200 step
+times (milliseconds) that thread is the wall.  Here
+
+* a loader thread only READS files (wav + feature frames) into pinned staging slots;
+* each utterance is copied ONCE, asynchronously on a copy stream, into device ring buffers holding the
+  concatenated float32 waveform and the concatenated feature frames (the reference's ``x_buffer`` / ``h_buffer``);
+* one kernel launch (``wnb_make_train_batch``, csrc/loader.cu) cuts a whole batch out of the rings: windowing with
+  the reference's hop arithmetic, mu-law (bit exact), scaler, (frames, D) -> (D, frames) layout, next-sample targets.
+
+Same batches, bit for bit, as ``bin.train.train_generator`` on the same file lists (tests/test_gpu_loader.py).
+"""
+import logging
+import threading
+from queue import Queue
+
+import numpy as np
+import torch
+
+from .. import _lib
+from .utils import read_hdf5, read_wav
+
+
+def load_pair_frames(wavfile, featfile, feature_type, upsampling_factor, use_upsampling_layer, use_speaker_code):
+    """One utterance at FRAME rate: waveform float32 (n,), features (frames, D), trimmed like the reference's
+    ``validate_length`` (train.py:35-64, 119-138).  For the extend_time mode (no up-sampling layer) the features stay
+    at frame rate -- the device kernel indexes them per sample -- but are float64 like ``extend_time``'s output."""
+    x, _ = read_wav(wavfile, dtype=np.float32)
+    h = read_hdf5(featfile, "/" + feature_type)
+    U = upsampling_factor
+    if not use_upsampling_layer:
+        h = np.asarray(h, dtype=np.float64)
+    if use_speaker_code:
+        sc = read_hdf5(featfile, "/speaker_code")
+        h = np.concatenate([h, np.tile(sc, [h.shape[0], 1])], axis=1)
+    if use_upsampling_layer:
+        if x.shape[0] > h.shape[0] * U:
+            x = x[:h.shape[0] * U]
+        if x.shape[0] < h.shape[0] * U:
+            mod_y = h.shape[0] * U - x.shape[0]
+            h = h[:-(mod_y // U + 1)]
+            x = x[:h.shape[0] * U]
+        assert len(x) == len(h) * U
+    else:
+        n = min(x.shape[0], h.shape[0] * U)      # validate_length(x, extend_time(h, U))
+        x = x[:n]
+        h = h[:(n + U - 1) // U]
+    return np.ascontiguousarray(x, dtype=np.float32), np.ascontiguousarray(h)
+
+
+class DeviceTrainGenerator(object):
+    """Drop-in for ``train_generator(...)`` in the mini-batch modes (``batch_length`` given): ``next()`` returns
+    ``((x, h), t)`` CUDA tensors -- x, t (B, T) int64, h (B, D, T/U or T) float32."""
+
+    def __init__(self, wav_list, feat_list, receptive_field, batch_length, batch_size=1, feature_type="world",
+                 n_quantize=256, mean=None, scale=None, shuffle=True, upsampling_factor=80, use_upsampling_layer=True,
+                 use_speaker_code=False, device=None, ring_windows=6, prefetch=8):
+        if batch_length is None:
+            raise ValueError("DeviceTrainGenerator covers the mini-batch modes; use train_generator for utterance batches")
+        self.lib = _lib.load()
+        self.dev = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+        self.wav_list, self.feat_list = list(wav_list), list(feat_list)
+        self.feature_type, self.shuffle = feature_type, shuffle
+        self.U, self.use_up, self.use_spk = upsampling_factor, use_upsampling_layer, use_speaker_code
+        self.B, self.mu = batch_size, n_quantize
+        U = upsampling_factor
+        if use_upsampling_layer:                          # train.py:99-103, 202-205
+            batch_mod = (receptive_field + batch_length) % U
+            logging.warning("batch length is decreased due to upsampling (%d -> %d)" % (
+                batch_length, batch_length - batch_mod))
+            batch_length -= batch_mod
+            self.h_bs = (receptive_field + batch_length) // U
+            self.T = self.h_bs * U                        # x_bs - 1
+            self.Tf = self.h_bs
+            self.hop = (batch_length // U) * U            # x_ss
+            self.need = (self.h_bs + 1) * U               # "while len(h_buffer) > h_bs"
+        else:                                             # train.py:106-110, 160-185
+            win = receptive_field + batch_length
+            self.T = self.Tf = win - 1
+            self.hop = batch_length
+            self.need = win + 1                           # "while len(x_buffer) > win"
+        self.mean = None if mean is None else torch.as_tensor(np.asarray(mean, np.float64)).to(self.dev)
+        self.scale = None if scale is None else torch.as_tensor(np.asarray(scale, np.float64)).to(self.dev)
+        # device rings: capacity for `ring_windows` batches worth of hops plus one window
+        self.cap_s = max(int(self.T + 2 + self.hop * self.B * ring_windows), 1 << 22)
+        self.cap_f = self.cap_s // U + 256
+        self.wave = torch.zeros(self.cap_s, dtype=torch.float32, device=self.dev)
+        self.fos = None if use_upsampling_layer else torch.zeros(self.cap_s, dtype=torch.int32, device=self.dev)
+        self.feat = None                                  # allocated at the first utterance (dtype / D follow the files)
+        self.head_s = self.tail_s = 0                     # absolute sample positions (ring index = pos % cap_s)
+        self.tail_f = 0                                   # absolute frame position of the next appended frame
+        self.copy_stream = torch.cuda.Stream(device=self.dev)
+        self.last_batch_event = None
+        self.utts = []                                    # (start_s, n, start_f, nf) of the utterances still in the ring
+        self.queue = Queue(prefetch)
+        self.thread = threading.Thread(target=self._reader, daemon=True)
+        self.thread.start()
+
+    # ------------------------------------------------------------------ loader thread: file I/O only
+    def _reader(self):
+        wl, fl = self.wav_list, self.feat_list
+        try:
+            if self.shuffle:
+                idx = np.random.permutation(len(wl))
+                wl, fl = [wl[i] for i in idx], [fl[i] for i in idx]
+            while True:
+                for w, f in zip(wl, fl):
+                    x, h = load_pair_frames(w, f, self.feature_type, self.U, self.use_up, self.use_spk)
+                    xp = torch.from_numpy(x).pin_memory()
+                    hp = torch.from_numpy(h).pin_memory()
+                    self.queue.put((xp, hp))
+                if self.shuffle:
+                    idx = np.random.permutation(len(wl))
+                    wl, fl = [wl[i] for i in idx], [fl[i] for i in idx]
+        except BaseException as e:     # noqa: BLE001 -- surface reader failures in the consumer
+            self.queue.put(e)
+
+    # ------------------------------------------------------------------ ring appends (async H2D on the copy stream)
+    def _ring_copy(self, ring, pos, cap, src):
+        n = src.shape[0]
+        o = pos % cap
+        first = min(n, cap - o)
+        ring[o:o + first].copy_(src[:first], non_blocking=True)
+        if first < n:
+            ring[:n - first].copy_(src[first:], non_blocking=True)
+
+    def _append(self, xp, hp):
+        n, nf = xp.shape[0], hp.shape[0]
+        if n == 0:
+            return
+        if self.feat is None:
+            self.D = hp.shape[1]
+            self.feat = torch.zeros(self.cap_f, self.D, dtype=hp.dtype, device=self.dev)
+            self.feat_f64 = 1 if hp.dtype == torch.float64 else 0
+        if hp.dtype != self.feat.dtype:
+            hp = hp.to(self.feat.dtype).pin_memory()
+        while self.utts and self.utts[0][0] + self.utts[0][1] <= self.head_s:
+            self.utts.pop(0)                              # fully consumed
+        head_f = self.tail_f
+        if self.utts:
+            s_, n_, f_, nf_ = self.utts[0]
+            head_f = f_ + max(self.head_s - s_, 0) // self.U
+        if self.tail_s - self.head_s + n > self.cap_s or self.tail_f - head_f + nf > self.cap_f:
+            raise _lib.WnbError("utterance of %d samples / %d frames does not fit the device ring (%d / %d)"
+                                % (n, nf, self.cap_s, self.cap_f))
+        self.utts.append((self.tail_s, n, self.tail_f, nf))
+        with torch.cuda.stream(self.copy_stream):
+            if self.last_batch_event is not None:
+                self.copy_stream.wait_event(self.last_batch_event)   # the overwritten region was read by earlier batches
+            self._ring_copy(self.wave, self.tail_s, self.cap_s, xp)
+            self._ring_copy(self.feat, self.tail_f, self.cap_f, hp)
+            if self.fos is not None:
+                fidx = (self.tail_f + torch.arange(n, dtype=torch.int64) // self.U).to(torch.int32).pin_memory()
+                self._ring_copy(self.fos, self.tail_s, self.cap_s, fidx)
+                self._keep = (xp, hp, fidx)
+            else:
+                self._keep = (xp, hp)
+            ev = torch.cuda.Event()
+            ev.record(self.copy_stream)
+        self.append_event = ev
+        self.tail_s += n
+        self.tail_f += nf
+
+    # ------------------------------------------------------------------ one batch
+    def next(self):
+        B, hop = self.B, self.hop
+        # the reference cuts a window whenever the buffer is long enough; B consecutive windows make a batch
+        while self.tail_s - (self.head_s + (B - 1) * hop) < self.need:
+            item = self.queue.get()
+            if isinstance(item, BaseException):
+                raise item
+            self._append(*item)
+        cur = torch.cuda.current_stream(self.dev)
+        cur.wait_event(self.append_event)
+        x = torch.empty(B, self.T, dtype=torch.int64, device=self.dev)
+        t = torch.empty(B, self.T, dtype=torch.int64, device=self.dev)
+        h = torch.empty(B, self.D, self.Tf, dtype=torch.float32, device=self.dev)
+        P = _lib.ptr
+        _lib.check(self.lib.wnb_make_train_batch(
+            P(self.wave), P(self.feat), P(self.fos), self.head_s, hop, self.U, self.cap_s, self.cap_f, P(self.mean),
+            P(self.scale), P(x), P(t), P(h), B, self.T, self.Tf, self.D, self.feat_f64, self.mu, cur.cuda_stream),
+            "make_train_batch")
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        self.last_batch_event = ev
+        self.head_s += hop * B
+        # read ahead: whatever the reader thread has ready goes to the device now (copy stream, behind this batch's
+        # kernel), so the next batches find their utterances resident and the copies overlap the training step
+        while (not self.queue.empty() and self.tail_s - self.head_s < self.cap_s // 2
+               and self.tail_s - self.head_s < 3 * (self.need + (B - 1) * hop)):
+            item = self.queue.get()
+            if isinstance(item, BaseException):
+                raise item
+            self._append(*item)
+        return (x, h), t
+
+    __next__ = next
+
+    def __iter__(self):
+        return self
