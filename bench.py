@@ -308,7 +308,10 @@ def run_ours(args):
                 ms_l = e4.elapsed_time(e5)
                 up_bytes = (gen.tail_s - s0_) * (4 + cfg.n_aux * 4.0 / U)
                 loader_e2e = {"ms": ms_l, "last_loss": last_l, "h2d_bytes_per_step": int(up_bytes / args.steps),
-                              "T": gen.T}
+                              "T": gen.T, "reader_ms_per_utterance": 1e3 * gen.stats["reader_s"] / max(gen.stats["utts"], 1),
+                              "consumer_wait_ms_per_batch": 1e3 * gen.stats["wait_s"] / max(gen.stats["batches"], 1),
+                              "launch_ms_per_batch": 1e3 * gen.stats.get("launch_s", 0.0) / max(gen.stats["batches"], 1),
+                              "reader_threads": gen.n_readers}
             finally:
                 shutil.rmtree(tmpd, ignore_errors=True)
         if dist is not None:
@@ -382,6 +385,10 @@ def run_ours(args):
                 "value": samples / (loader_e2e["ms"] / args.steps * 1e-3), "unit": "samples/s",
                 "ms_per_step": loader_e2e["ms"] / args.steps, "h2d_bytes_per_step": loader_e2e["h2d_bytes_per_step"],
                 "d2h_bytes_per_step": 4, "last_loss": loader_e2e["last_loss"],
+                "reader_ms_per_utterance": loader_e2e["reader_ms_per_utterance"],
+                "consumer_wait_ms_per_batch": loader_e2e["consumer_wait_ms_per_batch"],
+                "launch_ms_per_batch": loader_e2e["launch_ms_per_batch"],
+                "reader_threads": loader_e2e["reader_threads"],
                 "loop": "bin/train.py's data path: distinct batches every step cut on the device "
                         "(wnb_make_train_batch) from 24 synthetic 10 s wav + feature files read by the loader thread, "
                         "uploaded once per utterance from pinned memory on a copy stream; window %d samples"

@@ -267,8 +267,10 @@ WNB_API int wnb_decode_stream(int32_t* xs, const float* h, const float* up_w, co
 
 /* ---- a14-a16, warp-tiled variant for the BASELINE shape (R 64, S 512, Q 256, Ap 32, ks 2): same contract,
  * weights as ONE stream in warp-tile order (layout documented in csrc/decode_warp.cu; built by
- * nets/wavenet.py::_decode_warp_pack). */
-WNB_API size_t wnb_decode_warp_floats(int L);
+ * nets/wavenet.py::_decode_warp_pack).  Batches of <= 74 utterances run ONE UTTERANCE PER 2-CTA CLUSTER (CL = 2):
+ * each CTA streams its half of every matrix and the two exchange their halves of every activation vector through
+ * distributed shared memory; the stream then holds the two per-CTA streams back to back. */
+WNB_API size_t wnb_decode_warp_floats(int L, int CL);
 /* debug aid: per-phase cycle counters of the free-running steps (16 int64 per CTA; NULL = off) */
 WNB_API void wnb_decode_warp_set_timing(long long* device_buf);
 WNB_API int wnb_decode_warp_supported(int Q, int Ap, int R, int S, int ks, int L);
@@ -277,9 +279,11 @@ WNB_API int wnb_decode_warp(int32_t* xs, const float* h, const float* up_w, cons
                             const float* bp1, const float* bp2, const int32_t* host_dilations, int L,
                             void* queues, const int32_t* n_samples, const float* uniforms, float* logits_out,
                             int B, int P, int max_n, int n_pad, int Th, int A, int U, int mode, uint64_t seed,
-                            int W, void* stream_handle);
-/* consumer warps (8 or 16) the launcher uses for B utterances; the stream layout depends on it */
+                            int W, int CL, void* stream_handle);
+/* consumer warps (8 or 16) / CTAs per utterance (1 or 2) the launcher uses for B utterances; the stream layout depends
+ * on both */
 WNB_API int wnb_decode_warp_plan(int B);
+WNB_API int wnb_decode_warp_cluster(int B);
 
 #ifdef __cplusplus
 }

@@ -55,11 +55,12 @@ SIGNATURES = {
     "wnb_decode": (_I, [_P] * 14 + [_P, _I] + [_P] * 4 + [_I] * 13 + [_c.c_uint64, _P]),
     "wnb_decode_stream_floats": (_c.c_size_t, [_I] * 6),
     "wnb_decode_stream": (_I, [_P] * 11 + [_P, _I] + [_P] * 4 + [_I] * 13 + [_c.c_uint64, _P]),
-    "wnb_decode_warp_floats": (_c.c_size_t, [_I]),
+    "wnb_decode_warp_floats": (_c.c_size_t, [_I, _I]),
     "wnb_decode_warp_set_timing": (None, [_P]),
     "wnb_decode_warp_supported": (_I, [_I] * 6),
-    "wnb_decode_warp": (_I, [_P] * 11 + [_P, _I] + [_P] * 4 + [_I] * 8 + [_c.c_uint64, _I, _P]),
+    "wnb_decode_warp": (_I, [_P] * 11 + [_P, _I] + [_P] * 4 + [_I] * 8 + [_c.c_uint64, _I, _I, _P]),
     "wnb_decode_warp_plan": (_I, [_I]),
+    "wnb_decode_warp_cluster": (_I, [_I]),
     "wnb_pack_weights": (_I, [_P, _I, _P, _P, _P, _P]),
     "wnb_zero": (_I, [_P, _c.c_size_t, _P]),
     "wnb_make_train_batch": (_I, [_P, _P, _P, _L, _L, _I, _L, _L] + [_P] * 5 + [_I] * 6 + [_P]),

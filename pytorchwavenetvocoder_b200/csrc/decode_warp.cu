@@ -17,6 +17,14 @@
 // Per step the floor is the shared-memory read of the 8.6 MB of weights (67k cycles) or the L2->smem
 // stream, whichever is slower; utterances sharing a CTA (NU = 2, 4) reuse both.
 // Numerics identical in kind to v1/v2: fp32 FFMA, precise expf/tanhf, first-max argmax, Philox sampling.
+//
+// CL = 2 (batches of <= 74 utterances): ONE UTTERANCE PER 2-CTA CLUSTER.  The 16 "virtual" consumer warps of the
+// single-CTA form are split over the two CTAs (8 each); each CTA streams only ITS warps' half of every matrix
+// (4.3 MB instead of 8.6 MB per step through its L2 -> shared-memory path, the measured bound), computes its half of
+// every output vector and stores it into BOTH CTAs' shared memory (st.shared::cluster, 64..512 floats per phase);
+// the consumer barriers that separate the phases become cluster-wide mbarrier phases (every virtual warp arrives on
+// both CTAs' barrier with release.cluster, waits on its own with acquire.cluster).  Same per-warp arithmetic in the
+// same order as CL = 1, hence the same logits bit for bit.
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -53,6 +61,7 @@ struct Params {
   const float* stream;
   float* queues; const int32_t* n_samples; const float* uniforms; float* logits_out;
   int B, P, max_n, n_pad, Th, A, U, mode, L, nslot, split, big;
+  long long rank_stride;   // cluster form: floats between the two CTAs' streams
   unsigned long long seed;
   int dil[kMaxL];
   long long qoff[kMaxL];
@@ -76,6 +85,52 @@ __device__ __forceinline__ void bulk_g2s(void* smem, const void* gmem, uint32_t 
 }
 template <int W>
 __device__ __forceinline__ void cons_sync_w() { asm volatile("bar.sync 1, %0;" ::"n"(W * 32) : "memory"); }
+
+// ---- 2-CTA cluster helpers (CL == 2) ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+  return r;
+}
+// Cluster-wide barrier of the consumer warps of both CTAs: two mbarriers per CTA used alternately, each expecting
+// one arrival per VIRTUAL warp (local lane 0 + the peer's lane 0 through the shared::cluster window).
+struct XSync {
+  uint32_t bar_local;     // shared::cta address of bars[0]
+  uint32_t bar_remote;    // shared::cluster address of the peer's bars[0]
+  uint32_t n;
+  __device__ __forceinline__ void sync(int lane) {
+    const uint32_t off = (n & 1u) * 8u, parity = (n >> 1) & 1u;
+    __syncwarp();
+    if (lane == 0) {
+      asm volatile("mbarrier.arrive.release.cluster.shared::cta.b64 _, [%0];" ::"r"(bar_local + off) : "memory");
+      asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_remote + off) : "memory");
+    }
+    ptx::SpinGuard guard;
+    for (;;) {
+      uint32_t ok;
+      asm volatile(
+          "{\n\t.reg .pred P;\n\t"
+          "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2;\n\t"
+          "selp.b32 %0, 1, 0, P;\n\t}\n"
+          : "=r"(ok) : "r"(bar_local + off), "r"(parity) : "memory");
+      if (ok) break;
+      if (guard.expired()) { printf("wnb200: decode cluster barrier timed out after 20 s\n"); __trap(); }
+    }
+    n++;
+  }
+};
+// store to this CTA's shared memory and (CL == 2) to the same location of the peer CTA
+template <int CL>
+__device__ __forceinline__ void st_both(float* p, float v, uint32_t peer_delta) {
+  *p = v;
+  if constexpr (CL == 2)
+    asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(ptx::smem_u32(p) + peer_delta), "f"(v) : "memory");
+}
 
 struct Ring {
   unsigned char* base; uint64_t* full; uint64_t* empty; int nslot; int split; int slot_bytes;
@@ -174,11 +229,16 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
   out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
-template <int NU, int W, bool BIG>
-__global__ void __launch_bounds__(W * 32 + 64, 1) decode_warp_kernel(const Params p) {
-  constexpr int kCons = W * 32;          // consumer threads
+template <int NU, int W, bool BIG, int CL>
+__global__ void __launch_bounds__((W / CL) * 32 + 64, 1) decode_warp_kernel(const Params p) {
+  static_assert(CL == 1 || (CL == 2 && NU == 1 && W == 16), "cluster form: one utterance per CTA pair, 16 virtual warps");
+  constexpr int WP = W / CL;             // physical consumer warps of this CTA (W = virtual warps of the utterance group)
+  constexpr int kCons = WP * 32;         // consumer threads
   constexpr int kSlotB = BIG ? 2 * kSlot : kSlot;   // bytes per ring slot
-  constexpr int KPC = BIG ? 32 : 16;     // skip / post-1 rows (k) per chunk; post-2 has 2 * KPC
+  constexpr int KPC = (BIG ? 32 : 16) * CL;   // skip / post-1 rows (k) per chunk; post-2 has 2 * KPC
+  constexpr int kSrow = kS / CL, kQrow = kQ / CL;   // columns of a skip / post-1 / post-2 row in THIS CTA's stream
+  constexpr int kLayerF = kLayerFloats - (CL - 1) * (kW1Floats / 2 + kWresFloats / 2 + kWskipFloats / 2);
+  constexpr int kJBlock = WP * 2 * (kR / W) * 32;   // floats of one W1 j-block in this CTA's stream
   constexpr int CH = kR / W;             // gate / residual channels owned by a warp (8 or 4)
   constexpr int GV = 2 * CH;             // gate values per lane: [sigmoid CH | tanh CH]
   constexpr int SV = kS / W;             // skip / post-1 outputs per warp (64 or 32)
@@ -201,16 +261,20 @@ __global__ void __launch_bounds__(W * 32 + 64, 1) decode_warp_kernel(const Param
   float* pre_s = logit + NU * kQ;           // [W warps][GV*NU]   (= 128*NU floats for any W)
   float* qtap = pre_s + 128 * NU;           // [NU][L][64]
   __shared__ int s_n[NU];
+  __shared__ __align__(8) uint64_t xbars[2];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int u0 = blockIdx.x * NU;
+  const int rank = (CL == 2) ? (int)cluster_ctarank() : 0;
+  const int vw = rank * WP + warp;          // virtual warp: owns gate channels CH*vw.., skip columns SV*vw.., logits QV*vw..
+  const int u0 = (blockIdx.x / CL) * NU;
   const int stride_xs = p.P + p.max_n;
 
   if (tid == 0) {
     for (int i = 0; i < p.nslot; i++) {
       ptx::mbar_init(&full[i], 1);
-      ptx::mbar_init(&empty[i], W);
+      ptx::mbar_init(&empty[i], WP);
     }
+    if (CL == 2) { ptx::mbar_init(&xbars[0], W); ptx::mbar_init(&xbars[1], W); }
     *ready = 0u;
     ptx::fence_barrier_init();
   }
@@ -220,40 +284,56 @@ __global__ void __launch_bounds__(W * 32 + 64, 1) decode_warp_kernel(const Param
 #pragma unroll
   for (int u = 0; u < NU; u++) nmax = max(nmax, s_n[u]);
   if (nmax == 0) return;
+  XSync xs_{0u, 0u, 0u};
+  uint32_t peer_delta = 0;
+  if constexpr (CL == 2) {
+    // both CTAs must have initialised their barriers before the first remote arrival: hardware cluster barrier, once
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    xs_.bar_local = ptx::smem_u32(&xbars[0]);
+    xs_.bar_remote = mapa_u32(xs_.bar_local, (uint32_t)(rank ^ 1));
+    peer_delta = xs_.bar_remote - xs_.bar_local;
+  }
+  // barrier between phases: the consumer warps of this CTA (CL == 1) or of both CTAs of the cluster (CL == 2)
+  auto phase_sync = [&]() {
+    if constexpr (CL == 2) xs_.sync(lane); else cons_sync_w<W>();
+  };
+  const float* my_stream = p.stream + (size_t)rank * p.rank_stride;
   const int last_pos = p.P - 1 + nmax - 1;
   Ring ring{ring_base, full, empty, p.nslot, p.split, kSlotB, 0, 0u, 0ll, ready, 0u};
 
-  if (warp == W) {
+  if (warp == WP) {
     // ================================ producer warp ================================
     if (lane == 0) {
       for (int pos = 0; pos <= last_pos; pos++) {
         const bool want = pos >= p.P - 1;
         for (int l = 0; l < L; l++) {
-          const float* base = p.stream + (size_t)l * kLayerFloats;
+          const float* base = my_stream + (size_t)l * kLayerF;
           if (BIG) {
-            ring.push(base, 65536);                                        // W1 j = 0..3
+            ring.push(base, 4 * kJBlock * 4);                              // W1 j = 0..3
           } else {
-            ring.push(base, 32768);                                        // W1 j = 0,1
-            ring.push(base + 8192, 32768);                                 // W1 j = 2,3
+            ring.push(base, 2 * kJBlock * 4);                              // W1 j = 0,1
+            ring.push(base + 2 * kJBlock, 2 * kJBlock * 4);                // W1 j = 2,3
           }
-          ring.push(base + 16384, 16384 + kB1Floats * 4);                  // W1 j = 4, then b1
-          ring.push(base + kOffWres, (kWresFloats + kB2Floats) * 4);       // W2res, then b2
+          ring.push(base + 4 * kJBlock, (kJBlock + kB1Floats) * 4);        // W1 j = 4, then b1
+          const float* wres = base + 5 * kJBlock + kB1Floats;
+          ring.push(wres, (kWresFloats / CL + kB2Floats) * 4);             // W2res, then b2
           if (want)
-            for (int c = 0; c < 64 / KPC; c++) ring.push(base + kOffWskip + c * (KPC * kS), KPC * kS * 4);
+            for (int c = 0; c < 64 / KPC; c++)
+              ring.push(wres + kWresFloats / CL + kB2Floats + c * (KPC * kSrow), KPC * kSrow * 4);
         }
         if (want) {
-          const float* pb = p.stream + (size_t)L * kLayerFloats;
+          const float* pb = my_stream + (size_t)L * kLayerF;
           ring.push(pb, kPBiasFloats * 4);                                 // bp1 | bp2
           const float* p1 = pb + kPBiasFloats;
-          for (int c = 0; c < kS / KPC; c++) ring.push(p1 + (size_t)c * (KPC * kS), KPC * kS * 4);
-          const float* p2 = p1 + kP1Floats;
-          for (int c = 0; c < kS / (2 * KPC); c++) ring.push(p2 + (size_t)c * (2 * KPC * kQ), 2 * KPC * kQ * 4);
+          for (int c = 0; c < kS / KPC; c++) ring.push(p1 + (size_t)c * (KPC * kSrow), KPC * kSrow * 4);
+          const float* p2 = p1 + kP1Floats / CL;
+          for (int c = 0; c < kS / (2 * KPC); c++) ring.push(p2 + (size_t)c * (2 * KPC * kQrow), 2 * KPC * kQrow * 4);
         }
       }
     }
     return;
   }
-  if (warp == W + 1) {
+  if (warp == WP + 1) {
     // ================================ gatekeeper warp ================================
     if (lane == 0) {
       const int per_layer_warm = (BIG ? 2 : 3) + 1, per_layer_skip = 64 / KPC;
@@ -326,12 +406,12 @@ __global__ void __launch_bounds__(W * 32 + 64, 1) decode_warp_kernel(const Param
       qtap[e] = v;
     }
     WNB_T(0);
-    cons_sync_w<W>();
+    cons_sync_w<WP>();     // (CTA-local: the prologue only touches this CTA's shared memory)
     WNB_T(1);
     // layer 0's input (the front output) goes into its queue only now, after every tap has been read
     for (int e = tid; e < NU * kR; e += kCons) {
       const int u = e >> 6, r = e & 63;
-      if (u0 + u < p.B) {
+      if (u0 + u < p.B) {   // (CL == 2: both CTAs hold the same values and both write them)
         float* q0 = p.queues + (size_t)(u0 + u) * p.q_per_utt + p.qoff[0];
         __stcg(q0 + (size_t)(pos & (p.dil[0] - 1)) * kR + r, cur[e]);
       }
@@ -355,7 +435,7 @@ __global__ void __launch_bounds__(W * 32 + 64, 1) decode_warp_kernel(const Param
         if (j == 0 || (!BIG && j == 2) || j == 4) chunk = ring.acquire();
         // [j][warp][group g][lane][4]: consecutive lanes read consecutive 16 B -> conflict-free LDS.128
         const int jj = (j == 4) ? 0 : (BIG ? j : (j & 1));   // index of this j inside its chunk
-        const float4* wp = reinterpret_cast<const float4*>(chunk + (size_t)(jj * W + warp) * (GV * 32)) + lane;
+        const float4* wp = reinterpret_cast<const float4*>(chunk + (size_t)(jj * WP + warp) * (GV * 32)) + lane;
         float4 wv[GV / 4];
 #pragma unroll
         for (int g = 0; g < GV / 4; g++) wv[g] = wp[g * 32];
@@ -371,9 +451,9 @@ __global__ void __launch_bounds__(W * 32 + 64, 1) decode_warp_kernel(const Param
           }
         }
         if (j == 4) {   // b1 sits right behind the j = 4 weights in this chunk
-          const int c = warp * CH + (lane % CH);
-          gate_bs = chunk[4096 + c];
-          gate_bt = chunk[4096 + 64 + c];
+          const int c = vw * CH + (lane % CH);
+          gate_bs = chunk[kJBlock + c];
+          gate_bt = chunk[kJBlock + 64 + c];
         }
         if ((!BIG && j == 1) || j == 3 || j == 4) ring.release();
       }
@@ -381,13 +461,13 @@ __global__ void __launch_bounds__(W * 32 + 64, 1) decode_warp_kernel(const Param
       warp_reduce_scatter<NU * GV>(acc, my_pre, lane);
       __syncwarp();
       if (lane < CH * NU) {
-        const int u = lane / CH, cc = lane % CH, c = warp * CH + cc;
+        const int u = lane / CH, cc = lane % CH, c = vw * CH + cc;
         const float a = my_pre[u * GV + cc] + gate_bs;
         const float g = my_pre[u * GV + CH + cc] + gate_bt;
-        zs[u * kR + c] = sigmoidf_(a) * tanhf(g);
+        st_both<CL>(&zs[u * kR + c], sigmoidf_(a) * tanhf(g), peer_delta);
       }
       WNB_T(3);
-      cons_sync_w<W>();
+      phase_sync();
       WNB_T(4);
       // ---------------- phase B: residual 1x1 (split K) ----------------
       float skip_b[SL];
@@ -398,7 +478,7 @@ __global__ void __launch_bounds__(W * 32 + 64, 1) decode_warp_kernel(const Param
         const float* rc = ring.acquire();
 #pragma unroll
         for (int j = 0; j < 2; j++) {
-          const float4* wp = reinterpret_cast<const float4*>(rc + (size_t)(j * W + warp) * (CH * 32)) + lane;
+          const float4* wp = reinterpret_cast<const float4*>(rc + (size_t)(j * WP + warp) * (CH * 32)) + lane;
           float4 wv[CH / 4];
 #pragma unroll
           for (int g = 0; g < CH / 4; g++) wv[g] = wp[g * 32];
@@ -414,16 +494,16 @@ __global__ void __launch_bounds__(W * 32 + 64, 1) decode_warp_kernel(const Param
           }
         }
         // b2 = [res 64 | skip 512] sits right behind the res weights in this chunk
-        const float res_b = rc[kWresFloats + warp * CH + (lane % CH)];
+        const float res_b = rc[kWresFloats / CL + vw * CH + (lane % CH)];
 #pragma unroll
-        for (int e = 0; e < SL; e++) skip_b[e] = rc[kWresFloats + kR + warp * SV + lane * SL + e];
+        for (int e = 0; e < SL; e++) skip_b[e] = rc[kWresFloats / CL + kR + vw * SV + lane * SL + e];
         ring.release();
         warp_reduce_scatter<NU * CH>(racc, my_pre, lane);
         __syncwarp();
         if (lane < CH * NU) {
-          const int u = lane / CH, cc = lane % CH, c = warp * CH + cc;
+          const int u = lane / CH, cc = lane % CH, c = vw * CH + cc;
           const float v = my_pre[u * CH + cc] + res_b + cur[u * kR + c];
-          cur[u * kR + c] = v;
+          st_both<CL>(&cur[u * kR + c], v, peer_delta);
           if (l + 1 < L && u0 + u < p.B) {   // input of layer l+1 at time `pos` -> its dilation queue
             float* q = p.queues + (size_t)(u0 + u) * p.q_per_utt + p.qoff[l + 1];
             __stcg(q + (size_t)(pos & (p.dil[l + 1] - 1)) * kR + c, v);   // dilations are powers of two
@@ -440,7 +520,7 @@ __global__ void __launch_bounds__(W * 32 + 64, 1) decode_warp_kernel(const Param
           for (int e = 0; e < SL; e++) s[u][e] = 0.f;
 #pragma unroll 1
         for (int c4 = 0; c4 < 64 / KPC; c4++) {
-          const float* sc = ring.acquire() + warp * SV + lane * SL;
+          const float* sc = ring.acquire() + warp * SV + lane * SL;   // (column inside this CTA's kSrow-wide rows)
 #pragma unroll
           for (int k4 = 0; k4 < KPC; k4 += 4) {
             float4 zv[NU];
@@ -450,10 +530,10 @@ __global__ void __launch_bounds__(W * 32 + 64, 1) decode_warp_kernel(const Param
             for (int kk = 0; kk < 4; kk++) {
               float wv[SL];
               if constexpr (SL == 2) {
-                const float2 t2 = *reinterpret_cast<const float2*>(sc + (size_t)(k4 + kk) * kS);
+                const float2 t2 = *reinterpret_cast<const float2*>(sc + (size_t)(k4 + kk) * kSrow);
                 wv[0] = t2.x; wv[1] = t2.y;
               } else {
-                wv[0] = sc[(size_t)(k4 + kk) * kS];
+                wv[0] = sc[(size_t)(k4 + kk) * kSrow];
               }
 #pragma unroll
               for (int u = 0; u < NU; u++) {
@@ -476,7 +556,7 @@ __global__ void __launch_bounds__(W * 32 + 64, 1) decode_warp_kernel(const Param
         }
       }
       WNB_T(6);
-      cons_sync_w<W>();
+      phase_sync();
       WNB_T(7);
     }
 
@@ -485,16 +565,17 @@ __global__ void __launch_bounds__(W * 32 + 64, 1) decode_warp_kernel(const Param
 #pragma unroll
       for (int u = 0; u < NU; u++)
 #pragma unroll
-        for (int e = 0; e < SL; e++) skipx[u * kS + warp * SV + lane * SL + e] = fmaxf(skip_tot[u][e], 0.f);
+        for (int e = 0; e < SL; e++)
+          st_both<CL>(&skipx[u * kS + vw * SV + lane * SL + e], fmaxf(skip_tot[u][e], 0.f), peer_delta);
       float post_b1[SL], post_b2;
       {
         const float* pbias = ring.acquire();   // [bp1 512 | bp2 256]
 #pragma unroll
-        for (int e = 0; e < SL; e++) post_b1[e] = pbias[warp * SV + lane * SL + e];
-        post_b2 = pbias[kS + warp * QV + (lane % QV)];
+        for (int e = 0; e < SL; e++) post_b1[e] = pbias[vw * SV + lane * SL + e];
+        post_b2 = pbias[kS + vw * QV + (lane % QV)];
         ring.release();
       }
-      cons_sync_w<W>();
+      phase_sync();
       {
         float s[NU][SL];
 #pragma unroll
@@ -513,10 +594,10 @@ __global__ void __launch_bounds__(W * 32 + 64, 1) decode_warp_kernel(const Param
             for (int kk = 0; kk < 4; kk++) {
               float wv[SL];
               if constexpr (SL == 2) {
-                const float2 t2 = *reinterpret_cast<const float2*>(pc + (size_t)(k4 + kk) * kS);
+                const float2 t2 = *reinterpret_cast<const float2*>(pc + (size_t)(k4 + kk) * kSrow);
                 wv[0] = t2.x; wv[1] = t2.y;
               } else {
-                wv[0] = pc[(size_t)(k4 + kk) * kS];
+                wv[0] = pc[(size_t)(k4 + kk) * kSrow];
               }
 #pragma unroll
               for (int u = 0; u < NU; u++) {
@@ -532,10 +613,11 @@ __global__ void __launch_bounds__(W * 32 + 64, 1) decode_warp_kernel(const Param
         for (int e = 0; e < SL; e++) {
           const float bv = post_b1[e];
 #pragma unroll
-          for (int u = 0; u < NU; u++) h1[u * kS + warp * SV + lane * SL + e] = fmaxf(s[u][e] + bv, 0.f);
+          for (int u = 0; u < NU; u++)
+            st_both<CL>(&h1[u * kS + vw * SV + lane * SL + e], fmaxf(s[u][e] + bv, 0.f), peer_delta);
         }
       }
-      cons_sync_w<W>();
+      phase_sync();
       WNB_T(8);
       const int i = pos - (p.P - 1);
       {
@@ -555,7 +637,7 @@ __global__ void __launch_bounds__(W * 32 + 64, 1) decode_warp_kernel(const Param
 #pragma unroll
             for (int kk = 0; kk < 4; kk++) {
               if (KS == 1 || (kk & 1) == ksel) {
-                const float wv = pc[(size_t)(k4 + kk) * kQ];
+                const float wv = pc[(size_t)(k4 + kk) * kQrow];
 #pragma unroll
                 for (int u = 0; u < NU; u++) {
                   const float x = kk == 0 ? xv[u].x : kk == 1 ? xv[u].y : kk == 2 ? xv[u].z : xv[u].w;
@@ -573,13 +655,13 @@ __global__ void __launch_bounds__(W * 32 + 64, 1) decode_warp_kernel(const Param
           if (KS == 2) v += __shfl_xor_sync(0xffffffffu, v, 16);
           v += bv;
           if (ksel == 0) {
-            logit[u * kQ + warp * QV + lo] = v;
+            st_both<CL>(&logit[u * kQ + vw * QV + lo], v, peer_delta);
             if (p.logits_out && u0 + u < p.B && i < s_n[u])
-              p.logits_out[((size_t)(u0 + u) * p.max_n + i) * kQ + warp * QV + lo] = v;
+              p.logits_out[((size_t)(u0 + u) * p.max_n + i) * kQ + vw * QV + lo] = v;
           }
         }
       }
-      cons_sync_w<W>();
+      phase_sync();
       WNB_T(9);
       // ---------------- pick: warp u handles utterance u ----------------
       if (warp < NU) {
@@ -630,12 +712,15 @@ __global__ void __launch_bounds__(W * 32 + 64, 1) decode_warp_kernel(const Param
           for (int o = 16; o > 0; o >>= 1) cand = min(cand, __shfl_xor_sync(0xffffffffu, cand, o));
           pick = (cand == 0x7fffffff) ? kQ - 1 : cand;
         }
+        // (CL == 2: both CTAs hold the same 256 logits and make the same pick; each writes it -- same value -- so
+        //  that its own next prologue reads what it wrote, no cross-CTA dependency on global memory)
         if (lane == 0 && u0 + u < p.B && i < s_n[u]) p.xs[(size_t)(u0 + u) * stride_xs + pos + 1] = pick;
       }
-      cons_sync_w<W>();
+      cons_sync_w<WP>();
       WNB_T(10);
     }
   }
+  if constexpr (CL == 2) phase_sync();   // no CTA leaves while its peer may still store into its shared memory
   if (p.timing && tid == 0) {
     for (int i = 0; i < 12; i++) p.timing[(size_t)blockIdx.x * 16 + i] = tacc[i];
     p.timing[(size_t)blockIdx.x * 16 + 12] = ring.waited;
@@ -644,22 +729,28 @@ __global__ void __launch_bounds__(W * 32 + 64, 1) decode_warp_kernel(const Param
 
 }  // namespace dw
 
-// utterances per CTA and consumer warps for a batch of B utterances (shared by the packer and the launcher)
-static void decode_warp_plan(int B, int* NU, int* W) {
+// utterances per CTA, consumer warps and cluster size for a batch of B utterances (shared by the packer and the
+// launcher).  Up to 74 utterances (half the SMs): one utterance per 2-CTA cluster, so that 2 B SMs stream the weights.
+static void decode_warp_plan(int B, int* NU, int* W, int* CL) {
   int nu = 1;
   if (B > 148 * 2) nu = 4; else if (B > 148) nu = 2;
   *NU = nu;
   *W = (nu == 4) ? 8 : 16;   // 16 warps hide the smem->FMA latency; NU = 4 needs the registers of the 8-warp form
+  static const int cl_on = [] { const char* e = getenv("WNB_DECODE_CL"); return (e && e[0] == '1') ? 0 : 1; }();
+  *CL = (cl_on && B <= 74) ? 2 : 1;
 }
 
-int decode_warp_launch(dw::Params& p, int W_packed, cudaStream_t st) {
+int decode_warp_launch(dw::Params& p, int W_packed, int CL_packed, cudaStream_t st) {
   using namespace dw;
-  int NU, W;
-  decode_warp_plan(p.B, &NU, &W);
-  if (W != W_packed) {
-    set_error("decode_warp: stream packed for %d consumer warps but the plan for B=%d is %d", W_packed, p.B, W);
+  int NU, W, CL;
+  decode_warp_plan(p.B, &NU, &W, &CL);
+  if (W != W_packed || CL != CL_packed) {
+    set_error("decode_warp: stream packed for %d consumer warps / cluster %d but the plan for B=%d is %d / %d", W_packed,
+              CL_packed, p.B, W, CL);
     return WNB_ERR_INVALID;
   }
+  p.rank_stride = (long long)((size_t)p.L * (kLayerFloats - (CL - 1) * (kW1Floats / 2 + kWresFloats / 2 + kWskipFloats / 2)) +
+                              kPBiasFloats + (kP1Floats + kP2Floats) / CL);
   const size_t work = ((size_t)NU * (kR * 2 + kAp + 2 * kS + kQ + (size_t)p.L * kR) + 128 * NU) * sizeof(float);
   const long avail = 227L * 1024 - 256 - (long)work - 16 * 16;
   // three 64 KB slots (half as many mbarrier round trips per step) when they fit, else up to six 32 KB slots
@@ -677,21 +768,33 @@ int decode_warp_launch(dw::Params& p, int W_packed, cudaStream_t st) {
     p.split = sp;
   }
   const size_t smem = (size_t)nslot * (big ? 2 * kSlot : kSlot) + 2 * nslot * sizeof(uint64_t) + 16 + work;
-  const int grid = cdiv(p.B, NU);
-#define WNB_LAUNCH_DW(N, WW)                                                                                             \
-  do {                                                                                                                   \
-    if (big) {                                                                                                           \
-      WNB_CUDA(cudaFuncSetAttribute(decode_warp_kernel<N, WW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-      decode_warp_kernel<N, WW, true><<<grid, WW * 32 + 64, smem, st>>>(p);                                              \
-    } else {                                                                                                             \
-      WNB_CUDA(cudaFuncSetAttribute(decode_warp_kernel<N, WW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-      decode_warp_kernel<N, WW, false><<<grid, WW * 32 + 64, smem, st>>>(p);                                             \
-    }                                                                                                                    \
-  } while (0)
-  if (NU == 4) WNB_LAUNCH_DW(4, 8);
-  else if (NU == 2) WNB_LAUNCH_DW(2, 16);
-  else WNB_LAUNCH_DW(1, 16);
-#undef WNB_LAUNCH_DW
+  const int grid = cdiv(p.B, NU) * CL;
+  auto launch = [&](auto kernel, int threads) -> cudaError_t {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)threads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, p);
+  };
+  cudaError_t le;
+  if (CL == 2) le = big ? launch(decode_warp_kernel<1, 16, true, 2>, 8 * 32 + 64) : launch(decode_warp_kernel<1, 16, false, 2>, 8 * 32 + 64);
+  else if (NU == 4) le = big ? launch(decode_warp_kernel<4, 8, true, 1>, 8 * 32 + 64) : launch(decode_warp_kernel<4, 8, false, 1>, 8 * 32 + 64);
+  else if (NU == 2) le = big ? launch(decode_warp_kernel<2, 16, true, 1>, 16 * 32 + 64) : launch(decode_warp_kernel<2, 16, false, 1>, 16 * 32 + 64);
+  else le = big ? launch(decode_warp_kernel<1, 16, true, 1>, 16 * 32 + 64) : launch(decode_warp_kernel<1, 16, false, 1>, 16 * 32 + 64);
+  if (le != cudaSuccess) {
+    set_error("decode_warp: launch failed: %s", cudaGetErrorString(le));
+    return WNB_ERR_CUDA;
+  }
   WNB_CHECK_LAUNCH("decode_warp");
   return WNB_OK;
 }
@@ -702,9 +805,14 @@ using namespace wnb;
 
 extern "C" {
 
-// floats of the warp-tiled decode stream (layout: csrc/decode_warp.cu header) for L layers
-WNB_API size_t wnb_decode_warp_floats(int L) {
-  return (size_t)L * dw::kLayerFloats + dw::kPBiasFloats + dw::kP1Floats + dw::kP2Floats;
+// floats of the warp-tiled decode stream (layout: csrc/decode_warp.cu header) for L layers and cluster size CL (1 or 2:
+// CL per-CTA streams back to back, each with the full biases and 1/CL of every matrix)
+WNB_API size_t wnb_decode_warp_floats(int L, int CL) {
+  using namespace dw;
+  if (CL != 2) CL = 1;
+  const size_t per_rank = (size_t)L * (kLayerFloats - (CL - 1) * (kW1Floats / 2 + kWresFloats / 2 + kWskipFloats / 2)) +
+                          kPBiasFloats + (kP1Floats + kP2Floats) / CL;
+  return per_rank * CL;
 }
 
 // debug: device buffer (16 int64 per CTA) that the next wnb_decode_warp launches fill with per-phase cycle
@@ -720,16 +828,22 @@ WNB_API int wnb_decode_warp_supported(int Q, int Ap, int R, int S, int ks, int L
 
 // consumer warps (8 or 16) the launcher will use for B utterances: the stream must be packed accordingly
 WNB_API int wnb_decode_warp_plan(int B) {
-  int NU, W;
-  decode_warp_plan(B, &NU, &W);
+  int NU, W, CL;
+  decode_warp_plan(B, &NU, &W, &CL);
   return W;
+}
+// CTAs per utterance (cluster size, 1 or 2) the launcher will use for B utterances
+WNB_API int wnb_decode_warp_cluster(int B) {
+  int NU, W, CL;
+  decode_warp_plan(B, &NU, &W, &CL);
+  return CL;
 }
 
 WNB_API int wnb_decode_warp(int32_t* xs, const float* h, const float* up_w, const float* up_b, const float* wf,
                             const float* bf, const float* stream, const float* b1, const float* b2, const float* bp1,
                             const float* bp2, const int32_t* host_dilations, int L, void* queues,
                             const int32_t* n_samples, const float* uniforms, float* logits_out, int B, int P,
-                            int max_n, int n_pad, int Th, int A, int U, int mode, uint64_t seed, int W,
+                            int max_n, int n_pad, int Th, int A, int U, int mode, uint64_t seed, int W, int CL,
                             void* stream_handle) {
   WNB_REQUIRE(B > 0 && P >= 1 && max_n >= 1 && Th >= 1 && A > 0 && A <= dw::kAp && U >= 0 && L >= 1 && L <= dw::kMaxL,
               "decode_warp: bad shape");
@@ -753,7 +867,7 @@ WNB_API int wnb_decode_warp(int32_t* xs, const float* h, const float* up_w, cons
     off += (long long)host_dilations[l] * dw::kR;
   }
   p.q_per_utt = off;
-  int rc = decode_warp_launch(p, W, (cudaStream_t)stream_handle);
+  int rc = decode_warp_launch(p, W, CL, (cudaStream_t)stream_handle);
   if (rc == WNB_ERR_UNSUPPORTED) set_error("decode_warp: not enough shared memory for this depth");
   return rc;
 }

@@ -82,8 +82,8 @@ WNB_API int wnb_make_train_batch(const float* wave, const void* feat, const int3
   const int work = (T + 1 > D * Tf) ? T + 1 : D * Tf;
   dim3 grid((unsigned)((work + 255) / 256 < 148 ? (work + 255) / 256 : 148), (unsigned)B);
   make_train_batch_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(wave, feat, frame_of_sample, s0, hop, U, cap_s, cap_f, mean,
-                                                                 scale, x, t, h, B, T, Tf, D, feat_f64, (float)mu,
-                                                                 log(1.0 + (double)mu));
+                                                                 scale, x, t, h, B, T, Tf, D, feat_f64, (float)(mu - 1),
+                                                                 log(1.0 + (double)(mu - 1)));   // wavenet.py:27 mu = mu - 1
   WNB_CHECK_LAUNCH("make_train_batch");
   return WNB_OK;
 }

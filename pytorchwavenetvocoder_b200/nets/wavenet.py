@@ -768,25 +768,36 @@ class WaveNet(nn.Module):
         parts += [w["wp1d"].reshape(-1), w["wp2d"].reshape(-1)]
         return torch.cat(parts).contiguous()
 
-    def _decode_warp_pack(self, W):
-        """Warp-tile ordered stream for wnb_decode_warp with W consumer warps (layout: csrc/decode_warp.cu)."""
+    def _decode_warp_pack(self, W, CL=1):
+        """Warp-tile ordered stream for wnb_decode_warp with W (virtual) consumer warps (layout: csrc/decode_warp.cu).
+        CL = 2: one stream per CTA of the cluster, back to back -- CTA r gets the tiles of warps r*W/2 .. (r+1)*W/2 - 1
+        (= gate / residual channels, skip / post columns of its half) and the full bias vectors."""
         with torch.no_grad():
             wf, bf, W1, b1, W2, b2, Wp1, bp1, Wp2, bp2 = [t.detach().float() for t in self._pack()]
             L = W1.size(0)
             CH = 64 // W                     # gate / residual channels per warp
+            WP = W // CL
             # W1 (L,128,160)[o][k] -> [j][w][g][lane][4]: k = 32j+lane; a lane's 2*CH values (index 4g+e) are
             # (sigmoid rows CH*w.., tanh rows CH*w..); consecutive lanes are 16 B apart (conflict-free LDS.128)
             t1 = W1.reshape(L, 2, W, CH, 5, 32).permute(0, 4, 2, 1, 3, 5)          # [L][j][w][br][cc][lane]
-            t1 = t1.reshape(L, 5, W, 2 * CH // 4, 4, 32).permute(0, 1, 2, 3, 5, 4).reshape(L, -1)
+            t1 = t1.reshape(L, 5, W, 2 * CH // 4, 4, 32).permute(0, 1, 2, 3, 5, 4)  # [L][j][w][g][lane][4]
             # W2 res rows (L,64,64)[o][k] -> [j][w][g][lane][4]: k = 32j+lane, o = CH*w + 4g + e
             tr = W2[:, :64, :].reshape(L, W, CH, 2, 32).permute(0, 3, 1, 2, 4)     # [L][j][w][cc][lane]
-            tr = tr.reshape(L, 2, W, CH // 4, 4, 32).permute(0, 1, 2, 3, 5, 4).reshape(L, -1)
+            tr = tr.reshape(L, 2, W, CH // 4, 4, 32).permute(0, 1, 2, 3, 5, 4)      # [L][j][w][g][lane][4]
             # W2 skip rows (L,512,64)[o][k] -> [k][512]
-            ts = W2[:, 64:, :].transpose(1, 2).reshape(L, -1)
-            # biases ride in the stream right behind their matrices: [W1 | b1 | W2res | b2 | W2skip] per layer,
-            # then [bp1 | bp2 | Wp1^T | Wp2^T]
-            per_layer = torch.cat([t1, b1, tr, b2, ts], 1).reshape(-1)
-            return torch.cat([per_layer, bp1, bp2, Wp1.t().reshape(-1), Wp2.t().reshape(-1)]).contiguous()
+            ts = W2[:, 64:, :].transpose(1, 2)                                      # [L][64 k][512]
+            p1, p2 = Wp1.t(), Wp2.t()                                              # [512 k][512], [512 k][256]
+            S, Q = p1.size(1), p2.size(1)
+            parts = []
+            for r in range(CL):
+                ws = slice(r * WP, (r + 1) * WP)
+                # biases ride in the stream right behind their matrices: [W1 | b1 | W2res | b2 | W2skip] per layer,
+                # then [bp1 | bp2 | Wp1^T | Wp2^T]
+                per_layer = torch.cat([t1[:, :, ws].reshape(L, -1), b1, tr[:, :, ws].reshape(L, -1), b2,
+                                       ts[:, :, r * S // CL:(r + 1) * S // CL].reshape(L, -1)], 1).reshape(-1)
+                parts += [per_layer, bp1, bp2, p1[:, r * S // CL:(r + 1) * S // CL].reshape(-1),
+                          p2[:, r * Q // CL:(r + 1) * Q // CL].reshape(-1)]
+            return torch.cat(parts).contiguous()
 
     def _decode(self, x, h, n_samples_list, mode, uniforms=None, return_logits=False, seed=None, kernel="auto"):
         lib = _lib.load()
@@ -826,13 +837,13 @@ class WaveNet(nn.Module):
         rc = -3
         self.last_decode_kernel = None
         if kernel in ("auto", "warp") and lib.wnb_decode_warp_supported(Q, Ap, R, S, ks, L):
-            Wc = lib.wnb_decode_warp_plan(B)
-            wstream = self._decode_warp_pack(Wc)
-            assert wstream.numel() == lib.wnb_decode_warp_floats(L)
+            Wc, CLc = lib.wnb_decode_warp_plan(B), lib.wnb_decode_warp_cluster(B)
+            wstream = self._decode_warp_pack(Wc, CLc)
+            assert wstream.numel() == lib.wnb_decode_warp_floats(L, CLc)
             rc = lib.wnb_decode_warp(ptr(xs), ptr(h), ptr(upw), ptr(upb), ptr(w["wf"]), ptr(w["bf"]), ptr(wstream),
                                      ptr(w["b1"]), ptr(w["b2"]), ptr(w["bp1"]), ptr(w["bp2"]), dil, L, ptr(queues),
                                      ptr(nsm), ptr(uni), ptr(lg), B, P, max_n, n_pad, Th, A, U, cmode, cseed, Wc,
-                                     stream())
+                                     CLc, stream())
             if rc != -3 or kernel == "warp":
                 check(rc, "decode_warp")
             if rc == 0:

@@ -57,7 +57,7 @@ class DeviceTrainGenerator(object):
 
     def __init__(self, wav_list, feat_list, receptive_field, batch_length, batch_size=1, feature_type="world",
                  n_quantize=256, mean=None, scale=None, shuffle=True, upsampling_factor=80, use_upsampling_layer=True,
-                 use_speaker_code=False, device=None, ring_windows=6, prefetch=8):
+                 use_speaker_code=False, device=None, ring_windows=6, prefetch=4, readers=3):
         if batch_length is None:
             raise ValueError("DeviceTrainGenerator covers the mini-batch modes; use train_generator for utterance batches")
         self.lib = _lib.load()
@@ -95,28 +95,59 @@ class DeviceTrainGenerator(object):
         self.copy_stream = torch.cuda.Stream(device=self.dev)
         self.last_batch_event = None
         self.utts = []                                    # (start_s, n, start_f, nf) of the utterances still in the ring
-        self.queue = Queue(prefetch)
-        self.thread = threading.Thread(target=self._reader, daemon=True)
-        self.thread.start()
+        # reader threads: thread k reads utterances k, k + n, ... of the (shuffled, epoch after epoch) sequence into its own
+        # queue; the consumer pops the queues round-robin, so the order is the reference's
+        self.n_readers = max(1, int(readers))
+        self._plan_lock = threading.Lock()
+        self._order = []                                  # flattened utterance sequence planned so far (file pairs)
+        self._lists = (list(self.wav_list), list(self.feat_list))
+        self.queues = [Queue(prefetch) for _ in range(self.n_readers)]
+        self._next_q = 0
+        self.stats = {"reader_s": 0.0, "utts": 0, "wait_s": 0.0, "batches": 0}
+        self.threads = [threading.Thread(target=self._reader, args=(k,), daemon=True) for k in range(self.n_readers)]
+        for th in self.threads:
+            th.start()
 
-    # ------------------------------------------------------------------ loader thread: file I/O only
-    def _reader(self):
-        wl, fl = self.wav_list, self.feat_list
-        try:
-            if self.shuffle:
-                idx = np.random.permutation(len(wl))
-                wl, fl = [wl[i] for i in idx], [fl[i] for i in idx]
-            while True:
-                for w, f in zip(wl, fl):
-                    x, h = load_pair_frames(w, f, self.feature_type, self.U, self.use_up, self.use_spk)
-                    xp = torch.from_numpy(x).pin_memory()
-                    hp = torch.from_numpy(h).pin_memory()
-                    self.queue.put((xp, hp))
+    # ------------------------------------------------------------------ reader threads: file I/O only
+    def _utterance(self, pos):
+        """file pair at position `pos` of the infinite sequence (reference train.py:95-98, 308-312: one permutation of the
+        current lists at the start and after every epoch, drawn from the global numpy RNG)"""
+        with self._plan_lock:
+            while pos >= len(self._order):
+                wl, fl = self._lists
                 if self.shuffle:
                     idx = np.random.permutation(len(wl))
                     wl, fl = [wl[i] for i in idx], [fl[i] for i in idx]
+                    self._lists = (wl, fl)
+                self._order.extend(zip(wl, fl))
+            return self._order[pos]
+
+    def _reader(self, k):
+        import time
+        try:
+            pos = k
+            while True:
+                w, f = self._utterance(pos)
+                t0 = time.time()
+                x, h = load_pair_frames(w, f, self.feature_type, self.U, self.use_up, self.use_spk)
+                xp = torch.from_numpy(x).pin_memory()
+                hp = torch.from_numpy(h).pin_memory()
+                self.stats["reader_s"] += time.time() - t0
+                self.stats["utts"] += 1
+                self.queues[k].put((xp, hp))
+                pos += self.n_readers
         except BaseException as e:     # noqa: BLE001 -- surface reader failures in the consumer
-            self.queue.put(e)
+            self.queues[k].put(e)
+
+    def _pop(self, block=True):
+        q = self.queues[self._next_q]
+        if not block and q.empty():
+            return None
+        item = q.get()
+        if isinstance(item, BaseException):
+            raise item
+        self._next_q = (self._next_q + 1) % self.n_readers
+        return item
 
     # ------------------------------------------------------------------ ring appends (async H2D on the copy stream)
     def _ring_copy(self, ring, pos, cap, src):
@@ -168,11 +199,13 @@ class DeviceTrainGenerator(object):
     def next(self):
         B, hop = self.B, self.hop
         # the reference cuts a window whenever the buffer is long enough; B consecutive windows make a batch
+        import time
+        t0 = time.time()
         while self.tail_s - (self.head_s + (B - 1) * hop) < self.need:
-            item = self.queue.get()
-            if isinstance(item, BaseException):
-                raise item
-            self._append(*item)
+            self._append(*self._pop())
+        self.stats["wait_s"] += time.time() - t0
+        self.stats["batches"] += 1
+        t1 = time.time()
         cur = torch.cuda.current_stream(self.dev)
         cur.wait_event(self.append_event)
         x = torch.empty(B, self.T, dtype=torch.int64, device=self.dev)
@@ -189,12 +222,12 @@ class DeviceTrainGenerator(object):
         self.head_s += hop * B
         # read ahead: whatever the reader thread has ready goes to the device now (copy stream, behind this batch's
         # kernel), so the next batches find their utterances resident and the copies overlap the training step
-        while (not self.queue.empty() and self.tail_s - self.head_s < self.cap_s // 2
-               and self.tail_s - self.head_s < 3 * (self.need + (B - 1) * hop)):
-            item = self.queue.get()
-            if isinstance(item, BaseException):
-                raise item
+        while self.tail_s - self.head_s < min(self.cap_s // 2, 3 * (self.need + (B - 1) * hop)):
+            item = self._pop(block=False)
+            if item is None:
+                break
             self._append(*item)
+        self.stats["launch_s"] = self.stats.get("launch_s", 0.0) + time.time() - t1
         return (x, h), t
 
     __next__ = next

@@ -88,3 +88,42 @@ def test_pack_and_unpack_tables(cfg_t):
     # views are 16-byte aligned slices in parameters() order
     offs = [plan.grad_off[n] for n in plan.grad_names]
     assert offs == sorted(offs) and all(o % 4 == 0 for o in offs)
+
+
+def test_decode_cluster_stream_is_a_split_of_the_single_cta_stream():
+    """_decode_warp_pack(W, CL=2): CTA r's stream = the tiles of warps r*W/2.. of every matrix + the full biases; sizes
+    agree with wnb_decode_warp_floats (csrc/decode_warp.cu)."""
+    from pytorchwavenetvocoder_b200 import _lib
+    lib = _lib.load()
+    torch.manual_seed(1)
+    net = WaveNet(256, 28, 64, 512, 3, 2, 2, 80)
+    with torch.no_grad():
+        for p in net.parameters():
+            p.copy_(torch.randn_like(p))
+    L, W = 6, 16
+    one = net._decode_warp_pack(W, 1)
+    two = net._decode_warp_pack(W, 2)
+    assert one.numel() == lib.wnb_decode_warp_floats(L, 1) and two.numel() == lib.wnb_decode_warp_floats(L, 2)
+    half = two.numel() // 2
+    jb1, jb2 = 4096, 2048                    # floats of one W1 j-block: 16 warps / 8 warps
+    lay1 = 5 * jb1 + 128 + 4096 + 576 + 64 * 512
+    lay2 = 5 * jb2 + 128 + 2048 + 576 + 64 * 256
+    for r in range(2):
+        st = two[r * half:(r + 1) * half]
+        for l in range(L):
+            a, b = one[l * lay1:(l + 1) * lay1], st[l * lay2:(l + 1) * lay2]
+            for j in range(5):               # W1: [j][warp][...]: this CTA's 8 warps are contiguous inside a j-block
+                assert torch.equal(b[j * jb2:(j + 1) * jb2], a[j * jb1 + r * jb2:j * jb1 + (r + 1) * jb2])
+            oa, ob = 5 * jb1, 5 * jb2
+            assert torch.equal(b[ob:ob + 128], a[oa:oa + 128])                       # b1 (full)
+            oa, ob = oa + 128, ob + 128
+            for j in range(2):               # W2res: [j][warp][g][lane][4], 128 floats per warp
+                assert torch.equal(b[ob + j * 1024:ob + (j + 1) * 1024], a[oa + j * 2048 + r * 1024:oa + j * 2048 + (r + 1) * 1024])
+            oa, ob = oa + 4096, ob + 2048
+            assert torch.equal(b[ob:ob + 576], a[oa:oa + 576])                       # b2 (full)
+            oa, ob = oa + 576, ob + 576
+            assert torch.equal(b[ob:].view(64, 256), a[oa:].view(64, 512)[:, r * 256:(r + 1) * 256])
+        pa, pb = one[L * lay1:], st[L * lay2:]
+        assert torch.equal(pb[:768], pa[:768])                                       # bp1 | bp2
+        assert torch.equal(pb[768:768 + 512 * 256].view(512, 256), pa[768:768 + 512 * 512].view(512, 512)[:, r * 256:(r + 1) * 256])
+        assert torch.equal(pb[768 + 512 * 256:].view(512, 128), pa[768 + 512 * 512:].view(512, 256)[:, r * 128:(r + 1) * 128])
