@@ -314,6 +314,24 @@ def run_ours(args):
                               "reader_threads": gen.n_readers}
             finally:
                 shutil.rmtree(tmpd, ignore_errors=True)
+        fp32_line = None
+        if args.fp32_line and args.math == "tf32" and world == 1:
+            # the parity mode beside the tensor-core number: same model, same batch, math_mode = "fp32" (FFMA kernels,
+            # logits <= 1e-4 / gradients <= 1e-3 vs the reference), 1 warm-up + 2 timed steps
+            net.math_mode = "fp32"
+            step(xd, hd, td)
+            barrier()
+            ef0, ef1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ef0.record()
+            for _ in range(2):
+                step(xd, hd, td)
+            ef1.record()
+            barrier()
+            net.math_mode = args.math
+            msf = ef0.elapsed_time(ef1) / 2
+            fp32_line = {"ms_per_step": msf, "value": BATCH * BATCH_LENGTH / (msf * 1e-3), "unit": "samples/s",
+                         "dtype": "f32", "steps": 2,
+                         "note": "math_mode=fp32: every contraction in fp32 FFMA (the parity path of the tests)"}
         if dist is not None:
             tt = torch.tensor([ms, ms_e2e, loader_e2e["ms"] if loader_e2e else 0.0], device=dev, dtype=torch.float64)
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -380,6 +398,8 @@ def run_ours(args):
             "clocks": clocks,
             "roofline": roof,
         }
+        if fp32_line:
+            out["fp32_parity_mode"] = fp32_line
         if loader_e2e:
             out["e2e_data_loader"] = {
                 "value": samples / (loader_e2e["ms"] / args.steps * 1e-3), "unit": "samples/s",
@@ -435,18 +455,20 @@ def run_decode(args, dev, rank, world, dist):
     x_host = torch.full((args.decode_utts, 1), cfg.n_quantize // 2, dtype=torch.int64).pin_memory()
     nl = [n] * args.decode_utts
 
-    def once(host):
+    def once(host, n_run=None):
+        nlr = nl if n_run is None else [n_run] * args.decode_utts
         if host:
             x, h = x_host.to(dev, non_blocking=True), h_host.to(dev, non_blocking=True)
         else:
             x, h = once.xd, once.hd
-        gen = net._decode(x, h, nl, "sampling", seed=1234)
+        gen = net._decode(x, h, nlr, "sampling", seed=1234)
         if host:
             return gen.cpu()
         return gen
     once.xd, once.hd = x_host.to(dev), h_host.to(dev)
+    lib = _lib.load()
     with torch.no_grad():
-        once(False)
+        once(False, min(n, 2000))      # warm-up: a short run of the same kernel (one-time initialisation, clocks)
         torch.cuda.synchronize()
         if dist is not None:
             dist.barrier()
@@ -468,21 +490,53 @@ def run_decode(args, dev, rank, world, dist):
         ms, ms_e2e = float(tt[0]), float(tt[1])
     steps_incl_warmup = n + cfg.receptive_field - 1
     wbytes = sum(p.numel() for p in net.parameters()) * 4
+    kern = getattr(net, "last_decode_kernel", None)
+    cl = int(lib.wnb_decode_warp_cluster(args.decode_utts)) if kern == "warp" else 1
+    nu = 1 if args.decode_utts <= 148 else (2 if args.decode_utts <= 296 else 4)
+    ctas = (args.decode_utts + nu - 1) // nu * cl
+    us_step = ms * 1e3 / steps_incl_warmup
+    sm_mhz = 1965.0
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            sm_mhz = float(json.load(f).get("sm_max_mhz", sm_mhz))
+    except Exception:
+        pass
+    cyc_step = us_step * sm_mhz
+    # the recurrence is a per-sample dependency chain, not an HBM stream (SURVEY.md 8d "roofline -- decode"): what bounds a
+    # step is how fast ONE SM can pull its share of the 8.6 MB of weights through L2 -> shared memory and read it once
+    # with the FFMA GEMVs (128 B/clk shared-memory pipe); the HBM traffic per generated sample is < 10 B
+    per_cta_bytes = wbytes / cl
+    roof = {"bound": "per-sample dependency chain; per-SM L2->smem weight stream",
+            "kernel": "decode_%s_kernel, %d CTA(s) per utterance, %d CTAs on %d SMs" % (kern, cl, ctas, 148),
+            "us_per_step": us_step, "sm_cycles_per_step": cyc_step,
+            "smem_read_floor_cycles": per_cta_bytes / 128.0,
+            "frac_of_smem_floor": (per_cta_bytes / 128.0) / cyc_step,
+            "weight_stream_bytes_per_clk_per_sm": per_cta_bytes / cyc_step,
+            "l2_to_sm_weight_stream_GBps": ctas * per_cta_bytes / (us_step * 1e-6) / 1e9,
+            "algorithmic_hbm_bytes_per_sample": 4.0 * cfg.n_aux / max(U, 1) + 8.0,
+            "flops_per_sample": 4.2e6, "achieved_tflops": n_utt_total * n / (ms * 1e-3) * 4.2e6 / 1e12,
+            "dram_bytes_ncu": DECODE_DRAM_NCU}
     return {
         "metric": "autoregressive decode samples/s (persistent fast-generate kernel, sampling mode)",
         "value": n_utt_total * n / (ms * 1e-3), "unit": "samples/s", "n_gpus": world,
         "ms": ms, "higher_is_better": True, "scaling": "weak", "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "configs[3]: %d utterances/GPU x %d samples (bounded from 160000), arctic/sd "
-                               "30-layer 64/512, seed 128, aux N(0,1)" % (args.decode_utts, n),
+        "config": {"workload": "configs[3]: %d utterances/GPU x %d samples%s, arctic/sd "
+                               "30-layer 64/512, seed 128, aux N(0,1)"
+                               % (args.decode_utts, n, "" if n >= 159999 else " (bounded from 159999)"),
                    "utterances": n_utt_total, "samples_per_utterance": n,
                    "warmup_steps_in_time": cfg.receptive_field - 1},
-        "us_per_step": ms * 1e3 / steps_incl_warmup,
+        "us_per_step": us_step,
         "weight_stream_GBps": (args.decode_utts * steps_incl_warmup * wbytes) / (ms * 1e-3) / 1e9,
+        "roofline": roof,
         "e2e": {"value": n_utt_total * n / (ms_e2e * 1e-3), "unit": "samples/s",
                 "h2d_bytes_per_step": int(h_host.numel() * 4 + x_host.numel() * 8),
                 "d2h_bytes_per_step": int(args.decode_utts * n * 4)},
         "gpu_launches": int(launches),
     }
+
+
+# ncu dram__bytes_read.sum / dram__bytes_write.sum of ONE decode launch (profiles/r2_ncu_decode_*.txt); None = not captured
+DECODE_DRAM_NCU = None
 
 
 def _ref_nets():
@@ -678,9 +732,14 @@ def main():
                                                 "(recipe shape); the default is BASELINE.json configs[1]")
     ap.add_argument("--batch", type=int, default=None, help="override the per-GPU batch (default 8)")
     ap.add_argument("--decode-utts", type=int, default=64)
-    ap.add_argument("--decode-samples", type=int, default=32000)
+    ap.add_argument("--decode-samples", type=int, default=159999,
+                    help="samples per utterance (configs[3]: 2000 frames x 80 - 1 = 159 999, reference decode.py:158)")
+    ap.add_argument("--batch-length", type=int, default=None, help="override the nominal batch length (default 20000)")
+    ap.add_argument("--fp32-line", type=int, default=1, help="also time a few steps of the fp32 FFMA parity mode")
     args = ap.parse_args()
-    global CFG, BATCH
+    global CFG, BATCH, BATCH_LENGTH
+    if args.batch_length:
+        BATCH_LENGTH = args.batch_length
     if args.cfg:
         CFG = tuple(int(v) for v in args.cfg.split(","))
     if args.batch:

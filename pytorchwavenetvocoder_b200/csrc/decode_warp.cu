@@ -97,30 +97,38 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
   return r;
 }
-// Cluster-wide barrier of the consumer warps of both CTAs: two mbarriers per CTA used alternately, each expecting
-// one arrival per VIRTUAL warp (local lane 0 + the peer's lane 0 through the shared::cluster window).
+// Cluster-wide barrier of the consumer warps of both CTAs.  Two mbarriers per CTA used alternately, each expecting TWO
+// arrivals per phase: the consumer warps of a CTA first meet at a CTA barrier (their local and st.shared::cluster stores
+// are ordered before it), then ONE thread arrives -- with release.cluster -- on its own and on the peer's mbarrier;
+// lane 0 of every warp polls its own mbarrier with relaxed try_waits and fences once (acquire at cluster scope
+// invalidates L1, so it is paid once per warp and phase, not per poll or per thread).
 struct XSync {
   uint32_t bar_local;     // shared::cta address of bars[0]
   uint32_t bar_remote;    // shared::cluster address of the peer's bars[0]
   uint32_t n;
-  __device__ __forceinline__ void sync(int lane) {
+  template <int NTHREADS>
+  __device__ __forceinline__ void sync(int tid, int lane) {
     const uint32_t off = (n & 1u) * 8u, parity = (n >> 1) & 1u;
-    __syncwarp();
-    if (lane == 0) {
-      asm volatile("mbarrier.arrive.release.cluster.shared::cta.b64 _, [%0];" ::"r"(bar_local + off) : "memory");
+    asm volatile("bar.sync 1, %0;" ::"n"(NTHREADS) : "memory");
+    if (tid == 0) {
       asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_remote + off) : "memory");
+      asm volatile("mbarrier.arrive.release.cluster.shared::cta.b64 _, [%0];" ::"r"(bar_local + off) : "memory");
     }
-    ptx::SpinGuard guard;
-    for (;;) {
-      uint32_t ok;
-      asm volatile(
-          "{\n\t.reg .pred P;\n\t"
-          "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2;\n\t"
-          "selp.b32 %0, 1, 0, P;\n\t}\n"
-          : "=r"(ok) : "r"(bar_local + off), "r"(parity) : "memory");
-      if (ok) break;
-      if (guard.expired()) { printf("wnb200: decode cluster barrier timed out after 20 s\n"); __trap(); }
+    if (lane == 0) {
+      ptx::SpinGuard guard;
+      for (;;) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t.reg .pred P;\n\t"
+            "mbarrier.try_wait.parity.relaxed.cluster.shared::cta.b64 P, [%1], %2;\n\t"
+            "selp.b32 %0, 1, 0, P;\n\t}\n"
+            : "=r"(ok) : "r"(bar_local + off), "r"(parity) : "memory");
+        if (ok) break;
+        if (guard.expired()) { printf("wnb200: decode cluster barrier timed out after 20 s\n"); __trap(); }
+      }
+      asm volatile("fence.acq_rel.cluster;" ::: "memory");
     }
+    __syncwarp();
     n++;
   }
 };
@@ -274,7 +282,7 @@ __global__ void __launch_bounds__((W / CL) * 32 + 64, 1) decode_warp_kernel(cons
       ptx::mbar_init(&full[i], 1);
       ptx::mbar_init(&empty[i], WP);
     }
-    if (CL == 2) { ptx::mbar_init(&xbars[0], W); ptx::mbar_init(&xbars[1], W); }
+    if (CL == 2) { ptx::mbar_init(&xbars[0], 2); ptx::mbar_init(&xbars[1], 2); }
     *ready = 0u;
     ptx::fence_barrier_init();
   }
@@ -295,7 +303,7 @@ __global__ void __launch_bounds__((W / CL) * 32 + 64, 1) decode_warp_kernel(cons
   }
   // barrier between phases: the consumer warps of this CTA (CL == 1) or of both CTAs of the cluster (CL == 2)
   auto phase_sync = [&]() {
-    if constexpr (CL == 2) xs_.sync(lane); else cons_sync_w<W>();
+    if constexpr (CL == 2) xs_.template sync<kCons>(tid, lane); else cons_sync_w<W>();
   };
   const float* my_stream = p.stream + (size_t)rank * p.rank_stride;
   const int last_pos = p.P - 1 + nmax - 1;
@@ -513,11 +521,13 @@ __global__ void __launch_bounds__((W / CL) * 32 + 64, 1) decode_warp_kernel(cons
       WNB_T(5);
       // ---------------- phase B': skip 1x1, lanes own outputs SV*warp + SL*lane (+e) ----------------
       if (want) {
-        float s[NU][SL];
+        // (CL == 2 leaves 2 warps per scheduler: a single accumulator per output would make the K loop one dependent
+        //  FMA chain nobody hides; even / odd k go to two accumulators that are added at the end)
+        float s[NU][SL], s_odd[NU][SL];
 #pragma unroll
         for (int u = 0; u < NU; u++)
 #pragma unroll
-          for (int e = 0; e < SL; e++) s[u][e] = 0.f;
+          for (int e = 0; e < SL; e++) { s[u][e] = 0.f; s_odd[u][e] = 0.f; }
 #pragma unroll 1
         for (int c4 = 0; c4 < 64 / KPC; c4++) {
           const float* sc = ring.acquire() + warp * SV + lane * SL;   // (column inside this CTA's kSrow-wide rows)
@@ -539,7 +549,10 @@ __global__ void __launch_bounds__((W / CL) * 32 + 64, 1) decode_warp_kernel(cons
               for (int u = 0; u < NU; u++) {
                 const float z = kk == 0 ? zv[u].x : kk == 1 ? zv[u].y : kk == 2 ? zv[u].z : zv[u].w;
 #pragma unroll
-                for (int e = 0; e < SL; e++) s[u][e] = fmaf(wv[e], z, s[u][e]);
+                for (int e = 0; e < SL; e++) {
+                  if (CL == 2 && (kk & 1)) s_odd[u][e] = fmaf(wv[e], z, s_odd[u][e]);
+                  else s[u][e] = fmaf(wv[e], z, s[u][e]);
+                }
               }
             }
           }
@@ -550,7 +563,7 @@ __global__ void __launch_bounds__((W / CL) * 32 + 64, 1) decode_warp_kernel(cons
           const float bv = skip_b[e];
 #pragma unroll
           for (int u = 0; u < NU; u++) {
-            const float sv = s[u][e] + bv;
+            const float sv = (CL == 2 ? s[u][e] + s_odd[u][e] : s[u][e]) + bv;
             skip_tot[u][e] = (l == 0) ? sv : skip_tot[u][e] + sv;   // python `0 + s0 + s1 ...`, wavenet.py:374
           }
         }
@@ -577,11 +590,11 @@ __global__ void __launch_bounds__((W / CL) * 32 + 64, 1) decode_warp_kernel(cons
       }
       phase_sync();
       {
-        float s[NU][SL];
+        float s[NU][SL], s_odd[NU][SL];
 #pragma unroll
         for (int u = 0; u < NU; u++)
 #pragma unroll
-          for (int e = 0; e < SL; e++) s[u][e] = 0.f;
+          for (int e = 0; e < SL; e++) { s[u][e] = 0.f; s_odd[u][e] = 0.f; }
 #pragma unroll 1
         for (int c = 0; c < kS / KPC; c++) {
           const float* pc = ring.acquire() + warp * SV + lane * SL;
@@ -603,7 +616,10 @@ __global__ void __launch_bounds__((W / CL) * 32 + 64, 1) decode_warp_kernel(cons
               for (int u = 0; u < NU; u++) {
                 const float x = kk == 0 ? xv[u].x : kk == 1 ? xv[u].y : kk == 2 ? xv[u].z : xv[u].w;
 #pragma unroll
-                for (int e = 0; e < SL; e++) s[u][e] = fmaf(wv[e], x, s[u][e]);
+                for (int e = 0; e < SL; e++) {
+                  if (CL == 2 && (kk & 1)) s_odd[u][e] = fmaf(wv[e], x, s_odd[u][e]);
+                  else s[u][e] = fmaf(wv[e], x, s[u][e]);
+                }
               }
             }
           }
@@ -614,7 +630,8 @@ __global__ void __launch_bounds__((W / CL) * 32 + 64, 1) decode_warp_kernel(cons
           const float bv = post_b1[e];
 #pragma unroll
           for (int u = 0; u < NU; u++)
-            st_both<CL>(&h1[u * kS + vw * SV + lane * SL + e], fmaxf(s[u][e] + bv, 0.f), peer_delta);
+            st_both<CL>(&h1[u * kS + vw * SV + lane * SL + e],
+                        fmaxf((CL == 2 ? s[u][e] + s_odd[u][e] : s[u][e]) + bv, 0.f), peer_delta);
         }
       }
       phase_sync();

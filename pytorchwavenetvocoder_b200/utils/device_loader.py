@@ -51,6 +51,32 @@ def load_pair_frames(wavfile, featfile, feature_type, upsampling_factor, use_ups
     return np.ascontiguousarray(x, dtype=np.float32), np.ascontiguousarray(h)
 
 
+class WindowPlanner(object):
+    """The reference's window / batch bookkeeping (train.py:117, 160-185, 202-230) on stream positions only: cut every
+    window the buffer allows after each appended utterance, B consecutive windows make a batch, and at the end of an epoch
+    the windows of an incomplete batch are DROPPED (the batch lists are re-created at the top of ``while True``) while the
+    sample buffers carry over."""
+
+    def __init__(self, batch_size, hop, need):
+        self.B, self.hop, self.need = batch_size, hop, need
+        self.tail = self.next = 0
+        self.pending, self.ready = [], []
+
+    def append(self, n, last_of_epoch):
+        self.tail += n
+        while self.tail - self.next >= self.need:
+            self.pending.append(self.next)
+            self.next += self.hop
+            if len(self.pending) == self.B:
+                self.ready.append(self.pending[0])
+                self.pending = []
+        if last_of_epoch:
+            self.pending = []
+
+    def oldest_needed(self):
+        return self.ready[0] if self.ready else (self.pending[0] if self.pending else self.next)
+
+
 class DeviceTrainGenerator(object):
     """Drop-in for ``train_generator(...)`` in the mini-batch modes (``batch_length`` given): ``next()`` returns
     ``((x, h), t)`` CUDA tensors -- x, t (B, T) int64, h (B, D, T/U or T) float32."""
@@ -91,6 +117,7 @@ class DeviceTrainGenerator(object):
         self.fos = None if use_upsampling_layer else torch.zeros(self.cap_s, dtype=torch.int32, device=self.dev)
         self.feat = None                                  # allocated at the first utterance (dtype / D follow the files)
         self.head_s = self.tail_s = 0                     # absolute sample positions (ring index = pos % cap_s)
+        self.plan = WindowPlanner(self.B, self.hop, self.need)
         self.tail_f = 0                                   # absolute frame position of the next appended frame
         self.copy_stream = torch.cuda.Stream(device=self.dev)
         self.last_batch_event = None
@@ -119,7 +146,7 @@ class DeviceTrainGenerator(object):
                     idx = np.random.permutation(len(wl))
                     wl, fl = [wl[i] for i in idx], [fl[i] for i in idx]
                     self._lists = (wl, fl)
-                self._order.extend(zip(wl, fl))
+                self._order.extend((w_, f_, i_ + 1 == len(wl)) for i_, (w_, f_) in enumerate(zip(wl, fl)))
             return self._order[pos]
 
     def _reader(self, k):
@@ -127,14 +154,14 @@ class DeviceTrainGenerator(object):
         try:
             pos = k
             while True:
-                w, f = self._utterance(pos)
+                w, f, last_of_epoch = self._utterance(pos)
                 t0 = time.time()
                 x, h = load_pair_frames(w, f, self.feature_type, self.U, self.use_up, self.use_spk)
                 xp = torch.from_numpy(x).pin_memory()
                 hp = torch.from_numpy(h).pin_memory()
                 self.stats["reader_s"] += time.time() - t0
                 self.stats["utts"] += 1
-                self.queues[k].put((xp, hp))
+                self.queues[k].put((xp, hp, last_of_epoch))
                 pos += self.n_readers
         except BaseException as e:     # noqa: BLE001 -- surface reader failures in the consumer
             self.queues[k].put(e)
@@ -158,10 +185,12 @@ class DeviceTrainGenerator(object):
         if first < n:
             ring[:n - first].copy_(src[first:], non_blocking=True)
 
-    def _append(self, xp, hp):
+    def _append(self, xp, hp, last_of_epoch=False):
         n, nf = xp.shape[0], hp.shape[0]
         if n == 0:
+            self.plan.append(0, last_of_epoch)
             return
+        self.head_s = self.plan.oldest_needed()           # oldest sample a batch not launched yet still needs
         if self.feat is None:
             self.D = hp.shape[1]
             self.feat = torch.zeros(self.cap_f, self.D, dtype=hp.dtype, device=self.dev)
@@ -194,6 +223,7 @@ class DeviceTrainGenerator(object):
         self.append_event = ev
         self.tail_s += n
         self.tail_f += nf
+        self.plan.append(n, last_of_epoch)
 
     # ------------------------------------------------------------------ one batch
     def next(self):
@@ -201,8 +231,9 @@ class DeviceTrainGenerator(object):
         # the reference cuts a window whenever the buffer is long enough; B consecutive windows make a batch
         import time
         t0 = time.time()
-        while self.tail_s - (self.head_s + (B - 1) * hop) < self.need:
+        while not self.plan.ready:
             self._append(*self._pop())
+        s0 = self.plan.ready.pop(0)
         self.stats["wait_s"] += time.time() - t0
         self.stats["batches"] += 1
         t1 = time.time()
@@ -213,16 +244,15 @@ class DeviceTrainGenerator(object):
         h = torch.empty(B, self.D, self.Tf, dtype=torch.float32, device=self.dev)
         P = _lib.ptr
         _lib.check(self.lib.wnb_make_train_batch(
-            P(self.wave), P(self.feat), P(self.fos), self.head_s, hop, self.U, self.cap_s, self.cap_f, P(self.mean),
+            P(self.wave), P(self.feat), P(self.fos), s0, hop, self.U, self.cap_s, self.cap_f, P(self.mean),
             P(self.scale), P(x), P(t), P(h), B, self.T, self.Tf, self.D, self.feat_f64, self.mu, cur.cuda_stream),
             "make_train_batch")
         ev = torch.cuda.Event()
         ev.record(cur)
         self.last_batch_event = ev
-        self.head_s += hop * B
         # read ahead: whatever the reader thread has ready goes to the device now (copy stream, behind this batch's
         # kernel), so the next batches find their utterances resident and the copies overlap the training step
-        while self.tail_s - self.head_s < min(self.cap_s // 2, 3 * (self.need + (B - 1) * hop)):
+        while len(self.plan.ready) < 2 and self.tail_s - self.head_s < self.cap_s // 2:
             item = self._pop(block=False)
             if item is None:
                 break

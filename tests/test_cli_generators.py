@@ -91,3 +91,40 @@ def test_extend_time_and_alias_package():
     assert a.n_resch == 512 and a.n_skipch == 256 and a.batch_length == 20000 and a.use_upsampling_layer is True
     b = decode.get_parser().parse_args(["--feats", "f", "--checkpoint", "c", "--outdir", "o"])
     assert b.batch_size == 32 and b.fs == 16000
+
+
+@pytest.mark.parametrize("batch_length,batch_size,use_up", [(2000, 3, True), (1500, 2, False), (900, 1, True), (2000, 4, True)])
+def test_window_planner_reproduces_the_host_generator(corpus, batch_length, batch_size, use_up):
+    """utils/device_loader.WindowPlanner (the host bookkeeping of the on-device train_generator) + a plain numpy stream
+    give exactly the batches of train_generator, including the reference's dropped incomplete batch at each epoch end."""
+    from pytorchwavenetvocoder_b200.bin.train import train_generator
+    from pytorchwavenetvocoder_b200.utils.device_loader import WindowPlanner, load_pair_frames
+    wavs, feats, U, D = corpus
+    rf = 1 + 1023
+    host = train_generator(wavs, feats, receptive_field=rf, batch_length=batch_length, batch_size=batch_size,
+                           wav_transform=_enc, feat_transform=None, shuffle=False, upsampling_factor=U,
+                           use_upsampling_layer=use_up)
+    want = [host.next() for _ in range(14)]          # several epochs of this corpus
+    if use_up:
+        bl = batch_length - (rf + batch_length) % U
+        h_bs = (rf + bl) // U
+        T, hop, need = h_bs * U, (bl // U) * U, (h_bs + 1) * U
+    else:
+        T, hop, need = rf + batch_length - 1, batch_length, rf + batch_length + 1
+    plan = WindowPlanner(batch_size, hop, need)
+    xs, hs = [], []
+    for ep in range(12):
+        for i, (w, f) in enumerate(zip(wavs, feats)):
+            x, h = load_pair_frames(w, f, "world", U, use_up, False)
+            xs.append(x)
+            hs.append(h if use_up else h[np.arange(len(x)) // U])
+            plan.append(len(x), i + 1 == len(wavs))
+    sx, sh = np.concatenate(xs), np.concatenate(hs)
+    for k, ((xw, hw), tw) in enumerate(want):
+        s0 = plan.ready[k]
+        rows = np.stack([_enc(sx[s0 + b * hop:s0 + b * hop + T + 1]) for b in range(batch_size)])
+        assert np.array_equal(rows[:, :-1], xw.numpy()) and np.array_equal(rows[:, 1:], tw.numpy()), k
+        f0 = [(s0 + b * hop) // U if use_up else s0 + b * hop for b in range(batch_size)]
+        Tf = T // U if use_up else T
+        hh = np.stack([sh[f:f + Tf].T for f in f0]).astype(np.float32)
+        assert np.array_equal(hh, hw.numpy()), k
