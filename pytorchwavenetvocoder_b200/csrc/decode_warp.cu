@@ -97,144 +97,45 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
   return r;
 }
-// Cluster-wide barrier of the consumer warps of both CTAs.  Two mbarriers per CTA used alternately, each expecting TWO
-// arrivals per phase: the consumer warps of a CTA first meet at a CTA barrier (their local and st.shared::cluster stores
-// are ordered before it), then ONE thread arrives -- with release.cluster -- on its own and on the peer's mbarrier;
-// lane 0 of every warp polls its own mbarrier with relaxed try_waits and fences once (acquire at cluster scope
-// invalidates L1, so it is paid once per warp and phase, not per poll or per thread).
+// Phase hand-over between the two CTAs of a cluster WITHOUT fences: every value a CTA owes its peer is sent with
+// st.async (shared::cluster), which completes transaction bytes on an mbarrier in the PEER's shared memory, the way TMA
+// does.  A phase of a CTA's mbarrier completes when (a) its own consumer warps have met at a CTA barrier and one thread
+// has arrived with the number of bytes the peer owes for this phase (arrive.expect_tx) and (b) those bytes have landed.
+// Two mbarriers are used alternately; a CTA can never be more than one phase ahead of its peer, because each phase needs
+// the peer's data of that phase.
 struct XSync {
-  uint32_t bar_local;     // shared::cta address of bars[0]
-  uint32_t bar_remote;    // shared::cluster address of the peer's bars[0]
+  uint32_t bar_local;     // shared::cta address of xbars[0]
+  uint32_t bar_remote;    // shared::cluster address of the peer's xbars[0]
   uint32_t n;
+  __device__ __forceinline__ uint32_t peer_bar() const { return bar_remote + (n & 1u) * 8u; }
   template <int NTHREADS>
-  __device__ __forceinline__ void sync(int tid, int lane) {
-    const uint32_t off = (n & 1u) * 8u, parity = (n >> 1) & 1u;
-    asm volatile("bar.sync 1, %0;" ::"n"(NTHREADS) : "memory");
-    if (tid == 0) {
-      asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_remote + off) : "memory");
-      asm volatile("mbarrier.arrive.release.cluster.shared::cta.b64 _, [%0];" ::"r"(bar_local + off) : "memory");
+  __device__ __forceinline__ void sync(int tid, uint32_t expect_bytes) {
+    const uint32_t bar = bar_local + (n & 1u) * 8u, parity = (n >> 1) & 1u;
+    asm volatile("bar.sync 1, %0;" ::"n"(NTHREADS) : "memory");   // this CTA's share of the phase is complete and sent
+    if (tid == 0)
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(expect_bytes) : "memory");
+    ptx::SpinGuard guard;
+    for (;;) {
+      uint32_t ok;
+      asm volatile(
+          "{\n\t.reg .pred P;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+          "selp.b32 %0, 1, 0, P;\n\t}\n"
+          : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+      if (ok) break;
+      if (guard.expired()) { printf("wnb200: decode cluster hand-over timed out after 20 s\n"); __trap(); }
     }
-    if (lane == 0) {
-      ptx::SpinGuard guard;
-      for (;;) {
-        uint32_t ok;
-        asm volatile(
-            "{\n\t.reg .pred P;\n\t"
-            "mbarrier.try_wait.parity.relaxed.cluster.shared::cta.b64 P, [%1], %2;\n\t"
-            "selp.b32 %0, 1, 0, P;\n\t}\n"
-            : "=r"(ok) : "r"(bar_local + off), "r"(parity) : "memory");
-        if (ok) break;
-        if (guard.expired()) { printf("wnb200: decode cluster barrier timed out after 20 s\n"); __trap(); }
-      }
-      asm volatile("fence.acq_rel.cluster;" ::: "memory");
-    }
-    __syncwarp();
     n++;
   }
 };
-// store to this CTA's shared memory and (CL == 2) to the same location of the peer CTA
+// store to this CTA's shared memory and (CL == 2) send the value to the same location of the peer CTA, completing 4
+// transaction bytes on the peer's mbarrier of the current phase
 template <int CL>
-__device__ __forceinline__ void st_both(float* p, float v, uint32_t peer_delta) {
+__device__ __forceinline__ void st_both(float* p, float v, uint32_t peer_delta, uint32_t peer_bar) {
   *p = v;
   if constexpr (CL == 2)
-    asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(ptx::smem_u32(p) + peer_delta), "f"(v) : "memory");
-}
-
-struct Ring {
-  unsigned char* base; uint64_t* full; uint64_t* empty; int nslot; int split; int slot_bytes;
-  int slot; uint32_t phase;   // current chunk's slot and phase parity, advanced incrementally (no runtime division)
-  long long waited;           // debug: cycles spent inside acquire()
-  uint32_t* ready;            // number of chunks the gatekeeper warp has seen complete (monotonic)
-  uint32_t cidx;              // chunks this thread has consumed / published so far
-  __device__ __forceinline__ void advance() {
-    if (++slot == nslot) { slot = 0; phase ^= 1u; }
-  }
-  // consumer: wait until the gatekeeper has published chunk `cidx`.  A plain acquire-load poll of a shared
-  // counter (~30 cycles when the data is already there) instead of an mbarrier try_wait (~170 cycles): the
-  // gatekeeper warp is the only one that touches the TMA `full` barriers.
-  __device__ __forceinline__ const float* acquire() {
-    const long long t0 = clock64();
-    uint32_t seen;
-    ptx::SpinGuard guard;
-    for (;;) {
-      asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(seen) : "r"(ptx::smem_u32(ready)) : "memory");
-      if ((int32_t)(seen - cidx) > 0) break;
-      if (guard.expired()) { printf("wnb200: decode ring wait timed out after 20 s\n"); __trap(); }
-    }
-    waited += clock64() - t0;
-    return reinterpret_cast<const float*>(base + (size_t)slot * slot_bytes);
-  }
-  __device__ __forceinline__ void release() {           // consumer: whole warp done with the current chunk
-    __syncwarp();
-    if ((threadIdx.x & 31) == 0) ptx::mbar_arrive(&empty[slot]);
-    advance();
-    cidx++;
-  }
-  // gatekeeper: observe the TMA completion of the current chunk, then publish it to the consumers
-  __device__ __forceinline__ void gate() {
-    ptx::mbar_wait(&full[slot], phase);
-    cidx++;
-    asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(ptx::smem_u32(ready)), "r"(cidx) : "memory");
-    advance();
-  }
-  __device__ __forceinline__ void push(const float* src, uint32_t bytes) {  // producer
-    ptx::mbar_wait(&empty[slot], phase ^ 1u);
-    ptx::mbar_arrive_expect_tx(&full[slot], bytes);
-    // several smaller bulk copies per chunk keep more L2 requests in flight than one large copy
-    const uint32_t part = bytes / split;
-    for (int i = 0; i < split; i++)
-      bulk_g2s(base + (size_t)slot * slot_bytes + (size_t)i * part, reinterpret_cast<const unsigned char*>(src) + (size_t)i * part,
-               part, &full[slot]);
-    advance();
-  }
-};
-
-// Recursive-halving reduce-scatter over the 32 lanes of a warp: every lane contributes v[0..NV); afterwards
-// the total of value j is written to dst[j] by exactly one lane.  NV in {8, 16, 32, 64}.
-template <int NV>
-__device__ __forceinline__ void warp_reduce_scatter(float (&v)[NV], float* dst, int lane) {
-  int base = 0;
-  if constexpr (NV >= 2) {
-#pragma unroll
-    for (int lvl = 0; lvl < 5; lvl++) {
-      const int off = 16 >> lvl;
-      const int n = NV >> lvl;        // values held before this level
-      if (n >= 2) {
-        const int half = n >> 1;
-        const bool up = (lane & off) != 0;
-#pragma unroll
-        for (int t = 0; t < NV / 2; t++) {
-          if (t < half) {
-            const float send = up ? v[t] : v[t + half];
-            const float keep = up ? v[t + half] : v[t];
-            v[t] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-          }
-        }
-        base += up ? half : 0;
-      } else {
-        v[0] += __shfl_xor_sync(0xffffffffu, v[0], off);
-      }
-    }
-  }
-  constexpr int kLeft = (NV >= 32) ? NV / 32 : 1;           // values per lane at the end
-  constexpr int kDup = (NV >= 32) ? 1 : 32 / NV;            // lanes holding the same total
-  if ((lane & (kDup - 1)) == 0) {
-#pragma unroll
-    for (int t = 0; t < kLeft; t++) dst[base + t] = v[t];
-  }
-}
-
-__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
-                                              uint32_t k1, uint32_t (&out)[4]) {
-#pragma unroll
-  for (int i = 0; i < 10; i++) {
-    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
-    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
-    const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
-    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
-    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
-  }
-  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+    asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];"
+                 ::"r"(ptx::smem_u32(p) + peer_delta), "r"(__float_as_uint(v)), "r"(peer_bar) : "memory");
 }
 
 template <int NU, int W, bool BIG, int CL>
@@ -261,8 +162,8 @@ __global__ void __launch_bounds__((W / CL) * 32 + 64, 1) decode_warp_kernel(cons
   uint32_t* ready = reinterpret_cast<uint32_t*>(empty + p.nslot);   // + 3 pad words (keeps 16 B alignment)
   float* fw = reinterpret_cast<float*>(ready + 4);
   float* cur = fw;                          // [NU][64]
-  float* zs = cur + NU * kR;                // [NU][64]
-  float* hcol = zs + NU * kR;               // [NU][32]
+  float* zs0 = cur + NU * kR;               // [2][NU][64]: gate outputs of even / odd blocks (the peer CTA of a cluster
+  float* hcol = zs0 + 2 * NU * kR;          //               may already send block l+1's while block l's are being read)
   float* skipx = hcol + NU * kAp;           // [NU][512]  relu(skip sum) / post hidden input
   float* h1 = skipx + NU * kS;              // [NU][512]
   float* logit = h1 + NU * kS;              // [NU][256]
@@ -282,7 +183,7 @@ __global__ void __launch_bounds__((W / CL) * 32 + 64, 1) decode_warp_kernel(cons
       ptx::mbar_init(&full[i], 1);
       ptx::mbar_init(&empty[i], WP);
     }
-    if (CL == 2) { ptx::mbar_init(&xbars[0], 2); ptx::mbar_init(&xbars[1], 2); }
+    if (CL == 2) { ptx::mbar_init(&xbars[0], 1); ptx::mbar_init(&xbars[1], 1); }
     *ready = 0u;
     ptx::fence_barrier_init();
   }
@@ -301,9 +202,10 @@ __global__ void __launch_bounds__((W / CL) * 32 + 64, 1) decode_warp_kernel(cons
     xs_.bar_remote = mapa_u32(xs_.bar_local, (uint32_t)(rank ^ 1));
     peer_delta = xs_.bar_remote - xs_.bar_local;
   }
-  // barrier between phases: the consumer warps of this CTA (CL == 1) or of both CTAs of the cluster (CL == 2)
-  auto phase_sync = [&]() {
-    if constexpr (CL == 2) xs_.template sync<kCons>(tid, lane); else cons_sync_w<W>();
+  // barrier between phases: the consumer warps of this CTA (CL == 1) or the hand-over of `floats` values per CTA
+  // between the two CTAs of the cluster (CL == 2)
+  auto phase_sync = [&](int floats) {
+    if constexpr (CL == 2) xs_.template sync<kCons>(tid, (uint32_t)floats * 4u); else cons_sync_w<W>();
   };
   const float* my_stream = p.stream + (size_t)rank * p.rank_stride;
   const int last_pos = p.P - 1 + nmax - 1;
@@ -432,6 +334,7 @@ __global__ void __launch_bounds__((W / CL) * 32 + 64, 1) decode_warp_kernel(cons
       for (int e = 0; e < SL; e++) skip_tot[u][e] = 0.f;
 
     for (int l = 0; l < L; l++) {
+      float* zs = zs0 + (l & 1) * NU * kR;
       // ---------------- phase A: gate pre-activations, split K over lanes ----------------
       float acc[NU * GV];
 #pragma unroll
@@ -472,10 +375,10 @@ __global__ void __launch_bounds__((W / CL) * 32 + 64, 1) decode_warp_kernel(cons
         const int u = lane / CH, cc = lane % CH, c = vw * CH + cc;
         const float a = my_pre[u * GV + cc] + gate_bs;
         const float g = my_pre[u * GV + CH + cc] + gate_bt;
-        st_both<CL>(&zs[u * kR + c], sigmoidf_(a) * tanhf(g), peer_delta);
+        st_both<CL>(&zs[u * kR + c], sigmoidf_(a) * tanhf(g), peer_delta, xs_.peer_bar());
       }
       WNB_T(3);
-      phase_sync();
+      phase_sync(NU * kR / 2);
       WNB_T(4);
       // ---------------- phase B: residual 1x1 (split K) ----------------
       float skip_b[SL];
@@ -511,7 +414,7 @@ __global__ void __launch_bounds__((W / CL) * 32 + 64, 1) decode_warp_kernel(cons
         if (lane < CH * NU) {
           const int u = lane / CH, cc = lane % CH, c = vw * CH + cc;
           const float v = my_pre[u * CH + cc] + res_b + cur[u * kR + c];
-          st_both<CL>(&cur[u * kR + c], v, peer_delta);
+          st_both<CL>(&cur[u * kR + c], v, peer_delta, xs_.peer_bar());
           if (l + 1 < L && u0 + u < p.B) {   // input of layer l+1 at time `pos` -> its dilation queue
             float* q = p.queues + (size_t)(u0 + u) * p.q_per_utt + p.qoff[l + 1];
             __stcg(q + (size_t)(pos & (p.dil[l + 1] - 1)) * kR + c, v);   // dilations are powers of two
@@ -569,7 +472,7 @@ __global__ void __launch_bounds__((W / CL) * 32 + 64, 1) decode_warp_kernel(cons
         }
       }
       WNB_T(6);
-      phase_sync();
+      phase_sync(NU * kR / 2);
       WNB_T(7);
     }
 
@@ -579,7 +482,7 @@ __global__ void __launch_bounds__((W / CL) * 32 + 64, 1) decode_warp_kernel(cons
       for (int u = 0; u < NU; u++)
 #pragma unroll
         for (int e = 0; e < SL; e++)
-          st_both<CL>(&skipx[u * kS + vw * SV + lane * SL + e], fmaxf(skip_tot[u][e], 0.f), peer_delta);
+          st_both<CL>(&skipx[u * kS + vw * SV + lane * SL + e], fmaxf(skip_tot[u][e], 0.f), peer_delta, xs_.peer_bar());
       float post_b1[SL], post_b2;
       {
         const float* pbias = ring.acquire();   // [bp1 512 | bp2 256]
@@ -588,7 +491,7 @@ __global__ void __launch_bounds__((W / CL) * 32 + 64, 1) decode_warp_kernel(cons
         post_b2 = pbias[kS + vw * QV + (lane % QV)];
         ring.release();
       }
-      phase_sync();
+      phase_sync(NU * kS / 2);
       {
         float s[NU][SL], s_odd[NU][SL];
 #pragma unroll
@@ -631,10 +534,10 @@ __global__ void __launch_bounds__((W / CL) * 32 + 64, 1) decode_warp_kernel(cons
 #pragma unroll
           for (int u = 0; u < NU; u++)
             st_both<CL>(&h1[u * kS + vw * SV + lane * SL + e],
-                        fmaxf((CL == 2 ? s[u][e] + s_odd[u][e] : s[u][e]) + bv, 0.f), peer_delta);
+                        fmaxf((CL == 2 ? s[u][e] + s_odd[u][e] : s[u][e]) + bv, 0.f), peer_delta, xs_.peer_bar());
         }
       }
-      phase_sync();
+      phase_sync(NU * kS / 2);
       WNB_T(8);
       const int i = pos - (p.P - 1);
       {
@@ -672,13 +575,13 @@ __global__ void __launch_bounds__((W / CL) * 32 + 64, 1) decode_warp_kernel(cons
           if (KS == 2) v += __shfl_xor_sync(0xffffffffu, v, 16);
           v += bv;
           if (ksel == 0) {
-            st_both<CL>(&logit[u * kQ + vw * QV + lo], v, peer_delta);
+            st_both<CL>(&logit[u * kQ + vw * QV + lo], v, peer_delta, xs_.peer_bar());
             if (p.logits_out && u0 + u < p.B && i < s_n[u])
               p.logits_out[((size_t)(u0 + u) * p.max_n + i) * kQ + vw * QV + lo] = v;
           }
         }
       }
-      phase_sync();
+      phase_sync(NU * kQ / 2);
       WNB_T(9);
       // ---------------- pick: warp u handles utterance u ----------------
       if (warp < NU) {
@@ -737,7 +640,10 @@ __global__ void __launch_bounds__((W / CL) * 32 + 64, 1) decode_warp_kernel(cons
       WNB_T(10);
     }
   }
-  if constexpr (CL == 2) phase_sync();   // no CTA leaves while its peer may still store into its shared memory
+  if constexpr (CL == 2) {   // no CTA leaves while its peer may still send into its shared memory: a last 1-float hand-over
+    if (tid == 0) st_both<CL>(&pre_s[0], 0.f, peer_delta, xs_.peer_bar());
+    phase_sync(1);
+  }
   if (p.timing && tid == 0) {
     for (int i = 0; i < 12; i++) p.timing[(size_t)blockIdx.x * 16 + i] = tacc[i];
     p.timing[(size_t)blockIdx.x * 16 + 12] = ring.waited;
@@ -768,7 +674,7 @@ int decode_warp_launch(dw::Params& p, int W_packed, int CL_packed, cudaStream_t 
   }
   p.rank_stride = (long long)((size_t)p.L * (kLayerFloats - (CL - 1) * (kW1Floats / 2 + kWresFloats / 2 + kWskipFloats / 2)) +
                               kPBiasFloats + (kP1Floats + kP2Floats) / CL);
-  const size_t work = ((size_t)NU * (kR * 2 + kAp + 2 * kS + kQ + (size_t)p.L * kR) + 128 * NU) * sizeof(float);
+  const size_t work = ((size_t)NU * (kR * 3 + kAp + 2 * kS + kQ + (size_t)p.L * kR) + 128 * NU) * sizeof(float);
   const long avail = 227L * 1024 - 256 - (long)work - 16 * 16;
   // three 64 KB slots (half as many mbarrier round trips per step) when they fit, else up to six 32 KB slots
   const char* eb = getenv("WNB_DECODE_BIG");
