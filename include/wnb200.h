@@ -107,6 +107,8 @@ WNB_API int wnb_causal_conv1d_fwd(const float* x, const float* w, const float* b
  * wnb_mulaw_encode_f32); h[b][d][j] = float32 StandardScaler transform ((v - mean[d]) / scale[d] with sklearn's dtype
  * behaviour; mean == NULL: none) of frame (s0 + b*hop)/U + j (up-sampling layer: Tf = T/U, frame_of_sample NULL) or of
  * frame frame_of_sample[sample] (extend_time mode: Tf = T; an int32 ring parallel to `wave`).
+ * feat_f64: 1 = float64 rows; 0 = float32 rows, scaler in float64 arithmetic rounded to float32 after each step
+ * (scikit-learn 0.22, the reference's pin); 2 = float32 rows, scaler in float32 arithmetic (scikit-learn >= 1.x).
  * x, t (B,T) int64; h (B,D,Tf) fp32. */
 WNB_API int wnb_make_train_batch(const float* wave, const void* feat, const int32_t* frame_of_sample, int64_t s0,
                                  int64_t hop, int U, int64_t cap_s, int64_t cap_f, const double* mean, const double* scale,

@@ -138,6 +138,103 @@ __device__ __forceinline__ void st_both(float* p, float v, uint32_t peer_delta, 
                  ::"r"(ptx::smem_u32(p) + peer_delta), "r"(__float_as_uint(v)), "r"(peer_bar) : "memory");
 }
 
+struct Ring {
+  unsigned char* base; uint64_t* full; uint64_t* empty; int nslot; int split; int slot_bytes;
+  int slot; uint32_t phase;   // current chunk's slot and phase parity, advanced incrementally (no runtime division)
+  long long waited;           // debug: cycles spent inside acquire()
+  uint32_t* ready;            // number of chunks the gatekeeper warp has seen complete (monotonic)
+  uint32_t cidx;              // chunks this thread has consumed / published so far
+  __device__ __forceinline__ void advance() {
+    if (++slot == nslot) { slot = 0; phase ^= 1u; }
+  }
+  // consumer: wait until the gatekeeper has published chunk `cidx`.  A plain acquire-load poll of a shared
+  // counter (~30 cycles when the data is already there) instead of an mbarrier try_wait (~170 cycles): the
+  // gatekeeper warp is the only one that touches the TMA `full` barriers.
+  __device__ __forceinline__ const float* acquire() {
+    const long long t0 = clock64();
+    uint32_t seen;
+    ptx::SpinGuard guard;
+    for (;;) {
+      asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(seen) : "r"(ptx::smem_u32(ready)) : "memory");
+      if ((int32_t)(seen - cidx) > 0) break;
+      if (guard.expired()) { printf("wnb200: decode ring wait timed out after 20 s\n"); __trap(); }
+    }
+    waited += clock64() - t0;
+    return reinterpret_cast<const float*>(base + (size_t)slot * slot_bytes);
+  }
+  __device__ __forceinline__ void release() {           // consumer: whole warp done with the current chunk
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) ptx::mbar_arrive(&empty[slot]);
+    advance();
+    cidx++;
+  }
+  // gatekeeper: observe the TMA completion of the current chunk, then publish it to the consumers
+  __device__ __forceinline__ void gate() {
+    ptx::mbar_wait(&full[slot], phase);
+    cidx++;
+    asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(ptx::smem_u32(ready)), "r"(cidx) : "memory");
+    advance();
+  }
+  __device__ __forceinline__ void push(const float* src, uint32_t bytes) {  // producer
+    ptx::mbar_wait(&empty[slot], phase ^ 1u);
+    ptx::mbar_arrive_expect_tx(&full[slot], bytes);
+    // several smaller bulk copies per chunk keep more L2 requests in flight than one large copy
+    const uint32_t part = bytes / split;
+    for (int i = 0; i < split; i++)
+      bulk_g2s(base + (size_t)slot * slot_bytes + (size_t)i * part, reinterpret_cast<const unsigned char*>(src) + (size_t)i * part,
+               part, &full[slot]);
+    advance();
+  }
+};
+
+// Recursive-halving reduce-scatter over the 32 lanes of a warp: every lane contributes v[0..NV); afterwards
+// the total of value j is written to dst[j] by exactly one lane.  NV in {8, 16, 32, 64}.
+template <int NV>
+__device__ __forceinline__ void warp_reduce_scatter(float (&v)[NV], float* dst, int lane) {
+  int base = 0;
+  if constexpr (NV >= 2) {
+#pragma unroll
+    for (int lvl = 0; lvl < 5; lvl++) {
+      const int off = 16 >> lvl;
+      const int n = NV >> lvl;        // values held before this level
+      if (n >= 2) {
+        const int half = n >> 1;
+        const bool up = (lane & off) != 0;
+#pragma unroll
+        for (int t = 0; t < NV / 2; t++) {
+          if (t < half) {
+            const float send = up ? v[t] : v[t + half];
+            const float keep = up ? v[t + half] : v[t];
+            v[t] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+          }
+        }
+        base += up ? half : 0;
+      } else {
+        v[0] += __shfl_xor_sync(0xffffffffu, v[0], off);
+      }
+    }
+  }
+  constexpr int kLeft = (NV >= 32) ? NV / 32 : 1;           // values per lane at the end
+  constexpr int kDup = (NV >= 32) ? 1 : 32 / NV;            // lanes holding the same total
+  if ((lane & (kDup - 1)) == 0) {
+#pragma unroll
+    for (int t = 0; t < kLeft; t++) dst[base + t] = v[t];
+  }
+}
+
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                              uint32_t k1, uint32_t (&out)[4]) {
+#pragma unroll
+  for (int i = 0; i < 10; i++) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
 template <int NU, int W, bool BIG, int CL>
 __global__ void __launch_bounds__((W / CL) * 32 + 64, 1) decode_warp_kernel(const Params p) {
   static_assert(CL == 1 || (CL == 2 && NU == 1 && W == 16), "cluster form: one utterance per CTA pair, 16 virtual warps");

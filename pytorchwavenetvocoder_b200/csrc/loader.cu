@@ -11,7 +11,8 @@
 //                                                                  row = frame_of_sample[s0_b + j]   (extend_time, :172-176)
 // Positions are absolute stream positions; the buffers are rings (index = position mod capacity).
 // in the dtypes numpy / sklearn use (see mulaw_encode_f32_kernel in elementwise.cu; StandardScaler.transform on a
-// float32 array rounds to float32 after the subtraction and after the division, on float64 once at the final .float()).
+// float32 array rounds to float32 after the subtraction and after the division -- in float64 arithmetic with
+// scikit-learn 0.22, in float32 arithmetic with scikit-learn >= 1.x, selectable -- on float64 once at the final .float()).
 #include <cuda_runtime.h>
 #include <math.h>
 
@@ -49,13 +50,17 @@ __global__ void __launch_bounds__(256) make_train_batch_kernel(
     const int d = e / Tf, j = e - d * Tf;
     const int64_t row = (frame_of_sample ? (int64_t)frame_of_sample[(so + j) % cap_s] : fo + j) % cap_f;
     float out;
-    if (feat_f64) {
+    if (feat_f64 == 1) {
       const double v = reinterpret_cast<const double*>(feat)[row * D + d];
       out = mean ? (float)__ddiv_rn(__dadd_rn(v, -mean[d]), scale[d]) : (float)v;
     } else {
       const float v = reinterpret_cast<const float*>(feat)[row * D + d];
-      if (mean) {
-        const float c = (float)__dadd_rn((double)v, -mean[d]);   // X -= mean_   (float32 array, float64 operand)
+      if (mean && feat_f64 == 2) {
+        // scikit-learn >= 1.x: X -= astype(mean_, float32); X /= astype(scale_, float32)  (float32 arithmetic)
+        out = __fdiv_rn(__fsub_rn(v, (float)mean[d]), (float)scale[d]);
+      } else if (mean) {
+        // scikit-learn 0.22 (the reference's pin): in-place ops with float64 operands, rounded to float32 after each
+        const float c = (float)__dadd_rn((double)v, -mean[d]);   // X -= mean_
         out = (float)__ddiv_rn((double)c, scale[d]);             // X /= scale_
       } else {
         out = v;

@@ -51,6 +51,26 @@ def load_pair_frames(wavfile, featfile, feature_type, upsampling_factor, use_ups
     return np.ascontiguousarray(x, dtype=np.float32), np.ascontiguousarray(h)
 
 
+def _f32_scaler_mode():
+    """How the installed scikit-learn transforms a float32 array (StandardScaler.transform is what the reference's
+    feat_transform calls, train.py:470): 0 = float64 arithmetic rounded to float32 after the subtraction and after the
+    division (scikit-learn 0.22, the reference's pin), 2 = float32 arithmetic (scikit-learn >= 1.x casts mean_ / scale_
+    to the array's dtype first).  Probed, not parsed from the version string."""
+    from sklearn.preprocessing import StandardScaler
+    rng = np.random.RandomState(0)
+    x = rng.standard_normal((64, 4)).astype(np.float32)
+    sc = StandardScaler()
+    sc.mean_, sc.scale_ = rng.standard_normal(4), 0.5 + rng.rand(4)
+    got = sc.transform(x)
+    f64 = ((x.astype(np.float64) - sc.mean_).astype(np.float32).astype(np.float64) / sc.scale_).astype(np.float32)
+    f32 = (x - sc.mean_.astype(np.float32)) / sc.scale_.astype(np.float32)
+    if np.array_equal(got, f64):
+        return 0
+    if np.array_equal(got, f32):
+        return 2
+    raise _lib.WnbError("unrecognised StandardScaler float32 arithmetic: use --host_loader true")
+
+
 class WindowPlanner(object):
     """The reference's window / batch bookkeeping (train.py:117, 160-185, 202-230) on stream positions only: cut every
     window the buffer allows after each appended utterance, B consecutive windows make a batch, and at the end of an epoch
@@ -194,7 +214,7 @@ class DeviceTrainGenerator(object):
         if self.feat is None:
             self.D = hp.shape[1]
             self.feat = torch.zeros(self.cap_f, self.D, dtype=hp.dtype, device=self.dev)
-            self.feat_f64 = 1 if hp.dtype == torch.float64 else 0
+            self.feat_f64 = 1 if hp.dtype == torch.float64 else _f32_scaler_mode()
         if hp.dtype != self.feat.dtype:
             hp = hp.to(self.feat.dtype).pin_memory()
         while self.utts and self.utts[0][0] + self.utts[0][1] <= self.head_s:
