@@ -299,6 +299,7 @@ def run_ours(args):
                     return float(pending)
                 loader_loop(3)
                 barrier()
+                gen.stats.update(reader_s=0.0, utts=0, wait_s=0.0, batches=0, launch_s=0.0)   # steady state only
                 e4, e5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 s0_ = gen.tail_s
                 e4.record()

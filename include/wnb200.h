@@ -66,6 +66,11 @@ WNB_API int wnb_mulaw_encode_f32(const float* x, int64_t* y, int64_t n, int mu, 
 WNB_API int wnb_mulaw_encode_f64(const double* x, int64_t* y, int64_t n, int mu, void* stream);
 WNB_API int wnb_mulaw_decode_f64(const int64_t* y, double* x, int64_t n, int mu, void* stream);
 
+/* a17 (decode driver, bin/decode.py:318-319): generated codes -> PCM_16 samples for a whole batch on the device.  The
+ * input domain is the mu codes, so `table` (ntab int16, device) holds decode_mu_law + the writer's quantisation per code
+ * (built by nets.mulaw_pcm16_table); out[i] = table[idx[i] mod ntab]. */
+WNB_API int wnb_lut_i16(const int32_t* idx, const int16_t* table, int16_t* out, int64_t n, int ntab, void* stream);
+
 /* ---- a4/a5/a9: OneHot + causal conv as an embedding gather (wavenet.py:78-92, 513-516) ----- */
 WNB_API int wnb_front_embed_fwd(const int64_t* x /*(B,T)*/, const float* wf, const float* bias /*(R)*/,
                         float* out /*(B,T,R)*/, int B, int T, int Q, int R, int ks, void* stream);

@@ -31,6 +31,7 @@ SIGNATURES = {
     "wnb_mulaw_encode_f32": (_I, [_P, _P, _L, _I, _P]),
     "wnb_mulaw_encode_f64": (_I, [_P, _P, _L, _I, _P]),
     "wnb_mulaw_decode_f64": (_I, [_P, _P, _L, _I, _P]),
+    "wnb_lut_i16": (_I, [_P, _P, _P, _L, _I, _P]),
     "wnb_front_embed_fwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "wnb_front_embed_bwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "wnb_aux_upsample_fwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),

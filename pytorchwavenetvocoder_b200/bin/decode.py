@@ -31,7 +31,9 @@ from pytorchwavenetvocoder_b200.utils import find_files
 from pytorchwavenetvocoder_b200.utils import read_hdf5
 from pytorchwavenetvocoder_b200.utils import read_txt
 from pytorchwavenetvocoder_b200.utils import shape_hdf5
+from pytorchwavenetvocoder_b200.utils import have_soundfile
 from pytorchwavenetvocoder_b200.utils import write_wav
+from pytorchwavenetvocoder_b200.utils import write_wav_pcm16
 
 
 def pad_list(batch_list, pad_value=0.0):
@@ -156,12 +158,20 @@ def gpu_decode(feat_list, gpu, args, config):
             if args.batch_size > 1:
                 for feat_ids, (batch_x, batch_h, n_samples_list) in generator:
                     logging.info("decoding start")
-                    samples_list = model.batch_fast_generate(batch_x, batch_h, n_samples_list, args.intervals)
                     # batch_fast_generate returns completion order = ascending length, ties by batch index
                     order = sorted(range(len(feat_ids)), key=lambda b: (n_samples_list[b], b))
+                    if not have_soundfile():
+                        # the PCM_16 quantisation is ours (stdlib writer): do decode_mu_law + quantisation for the whole
+                        # batch on the device and move 2 bytes per sample (reference :316-319 does both on the host)
+                        pcm_list = model.batch_fast_generate_pcm16(batch_x, batch_h, n_samples_list, args.intervals)
+                        for b, pcm in zip(order, pcm_list):
+                            write_wav_pcm16(args.outdir + "/" + feat_ids[b] + ".wav", pcm, args.fs)
+                            logging.info("wrote %s.wav in %s." % (feat_ids[b], args.outdir))
+                        continue
+                    samples_list = model.batch_fast_generate(batch_x, batch_h, n_samples_list, args.intervals)
                     for b, samples in zip(order, samples_list):
                         wav = decode_mu_law(samples, config.n_quantize)
-                        write_wav(args.outdir + "/" + feat_ids[b] + ".wav", wav, args.fs)
+                        write_wav(args.outdir + "/" + feat_ids[b] + ".wav", wav, args.fs)   # libsndfile quantises
                         logging.info("wrote %s.wav in %s." % (feat_ids[b], args.outdir))
             else:
                 for feat_id, (x, h, n_samples) in generator:

@@ -162,6 +162,17 @@ __global__ void mulaw_decode_f64_kernel(const int64_t* __restrict__ y, double* _
   }
 }
 
+// codes -> PCM_16 for a whole batch (decode driver, bin/decode.py:318-319: decode_mu_law + write "PCM_16"): the input
+// domain is the mu integer codes, so the host evaluates decode + quantisation once per code and this is a 2-byte gather
+__global__ void lut_i16_kernel(const int32_t* __restrict__ idx, const int16_t* __restrict__ table, int16_t* __restrict__ out,
+                               int64_t n, int ntab) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    int v = idx[i] % ntab;
+    if (v < 0) v += ntab;
+    out[i] = __ldg(table + v);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // front embedding gather (wavenet.py:78-92 OneHot + :513-516 causal conv)
 //   out[b][t][r] = bias[r] + sum_k wf[k][x[b][t-(ks-1-k)] mod Q][r]   (missing history: zero)
@@ -398,6 +409,14 @@ WNB_API int wnb_mulaw_decode_f64(const int64_t* y, double* x, int64_t n, int mu,
   }
   mulaw_decode_f64_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(y, x, n, m, mu, tab);
   WNB_CHECK_LAUNCH("mulaw_decode_f64");
+  return WNB_OK;
+}
+
+WNB_API int wnb_lut_i16(const int32_t* idx, const int16_t* table, int16_t* out, int64_t n, int ntab, void* stream) {
+  WNB_REQUIRE(n >= 0 && ntab > 0 && (n == 0 || (idx && table && out)), "lut_i16: bad arguments");
+  if (n == 0) return WNB_OK;
+  lut_i16_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(idx, table, out, n, ntab);
+  WNB_CHECK_LAUNCH("lut_i16");
   return WNB_OK;
 }
 

@@ -27,7 +27,7 @@ from .. import _lib
 from .._lib import MATH_FP32, MATH_TF32, MODE_ARGMAX, MODE_SAMPLING, check, ptr, stream
 
 __all__ = ["encode_mu_law", "decode_mu_law", "initialize", "OneHot", "CausalConv1d", "UpSampling",
-           "WaveNet", "cross_entropy"]
+           "WaveNet", "cross_entropy", "mulaw_pcm16_table", "codes_to_pcm16"]
 
 # bench.py sets this to a list to get (start, end) CUDA-event pairs around every fused-block launch
 PROFILE_EVENTS = None
@@ -80,6 +80,25 @@ def decode_mu_law(y, mu=256):
     xt = torch.empty(yt.numel(), dtype=torch.float64, device=dev)
     check(lib.wnb_mulaw_decode_f64(ptr(yt), ptr(xt), yt.numel(), int(mu), stream()), "mulaw_decode")
     return xt.cpu().numpy().reshape(y.shape)
+
+
+def mulaw_pcm16_table(mu=256):
+    """int16 PCM value of every mu-law code: ``decode_mu_law`` (reference wavenet.py:33-47) followed by the PCM_16
+    quantisation of ``utils.write_wav``'s stdlib writer (round-half-even of x * 32768, clipped to int16)."""
+    x = decode_mu_law(np.arange(mu), mu)
+    return np.clip(np.round(x * 32768.0), -32768, 32767).astype(np.int16)
+
+
+def codes_to_pcm16(codes, mu=256):
+    """(B, n) int32 CUDA tensor of generated codes -> (B, n) int16 CUDA tensor (one gather kernel for the whole batch)."""
+    lib = _lib.load()
+    codes = codes.contiguous()
+    if codes.dtype != torch.int32:
+        codes = codes.to(torch.int32)
+    tab = torch.from_numpy(mulaw_pcm16_table(mu)).to(codes.device)
+    out = torch.empty(codes.shape, dtype=torch.int16, device=codes.device)
+    check(lib.wnb_lut_i16(ptr(codes), ptr(tab), ptr(out), codes.numel(), int(mu), stream()), "lut_i16")
+    return out
 
 
 def initialize(m):
@@ -883,6 +902,15 @@ class WaveNet(nn.Module):
             logging.info("%d/%d generated in %.3f sec (%.6f sec / sample)" % (n_samples, n_samples, el,
                                                                               el / max(n_samples, 1)))
         return out
+
+    def batch_fast_generate_pcm16(self, x, h, n_samples_list, intervals=None, mode="sampling"):
+        """``batch_fast_generate`` + ``decode_mu_law`` + PCM_16 quantisation (reference bin/decode.py:316-319) without
+        leaving the device in between: one decode launch, one gather kernel for the whole batch, 2 bytes per sample over
+        PCIe.  Returns int16 arrays in COMPLETION order like ``batch_fast_generate``."""
+        n_list = [int(n) for n in n_samples_list]
+        pcm = codes_to_pcm16(self._decode(x, h, n_list, mode), self.n_quantize).cpu().numpy()
+        order = sorted(range(len(n_list)), key=lambda b: (n_list[b], b))
+        return [pcm[b, :n_list[b]].copy() for b in order]
 
     def batch_fast_generate(self, x, h, n_samples_list, intervals=None, mode="sampling"):
         """GENERATE WAVEFORM WITH FAST ALGORITHM IN BATCH MODE (reference wavenet.py:397-511).

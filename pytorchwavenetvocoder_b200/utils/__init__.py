@@ -1,2 +1,2 @@
 from .utils import *  # noqa
-from .utils import read_wav, write_wav  # noqa
+from .utils import have_soundfile, read_wav, write_wav, write_wav_pcm16  # noqa

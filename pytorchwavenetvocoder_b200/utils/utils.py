@@ -189,6 +189,24 @@ def read_wav(path, dtype=np.float32):
             return (data.astype(dtype) / dtype(32768)), w.getframerate()
 
 
+def have_soundfile():
+    try:
+        import soundfile  # noqa: F401
+        return True
+    except ImportError:
+        return False
+
+
+def write_wav_pcm16(path, pcm, fs):
+    """Write int16 samples (already quantised, e.g. by nets.codes_to_pcm16 on the device) as a mono PCM_16 wav."""
+    import wave
+    with wave.open(path, "wb") as w:
+        w.setnchannels(1)
+        w.setsampwidth(2)
+        w.setframerate(int(fs))
+        w.writeframes(np.ascontiguousarray(pcm, dtype="<i2").tobytes())
+
+
 def write_wav(path, x, fs):
     """``sf.write(path, x, fs, "PCM_16")`` (reference bin/decode.py:319)."""
     try:

@@ -298,3 +298,20 @@ def test_causal_conv1d_standalone():
         ref = O.causal_conv(x.cpu().numpy().astype(np.float64), m.conv.weight.detach().cpu().numpy().astype(np.float64),
                             m.conv.bias.detach().cpu().numpy().astype(np.float64), d)
         np.testing.assert_allclose(y.cpu().numpy(), ref, atol=1e-5, rtol=0)
+
+
+def test_codes_to_pcm16_matches_host_decode_and_writer(tmp_path):
+    """f2: decode_mu_law + PCM_16 quantisation for a whole batch on the device == the host path of bin/decode.py
+    (decode_mu_law per utterance, then utils.write_wav's stdlib PCM_16 writer), sample for sample."""
+    from pytorchwavenetvocoder_b200.nets import codes_to_pcm16, decode_mu_law
+    from pytorchwavenetvocoder_b200.utils import read_wav, write_wav_pcm16
+    rng = np.random.RandomState(3)
+    codes = rng.randint(0, 256, size=(5, 4000)).astype(np.int32)
+    codes[0, :256] = np.arange(256)
+    pcm = codes_to_pcm16(torch.from_numpy(codes).cuda(), 256).cpu().numpy()
+    want = np.clip(np.round(decode_mu_law(codes.astype(np.int64), 256) * 32768.0), -32768, 32767).astype(np.int16)
+    assert pcm.dtype == np.int16 and np.array_equal(pcm, want)
+    p = str(tmp_path / "a.wav")
+    write_wav_pcm16(p, pcm[1], 16000)
+    x, fs = read_wav(p)
+    assert fs == 16000 and np.array_equal(np.round(x * 32768.0).astype(np.int16), pcm[1])

@@ -7,7 +7,7 @@ lib = _lib.load()
 dev = torch.device('cuda')
 cfg, net = make_model(dev, 'fp32'); net.eval()
 B, n = int(sys.argv[1]) if len(sys.argv) > 1 else 64, 2000
-buf = torch.zeros(B * 16, dtype=torch.int64, device=dev)
+buf = torch.zeros(2 * B * 16, dtype=torch.int64, device=dev)   # (2 CTAs per utterance in the cluster form)
 lib.wnb_decode_warp_set_timing(ctypes.c_void_p(buf.data_ptr()))
 h = torch.randn(B, 28, (n + 80) // 80, device=dev); x = torch.full((B, 1), 128, dtype=torch.int64, device=dev)
 with torch.no_grad():
