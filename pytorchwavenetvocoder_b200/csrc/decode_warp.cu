@@ -108,12 +108,22 @@ struct XSync {
   uint32_t bar_remote;    // shared::cluster address of the peer's xbars[0]
   uint32_t n;
   __device__ __forceinline__ uint32_t peer_bar() const { return bar_remote + (n & 1u) * 8u; }
+  // arrive(): this CTA's share of the phase is complete and sent; wait(): the peer's share has landed.  Work that does
+  // not depend on the peer's data may sit between the two (it hides the ~250-cycle DSMEM latency).
+  template <int NTHREADS>
+  __device__ __forceinline__ void arrive(int tid, uint32_t expect_bytes) {
+    asm volatile("bar.sync 1, %0;" ::"n"(NTHREADS) : "memory");
+    if (tid == 0)
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_local + (n & 1u) * 8u),
+                   "r"(expect_bytes) : "memory");
+  }
   template <int NTHREADS>
   __device__ __forceinline__ void sync(int tid, uint32_t expect_bytes) {
+    arrive<NTHREADS>(tid, expect_bytes);
+    wait();
+  }
+  __device__ __forceinline__ void wait() {
     const uint32_t bar = bar_local + (n & 1u) * 8u, parity = (n >> 1) & 1u;
-    asm volatile("bar.sync 1, %0;" ::"n"(NTHREADS) : "memory");   // this CTA's share of the phase is complete and sent
-    if (tid == 0)
-      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(expect_bytes) : "memory");
     ptx::SpinGuard guard;
     for (;;) {
       uint32_t ok;
@@ -245,6 +255,7 @@ __global__ void __launch_bounds__((W / CL) * 32 + 64, 1) decode_warp_kernel(cons
   constexpr int kSrow = kS / CL, kQrow = kQ / CL;   // columns of a skip / post-1 / post-2 row in THIS CTA's stream
   constexpr int kLayerF = kLayerFloats - (CL - 1) * (kW1Floats / 2 + kWresFloats / 2 + kWskipFloats / 2);
   constexpr int kJBlock = WP * 2 * (kR / W) * 32;   // floats of one W1 j-block in this CTA's stream
+  constexpr bool kW1One = BIG && CL == 2;           // the halved W1 (40.5 KB with b1) fits one 64 KB slot: one acquire
   constexpr int CH = kR / W;             // gate / residual channels owned by a warp (8 or 4)
   constexpr int GV = 2 * CH;             // gate values per lane: [sigmoid CH | tanh CH]
   constexpr int SV = kS / W;             // skip / post-1 outputs per warp (64 or 32)
@@ -304,6 +315,12 @@ __global__ void __launch_bounds__((W / CL) * 32 + 64, 1) decode_warp_kernel(cons
   auto phase_sync = [&](int floats) {
     if constexpr (CL == 2) xs_.template sync<kCons>(tid, (uint32_t)floats * 4u); else cons_sync_w<W>();
   };
+  auto phase_arrive = [&](int floats) {   // split form: (CL == 1: nothing to send, the barrier happens in phase_wait)
+    if constexpr (CL == 2) xs_.template arrive<kCons>(tid, (uint32_t)floats * 4u);
+  };
+  auto phase_wait = [&]() {
+    if constexpr (CL == 2) xs_.wait(); else cons_sync_w<W>();
+  };
   const float* my_stream = p.stream + (size_t)rank * p.rank_stride;
   const int last_pos = p.P - 1 + nmax - 1;
   Ring ring{ring_base, full, empty, p.nslot, p.split, kSlotB, 0, 0u, 0ll, ready, 0u};
@@ -315,13 +332,17 @@ __global__ void __launch_bounds__((W / CL) * 32 + 64, 1) decode_warp_kernel(cons
         const bool want = pos >= p.P - 1;
         for (int l = 0; l < L; l++) {
           const float* base = my_stream + (size_t)l * kLayerF;
-          if (BIG) {
-            ring.push(base, 4 * kJBlock * 4);                              // W1 j = 0..3
+          if (kW1One) {
+            ring.push(base, (5 * kJBlock + kB1Floats) * 4);                // W1 j = 0..4, then b1: one chunk
           } else {
-            ring.push(base, 2 * kJBlock * 4);                              // W1 j = 0,1
-            ring.push(base + 2 * kJBlock, 2 * kJBlock * 4);                // W1 j = 2,3
+            if (BIG) {
+              ring.push(base, 4 * kJBlock * 4);                            // W1 j = 0..3
+            } else {
+              ring.push(base, 2 * kJBlock * 4);                            // W1 j = 0,1
+              ring.push(base + 2 * kJBlock, 2 * kJBlock * 4);              // W1 j = 2,3
+            }
+            ring.push(base + 4 * kJBlock, (kJBlock + kB1Floats) * 4);      // W1 j = 4, then b1
           }
-          ring.push(base + 4 * kJBlock, (kJBlock + kB1Floats) * 4);        // W1 j = 4, then b1
           const float* wres = base + 5 * kJBlock + kB1Floats;
           ring.push(wres, (kWresFloats / CL + kB2Floats) * 4);             // W2res, then b2
           if (want)
@@ -343,7 +364,7 @@ __global__ void __launch_bounds__((W / CL) * 32 + 64, 1) decode_warp_kernel(cons
   if (warp == WP + 1) {
     // ================================ gatekeeper warp ================================
     if (lane == 0) {
-      const int per_layer_warm = (BIG ? 2 : 3) + 1, per_layer_skip = 64 / KPC;
+      const int per_layer_warm = (kW1One ? 1 : (BIG ? 2 : 3)) + 1, per_layer_skip = 64 / KPC;
       const int post_chunks = 1 + kS / KPC + kS / (2 * KPC);
       for (int pos = 0; pos <= last_pos; pos++) {
         const bool want = pos >= p.P - 1;
@@ -440,9 +461,9 @@ __global__ void __launch_bounds__((W / CL) * 32 + 64, 1) decode_warp_kernel(cons
       float gate_bs = 0.f, gate_bt = 0.f;
 #pragma unroll
       for (int j = 0; j < 5; j++) {
-        if (j == 0 || (!BIG && j == 2) || j == 4) chunk = ring.acquire();
+        if (j == 0 || (!kW1One && ((!BIG && j == 2) || j == 4))) chunk = ring.acquire();
         // [j][warp][group g][lane][4]: consecutive lanes read consecutive 16 B -> conflict-free LDS.128
-        const int jj = (j == 4) ? 0 : (BIG ? j : (j & 1));   // index of this j inside its chunk
+        const int jj = kW1One ? j : ((j == 4) ? 0 : (BIG ? j : (j & 1)));   // index of this j inside its chunk
         const float4* wp = reinterpret_cast<const float4*>(chunk + (size_t)(jj * WP + warp) * (GV * 32)) + lane;
         float4 wv[GV / 4];
 #pragma unroll
@@ -460,10 +481,10 @@ __global__ void __launch_bounds__((W / CL) * 32 + 64, 1) decode_warp_kernel(cons
         }
         if (j == 4) {   // b1 sits right behind the j = 4 weights in this chunk
           const int c = vw * CH + (lane % CH);
-          gate_bs = chunk[kJBlock + c];
-          gate_bt = chunk[kJBlock + 64 + c];
+          gate_bs = chunk[(kW1One ? 5 : 1) * kJBlock + c];
+          gate_bt = chunk[(kW1One ? 5 : 1) * kJBlock + 64 + c];
         }
-        if ((!BIG && j == 1) || j == 3 || j == 4) ring.release();
+        if (kW1One ? (j == 4) : ((!BIG && j == 1) || j == 3 || j == 4)) ring.release();
       }
       WNB_T(2);
       warp_reduce_scatter<NU * GV>(acc, my_pre, lane);
@@ -519,6 +540,7 @@ __global__ void __launch_bounds__((W / CL) * 32 + 64, 1) decode_warp_kernel(cons
         }
       }
       WNB_T(5);
+      phase_arrive(NU * kR / 2);   // the residual outputs are on their way to the peer while the skip GEMV runs
       // ---------------- phase B': skip 1x1, lanes own outputs SV*warp + SL*lane (+e) ----------------
       if (want) {
         // (CL == 2 leaves 2 warps per scheduler: a single accumulator per output would make the K loop one dependent
@@ -569,7 +591,7 @@ __global__ void __launch_bounds__((W / CL) * 32 + 64, 1) decode_warp_kernel(cons
         }
       }
       WNB_T(6);
-      phase_sync(NU * kR / 2);
+      phase_wait();
       WNB_T(7);
     }
 

@@ -32,7 +32,7 @@ constexpr int kMaxSeg = 4;
 
 struct Seg { int amap; int shift; int K; int bmap; int b_k0; int b_n0; int b_n1; };  // b_n1 >= 0: rows of the 2nd half of N
 struct alignas(64) Params {
-  CUtensorMap maps[10];   // [0..3] A tensors, [4..7] weight matrices, [8] output, [9] second output
+  CUtensorMap maps[11];   // [0..3] A tensors, [4..7] weight matrices, [8] output, [9] second output, [10] epilogue tile
   Seg seg[kMaxSeg];
   int nseg, N, T, B, nstages, nacc;
   const float* bias; const float* mask; int ldmask; const float* add; int ldadd;
@@ -54,6 +54,11 @@ struct alignas(64) Params {
   // weight chunk is fetched from L2 once per 256 rows instead of once per 128 (the K >= 512 GEMMs are bound by the
   // L2 -> SM path, not by HBM or the tensor pipe).  The two accumulators are the two TMEM buffers (N <= 256).
   int mt, stg_boxes;
+  // etile != 0 (NtTcOpts::stage_epilogue_operand): the epilogue's per-row operand -- 1: the dz slice of the gate backward,
+  // 2: the residual `add` of a <= 64-column primary output -- is brought in by the PRODUCER as one [128 x 64] TMA tile per
+  // time tile (maps[10], two swizzled sub-tiles) instead of per-lane row loads from global memory: the epilogue warps
+  // pace these kernels and were stalled on exactly those loads (ncu: 51 % long-scoreboard on L1TEX).
+  int etile;
 };
 
 // barrier layout in smem: full[nstages] empty[nstages] dfull[2] dempty[2]
@@ -86,12 +91,15 @@ __global__ void __launch_bounds__(kThreadsN, 1) gemm_nt_tc_kernel(const __grid_c
   const int a_bytes = p.mt * kASub;
   const int stage_bytes = a_bytes + N * 128;
   unsigned char* stg_base = smem + (size_t)p.nstages * stage_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(stg_base + kEpiWarpsN * p.stg_boxes * kStg);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stg_base + kEpiWarpsN * p.stg_boxes * kStg + (p.etile ? 2 * kASub : 0));
   uint64_t* full = bars;
   uint64_t* empty = bars + p.nstages;
   uint64_t* dfull = bars + 2 * p.nstages;
   uint64_t* dempty = dfull + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dempty + 2);
+  uint64_t* efull = dempty + 2;       // epilogue-operand tile landed / consumed (etile)
+  uint64_t* eempty = efull + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(eempty + 1);
+  unsigned char* ebuf = stg_base + kEpiWarpsN * p.stg_boxes * kStg;   // 2 x [128 x 32] sub-tiles when etile
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rows_per_tile = kTM * p.mt;
   const int tiles_per_b = (p.T + rows_per_tile - 1) / rows_per_tile;
@@ -108,6 +116,8 @@ __global__ void __launch_bounds__(kThreadsN, 1) gemm_nt_tc_kernel(const __grid_c
       ptx::mbar_init(&dfull[i], 1);
       ptx::mbar_init(&dempty[i], 32 * kEpiWarpsN);
     }
+    ptx::mbar_init(efull, 1);
+    ptx::mbar_init(eempty, 32 * kEpiWarpsN);
     ptx::fence_barrier_init();
   }
   if (warp == 1) ptx::tmem_alloc<512>(tmem_slot);
@@ -125,11 +135,17 @@ __global__ void __launch_bounds__(kThreadsN, 1) gemm_nt_tc_kernel(const __grid_c
   // thread is active and issues the uniform-datapath TMA / tcgen05 instructions without a per-thread ELECT loop
   if (warp == 0) {
     if (ptx::elect_one()) {
-      for (int i = 0; i < 10; i++) ptx::prefetch_tmap(&p.maps[i]);
-      uint32_t st = 0, ph = 0;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      for (int i = 0; i < 11; i++) ptx::prefetch_tmap(&p.maps[i]);
+      uint32_t st = 0, ph = 0, pit = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, pit++) {
         const int tt = tile / p.nblk, ncol0 = (tile - tt * p.nblk) * N;
         const int b = tt / tiles_per_b, t0 = (tt - b * tiles_per_b) * rows_per_tile;
+        if (p.etile) {   // the epilogue's operand tile of this time tile goes first: it is needed as soon as the accumulator is
+          wait(eempty, (pit & 1) ^ 1, NP_P_EMPTY);
+          ptx::mbar_arrive_expect_tx(efull, 2 * kASub);
+          ptx::tma_load_3d(ebuf, &p.maps[10], efull, 0, t0, b);
+          ptx::tma_load_3d(ebuf + kASub, &p.maps[10], efull, 32, t0, b);
+        }
         for (int s = 0; s < p.nseg; s++) {
           const Seg sg = p.seg[s];
           for (int kc = 0; kc < sg.K / 32; kc++) {
@@ -225,8 +241,9 @@ __global__ void __launch_bounds__(kThreadsN, 1) gemm_nt_tc_kernel(const __grid_c
       // operands of the epilogue that do not depend on the accumulator are requested before waiting for it, so
       // their DRAM latency overlaps the mainloop of this tile: dz of the gate backward, `add` of the first chunk
       float4 pre[8];
-      const bool pre_dz = EPI != EPI_PLAIN && p.gate_mode >= 2 && row_ok && hf * 32 < 64;
-      const bool pre_add = EPI == EPI_PLAIN && p.add && row_ok && hf * 32 < N && !(p.out2_col0 > 0 && hf * 32 >= p.out2_col0);
+      const bool pre_dz = EPI != EPI_PLAIN && p.gate_mode >= 2 && row_ok && hf * 32 < 64 && !p.etile;
+      const bool pre_add = EPI == EPI_PLAIN && p.add && row_ok && hf * 32 < N && !(p.out2_col0 > 0 && hf * 32 >= p.out2_col0) &&
+                           !p.etile;
       if (pre_dz) {
         const float4* dr = reinterpret_cast<const float4*>(p.gate_dz + grow * p.gate_ld_dz + p.gate_c0 + hf * 32);
 #pragma unroll
@@ -238,6 +255,13 @@ __global__ void __launch_bounds__(kThreadsN, 1) gemm_nt_tc_kernel(const __grid_c
       }
       wait(&dfull[buf], use & 1, NP_E_DFULL);
       ptx::tc_fence_after();
+      if (p.etile == 1) {   // this row's 32 dz channels out of the staged tile (rows past T were zero-filled by TMA)
+        wait(efull, it & 1, NP_E_DFULL);
+        const float4* er = reinterpret_cast<const float4*>(ebuf + hf * kASub + (q * 32 + lane) * 128);
+#pragma unroll
+        for (int j = 0; j < 8; j++) pre[j] = er[j ^ (lane & 7)];
+        ptx::mbar_arrive(eempty);
+      }
       if constexpr (EPI == EPI_GATE_BWD_NOZ) {
         // ---- gate backward without the z output (the stack path): two passes of 16 gate channels keep the live
         //      registers under the 168 this kernel gets (the 32-channel form below spilled); the two dpre boxes of
@@ -276,7 +300,7 @@ __global__ void __launch_bounds__(kThreadsN, 1) gemm_nt_tc_kernel(const __grid_c
 #pragma unroll
             for (int k = 0; k < 4; k++) {
               const int i = 4 * jj + k;
-              float dz = row_ok ? dzs[k] : 0.f;
+              float dz = (row_ok || p.etile) ? dzs[k] : 0.f;
               if (p.gate_mode == 3) dz += dzp[i];
               const float sg = 0.5f * ptx::tanh_approx(0.5f * (a[i] + bsa[k])) + 0.5f;
               const float th = ptx::tanh_approx(g[i] + bta[k]);
@@ -427,7 +451,16 @@ __global__ void __launch_bounds__(kThreadsN, 1) gemm_nt_tc_kernel(const __grid_c
 #pragma unroll
           for (int i = 0; i < 32; i++) v[i] += __ldg(p.bias + ncol0 + c0 + i);
         }
-        if (p.add && row_ok && !second) {
+        if (p.etile == 2 && c0 < 64) {   // staged residual tile: sub-tile c0 / 32, this thread's row
+          wait(efull, it & 1, NP_E_DFULL);
+          const float4* er = reinterpret_cast<const float4*>(ebuf + (c0 >> 5) * kASub + (q * 32 + lane) * 128);
+#pragma unroll
+          for (int j = 0; j < 8; j++) {
+            const float4 a = er[j ^ (lane & 7)];
+            v[4 * j] += a.x; v[4 * j + 1] += a.y; v[4 * j + 2] += a.z; v[4 * j + 3] += a.w;
+          }
+          ptx::mbar_arrive(eempty);
+        } else if (p.add && row_ok && !second) {
           const float4* ar = reinterpret_cast<const float4*>(p.add + grow * p.ldadd + ncol0 + c0);
           const bool use_pre = pre_add && c0 == hf * 32;
 #pragma unroll
@@ -513,6 +546,17 @@ static bool map3(CUtensorMap* m, const float* base, int C, int T, int B, int box
   if (!enc) return false;
   cuuint64_t gdim[3] = {(cuuint64_t)C, (cuuint64_t)T, (cuuint64_t)B};
   cuuint64_t gstr[2] = {(cuuint64_t)C * 4, (cuuint64_t)C * 4 * (cuuint64_t)T};
+  cuuint32_t box[3] = {32, (cuuint32_t)box_rows, 1}, es[3] = {1, 1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), gdim, gstr, box, es,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+// (B, T, C) view with row pitch ld floats (a channel slice of a wider tensor)
+static bool map3ld(CUtensorMap* m, const float* base, int C, int ld, int T, int B, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return false;
+  cuuint64_t gdim[3] = {(cuuint64_t)C, (cuuint64_t)T, (cuuint64_t)B};
+  cuuint64_t gstr[2] = {(cuuint64_t)ld * 4, (cuuint64_t)ld * 4 * (cuuint64_t)T};
   cuuint32_t box[3] = {32, (cuuint32_t)box_rows, 1}, es[3] = {1, 1, 1};
   return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), gdim, gstr, box, es,
              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -609,14 +653,26 @@ int gemm_nt_tc(const NtTcSeg* segs, int nseg, int N, float* out, int ld_out, con
     return WNB_ERR_INVALID;
   }
   p.stg_boxes = p.mt == 2 ? 1 : 2;
+  p.maps[10] = p.maps[8];
+  if (opts && opts->stage_epilogue_operand && p.mt == 1) {
+    // 1: gate-backward dz slice (EPI_GATE_BWD_NOZ, R = 64 shorthand), 2: residual add of a <= 64-column primary output
+    const bool dz_ok = p.gate_mode >= 2 && p.gate_skip_z && p.gate_R == 64 && p.gate_c0 == 0 && gate_dz &&
+                       (reinterpret_cast<uintptr_t>(gate_dz) & 15) == 0 && p.gate_ld_dz % 4 == 0;
+    const int primary = out2 ? out2_col0 : N;
+    const bool add_ok = !p.gate_mode && add && !mask && primary == 64 && p.nblk == 1 &&
+                        (reinterpret_cast<uintptr_t>(add) & 15) == 0 && ldadd % 4 == 0;
+    if (dz_ok && map3ld(&p.maps[10], gate_dz, 64, p.gate_ld_dz, T, B, kTM)) p.etile = 1;
+    else if (add_ok && map3ld(&p.maps[10], add, 64, ldadd, T, B, kTM)) p.etile = 2;
+  }
+  const int ebytes = p.etile ? 2 * kASub : 0;
   const int stage_bytes = p.mt * kASub + N * 128;
-  int nst = (int)((227 * 1024 - 1024 - 512 - kEpiWarpsN * p.stg_boxes * kStg) / stage_bytes);
+  int nst = (int)((227 * 1024 - 1024 - 512 - kEpiWarpsN * p.stg_boxes * kStg - ebytes) / stage_bytes);
   static int max_stages = 0;
   if (!max_stages) { const char* e = getenv("WNB_NT_MAXSTAGES"); max_stages = e ? atoi(e) : 4; if (max_stages < 2) max_stages = 2; }
   if (nst > max_stages) nst = max_stages;
   if (nst < 2) { set_error("gemm_nt_tc: N too large"); return WNB_ERR_INVALID; }
   p.nstages = nst;
-  const size_t smem = (size_t)nst * stage_bytes + kEpiWarpsN * p.stg_boxes * kStg + 512 + 1024;
+  const size_t smem = (size_t)nst * stage_bytes + kEpiWarpsN * p.stg_boxes * kStg + ebytes + 512 + 1024;
   WNB_CUDA(ensure_dynamic_smem(reinterpret_cast<const void*>(gemm_nt_tc_kernel<false, 0>), smem));
   WNB_CUDA(ensure_dynamic_smem(reinterpret_cast<const void*>(gemm_nt_tc_kernel<false, 1>), smem));
   WNB_CUDA(ensure_dynamic_smem(reinterpret_cast<const void*>(gemm_nt_tc_kernel<false, 2>), smem));

@@ -29,6 +29,12 @@ static int pick_block(int total, const int* cands, int n) {
   return 0;
 }
 
+// WNB_STAGE_EPI=0 restores the per-lane global loads of the epilogue operands (A/B switch for the measurement)
+static int stage_epi() {
+  static const int on = [] { const char* e = getenv("WNB_STAGE_EPI"); return (e && e[0] == '0') ? 0 : 1; }();
+  return on;
+}
+
 static bool stack_supported(int R, int S, int Ap, int ks, int L) {
   if (!resblock_fwd_z_supported(R, Ap, ks)) return false;
   if (L < 1 || L > 64 /* wnb_stack_bwd's segment table, wgrad kMaxSeg */) return false;
@@ -156,7 +162,7 @@ WNB_API int wnb_stack_bwd(const float* xs, const float* haux, const float* zall,
       const float* wg = wgate + (size_t)l * 3 * R * (K1 + R);
       const NtTcSeg sg[4] = {{xin, R, -d, R, wg, 3 * R, K1 + R, 0, 0}, {xin, R, 0, R, wg, 3 * R, K1 + R, R, 0},
                              {haux, Ap, 0, Ap, wg, 3 * R, K1 + R, 2 * R, 0}, {dout, R, 0, R, wg, 3 * R, K1 + R, K1, 0}};
-      const NtTcOpts o{1, ldz, 1, dout ? 1 : 0, 1};
+      const NtTcOpts o{1, ldz, 1, dout ? 1 : 0, 1, stage_epi()};
       ProfScope ps(WNB_PROF_GATE_BWD, st);
       if ((rc = gemm_nt_tc(sg, dout ? 4 : 3, dout ? 3 * R : 2 * R, dxin /* z output suppressed */, R,
                            b1 + (size_t)l * 2 * R, nullptr, 0, nullptr, 0, 0, 0, B, T, st, dzl, dpre, nullptr, 0, 0,
@@ -167,13 +173,17 @@ WNB_API int wnb_stack_bwd(const float* xs, const float* haux, const float* zall,
     if (dhaux) {
       ProfScope ps(WNB_PROF_DX_GEMM, st);
       const NtTcSeg sx[2] = {{dpre, 2 * R, d, 2 * R, w1tl, R, 2 * R, 0, 0}, {dpre, 2 * R, 0, 2 * R, w1tl, K1, 2 * R, 0, R}};
+      const NtTcOpts ox{1, 0, 0, 0, 1, stage_epi()};
       if ((rc = gemm_nt_tc(sx, 2, R + Ap, dxin, R, nullptr, nullptr, 0, dout, R, 0, 0, B, T, st, nullptr, nullptr, dhaux,
-                           Ap, R)) != WNB_OK)
+                           Ap, R, nullptr, &ox)) != WNB_OK)
         return rc;
     } else {
       ProfScope ps(WNB_PROF_DX_GEMM, st);
       const NtTcSeg sx[2] = {{dpre, 2 * R, d, 2 * R, w1tl, K1, 2 * R, 0, 0}, {dpre, 2 * R, 0, 2 * R, w1tl, K1, 2 * R, 0, R}};
-      if ((rc = gemm_nt_tc(sx, 2, R, dxin, R, nullptr, nullptr, 0, dout, R, 0, 0, B, T, st)) != WNB_OK) return rc;
+      const NtTcOpts ox{1, 0, 0, 0, 1, stage_epi()};
+      if ((rc = gemm_nt_tc(sx, 2, R, dxin, R, nullptr, nullptr, 0, dout, R, 0, 0, B, T, st, nullptr, nullptr, nullptr, 0, 0,
+                           nullptr, &ox)) != WNB_OK)
+        return rc;
     }
     dout = dxin;
   }

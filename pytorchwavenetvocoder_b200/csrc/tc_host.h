@@ -38,6 +38,8 @@ struct NtTcOpts {
   int gate_fused_dz; // gate-backward shorthand with N == 192: accumulator columns 128..191 are added to dz
   int m_tiles;       // 2: a CTA tile is two 128-row time tiles sharing every weight chunk (plain epilogue, N <= 256):
                      //    halves the L2 -> SM weight traffic of the K >= 512 GEMMs (skip, dZ_all, post network)
+  int stage_epilogue_operand;   // 1: the gate-backward dz slice / a 64-column residual `add` reaches the epilogue as a TMA
+                                //    tile loaded by the producer warp instead of per-lane row loads (gate backward, dX)
 };
 // default of NtTcOpts::m_tiles for the K >= 512 GEMMs: 2, WNB_NT_MT=1 in the environment restores one tile per CTA
 int nt_default_m_tiles();
