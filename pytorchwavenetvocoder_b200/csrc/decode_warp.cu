@@ -376,6 +376,42 @@ __global__ void __launch_bounds__((W / CL) * 32 + 64, 1) decode_warp_kernel(cons
   }
 
   // ================================ consumer warps ================================
+  // aux column and every block's dilation-queue tap for time step `pos_t`, by threads t0, t0 + nt, ...  (used by the step
+  // prologue, and -- for the NEXT step -- by the warps that are idle while warp 0 picks the sample: neither depends on it)
+  auto fetch_aux_taps = [&](int pos_t, int t0, int nt) {
+    for (int e = t0; e < NU * kAp; e += nt) {
+      const int u = e >> 5, a = e & 31;
+      const int ug = min(u0 + u, p.B - 1);
+      float v = 0.f;
+      if (a < p.A) {
+        const int j = max(pos_t - p.n_pad, 0);
+        if (p.U > 0) {
+          const int tf = min(j / p.U, p.Th - 1), jj = j % p.U;
+          v = fmaf(__ldg(p.h + ((size_t)ug * p.A + a) * p.Th + tf), __ldg(p.up_w + jj), __ldg(p.up_b));
+        } else {
+          v = __ldg(p.h + ((size_t)ug * p.A + a) * p.Th + min(j, p.Th - 1));
+        }
+      }
+      hcol[e] = v;
+    }
+    for (int e = t0; e < NU * L * kR; e += nt) {
+      const int r = e & 63;
+      const int ul = e >> 6;                                 // u * L + l  (no runtime division: NU <= 4)
+      const int u = (ul >= L) + (ul >= 2 * L) + (ul >= 3 * L);
+      const int l = ul - u * L;
+      const int ug = min(u0 + u, p.B - 1);
+      const int d = p.dil[l];
+      float v = 0.f;
+      // tap = this layer's input at time pos_t - d: ring slot (pos_t - d) % d == pos_t % d, i.e. the slot that is
+      // overwritten with the time-`pos_t` input later in THAT step -> all reads happen before its first barrier
+      if (pos_t - d >= 0) {
+        const float* q = p.queues + (size_t)ug * p.q_per_utt + p.qoff[l];
+        v = __ldcg(q + (size_t)(pos_t & (d - 1)) * kR + r);
+      }
+      qtap[e] = v;
+    }
+  };
+  bool have_next = false;    // hcol / qtap already hold the next step's values (prefetched during the pick)
   float* my_pre = pre_s + warp * GV * NU;
   long long tacc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   long long tlast = clock64();
@@ -402,37 +438,8 @@ __global__ void __launch_bounds__((W / CL) * 32 + 64, 1) decode_warp_kernel(cons
       }
       cur[e] = v;
     }
-    for (int e = tid; e < NU * kAp; e += kCons) {
-      const int u = e >> 5, a = e & 31;
-      const int ug = min(u0 + u, p.B - 1);
-      float v = 0.f;
-      if (a < p.A) {
-        const int j = max(pos - p.n_pad, 0);
-        if (p.U > 0) {
-          const int tf = min(j / p.U, p.Th - 1), jj = j % p.U;
-          v = fmaf(__ldg(p.h + ((size_t)ug * p.A + a) * p.Th + tf), __ldg(p.up_w + jj), __ldg(p.up_b));
-        } else {
-          v = __ldg(p.h + ((size_t)ug * p.A + a) * p.Th + min(j, p.Th - 1));
-        }
-      }
-      hcol[e] = v;
-    }
-    for (int e = tid; e < NU * L * kR; e += kCons) {
-      const int r = e & 63;
-      const int ul = e >> 6;                                 // u * L + l  (no runtime division: NU <= 4)
-      const int u = (ul >= L) + (ul >= 2 * L) + (ul >= 3 * L);
-      const int l = ul - u * L;
-      const int ug = min(u0 + u, p.B - 1);
-      const int d = p.dil[l];
-      float v = 0.f;
-      // tap = this layer's input at time pos - d: ring slot (pos - d) % d == pos % d, i.e. the slot that is
-      // overwritten with the time-`pos` input later in THIS step -> all reads happen here, before the barrier
-      if (pos - d >= 0) {
-        const float* q = p.queues + (size_t)ug * p.q_per_utt + p.qoff[l];
-        v = __ldcg(q + (size_t)(pos & (d - 1)) * kR + r);
-      }
-      qtap[e] = v;
-    }
+    if (!have_next) fetch_aux_taps(pos, tid, kCons);
+    have_next = false;
     WNB_T(0);
     cons_sync_w<WP>();     // (CTA-local: the prologue only touches this CTA's shared memory)
     WNB_T(1);
@@ -702,7 +709,11 @@ __global__ void __launch_bounds__((W / CL) * 32 + 64, 1) decode_warp_kernel(cons
       }
       phase_sync(NU * kQ / 2);
       WNB_T(9);
-      // ---------------- pick: warp u handles utterance u ----------------
+      // ---------------- pick: warp u handles utterance u; the other warps fetch the next step's aux column and taps ------
+      if (warp >= NU && pos < last_pos && kCons > 32 * NU) {
+        fetch_aux_taps(pos + 1, tid - 32 * NU, kCons - 32 * NU);
+      }
+      have_next = pos < last_pos && kCons > 32 * NU;
       if (warp < NU) {
         const int u = warp;
         const float* lg = logit + u * kQ;

@@ -45,6 +45,7 @@ struct alignas(64) Params {
   // bias = sigmoid-branch bias, bias2 = tanh-branch bias (already offset by gate_c0)
   const float* gate_dz; const float* bias2;
   int gate_mode, gate_c0, gate_R;
+  int gate_gc;   // gate channels per tile: N == 2 * gate_gc (64, or 128 for the composed path) [+ 64 dz columns in mode 3]
   // split output: columns >= out2_col0 (> 0) are reduce-added into maps[9] at column c - out2_col0; bias / add /
   // mask / ReLU apply to the primary columns only
   int out2_col0;
@@ -322,8 +323,9 @@ __global__ void __launch_bounds__(kThreadsN, 1) gemm_nt_tc_kernel(const __grid_c
         continue;
       }
       if constexpr (EPI == EPI_GATE) {
-        // ---- gate epilogues: pair sigmoid column c with tanh column 64 + c ----
-        for (int c0 = hf * 32; c0 < 64; c0 += 64) {
+        // ---- gate epilogues: pair sigmoid column c with tanh column GC + c (GC = 64 or 128 gate channels per tile) ----
+        const int GC = p.gate_gc;
+        for (int c0 = hf * 32; c0 < GC; c0 += 64) {
           float a[32], g[32];
           {
             float lo[16], hi[16];
@@ -332,8 +334,8 @@ __global__ void __launch_bounds__(kThreadsN, 1) gemm_nt_tc_kernel(const __grid_c
             ptx::tc_wait_ld();
 #pragma unroll
             for (int i = 0; i < 16; i++) { a[i] = lo[i]; a[16 + i] = hi[i]; }
-            ptx::tmem_ld16(tmem + lane_base + buf * N + 64 + c0, lo);
-            ptx::tmem_ld16(tmem + lane_base + buf * N + 64 + c0 + 16, hi);
+            ptx::tmem_ld16(tmem + lane_base + buf * N + GC + c0, lo);
+            ptx::tmem_ld16(tmem + lane_base + buf * N + GC + c0 + 16, hi);
             ptx::tc_wait_ld();
 #pragma unroll
             for (int i = 0; i < 16; i++) { g[i] = lo[i]; g[16 + i] = hi[i]; }
@@ -341,14 +343,16 @@ __global__ void __launch_bounds__(kThreadsN, 1) gemm_nt_tc_kernel(const __grid_c
           float dzp[32];
           if (p.gate_mode == 3) {
             float lo[16], hi[16];
-            ptx::tmem_ld16(tmem + lane_base + buf * N + 128 + c0, lo);
-            ptx::tmem_ld16(tmem + lane_base + buf * N + 128 + c0 + 16, hi);
+            ptx::tmem_ld16(tmem + lane_base + buf * N + 2 * GC + c0, lo);
+            ptx::tmem_ld16(tmem + lane_base + buf * N + 2 * GC + c0 + 16, hi);
             ptx::tc_wait_ld();
 #pragma unroll
             for (int i = 0; i < 16; i++) { dzp[i] = lo[i]; dzp[16 + i] = hi[i]; }
           }
-          ptx::tc_fence_before();
-          ptx::mbar_arrive(&dempty[buf]);   // this warp's share of the accumulator is in registers
+          if (c0 + 64 >= GC) {   // this warp's last chunk: its share of the accumulator is in registers
+            ptx::tc_fence_before();
+            ptx::mbar_arrive(&dempty[buf]);
+          }
           float dzv[32];
           if (p.gate_mode == 1) {
             // forward: z only
@@ -357,10 +361,12 @@ __global__ void __launch_bounds__(kThreadsN, 1) gemm_nt_tc_kernel(const __grid_c
               const float sg = 0.5f * ptx::tanh_approx(0.5f * (a[i] + __ldg(p.bias + c0 + i))) + 0.5f;
               dzv[i] = sg * ptx::tanh_approx(g[i] + __ldg(p.bias2 + c0 + i));
             }
-            unsigned char* sb = stg + (nstore & 1) * kStg;
+            unsigned char* sb = stg + (nstore & box_mask) * kStg;
             {
               const long long tb = PROF ? clock64() : 0;
-              if (lane == 0) ptx::bulk_wait_read<1>();
+              if (lane == 0) {
+                if (box_mask) ptx::bulk_wait_read<1>(); else ptx::bulk_wait_read<0>();
+              }
               __syncwarp();
               if constexpr (PROF) acc[NP_E_BULK] += clock64() - tb;
             }
@@ -378,9 +384,11 @@ __global__ void __launch_bounds__(kThreadsN, 1) gemm_nt_tc_kernel(const __grid_c
             continue;
           }
           if (row_ok) {
+            const float4* dr = reinterpret_cast<const float4*>(p.gate_dz + grow * p.gate_ld_dz + p.gate_c0 + c0);
+            const bool use_pre = pre_dz && c0 == hf * 32;   // the first chunk was requested before the accumulator wait
 #pragma unroll
             for (int j = 0; j < 8; j++) {
-              const float4 d4 = pre[j];   // requested before the accumulator wait (c0 == hf * 32)
+              const float4 d4 = use_pre ? pre[j] : __ldg(dr + j);
               dzv[4 * j] = d4.x; dzv[4 * j + 1] = d4.y; dzv[4 * j + 2] = d4.z; dzv[4 * j + 3] = d4.w;
             }
           } else {
@@ -404,10 +412,12 @@ __global__ void __launch_bounds__(kThreadsN, 1) gemm_nt_tc_kernel(const __grid_c
           for (int which = 0; which < 3; which++) {
             if (which == 0 && p.gate_skip_z) continue;   // (constant trip count: a / g / dzv stay in registers)
             const float* src = which == 0 ? dzv : (which == 1 ? a : g);
-            unsigned char* sb = stg + (nstore & 1) * kStg;
+            unsigned char* sb = stg + (nstore & box_mask) * kStg;
             {
               const long long tb = PROF ? clock64() : 0;
-              if (lane == 0) ptx::bulk_wait_read<1>();
+              if (lane == 0) {
+                if (box_mask) ptx::bulk_wait_read<1>(); else ptx::bulk_wait_read<0>();
+              }
               __syncwarp();
               if constexpr (PROF) acc[NP_E_BULK] += clock64() - tb;
             }
@@ -592,7 +602,7 @@ int gemm_nt_tc(const NtTcSeg* segs, int nseg, int N, float* out, int ld_out, con
   }
   Params p;
   memset(&p, 0, sizeof(p));
-  const int nbox = gate ? 64 : (N > 256 ? 256 : N);
+  const int nbox = gate ? N / 2 : (N > 256 ? 256 : N);   // (gate: two boxes of GC = N/2 rows, sigmoid rows and tanh rows)
   for (int s = 0; s < nseg; s++) {
     if (segs[s].K % 32 != 0) { set_error("gemm_nt_tc: K must be a multiple of 32"); return WNB_ERR_INVALID; }
     if (!map3(&p.maps[s], segs[s].a, segs[s].CA, T, B, kTM) ||
@@ -613,9 +623,11 @@ int gemm_nt_tc(const NtTcSeg* segs, int nseg, int N, float* out, int ld_out, con
     }
     if (reinterpret_cast<uintptr_t>(bias) & 15) { set_error("gemm_nt_tc: gate bias must be 16-byte aligned"); return WNB_ERR_INVALID; }
     p.gate_dz = gate_dz; p.bias = bias; p.bias2 = bias + 64; p.gate_mode = fused_dz ? 3 : 2; p.gate_c0 = 0; p.gate_R = 64;
+    p.gate_gc = 64;
   }
-  if (gate) {      // general form: 64 gate channels [c0, c0+64) of R; W rows c0.. (sigmoid) and R+c0.. (tanh)
-    if (N != 128 || gate->R % 64 != 0 || gate->c0 % 64 != 0 || gate->c0 + 64 > gate->R || !gate->bias_sig ||
+  if (gate) {      // general form: GC = N/2 (64 or 128) gate channels [c0, c0+GC) of R; W rows c0.. (sigmoid) and R+c0.. (tanh)
+    const int GC = N / 2;
+    if ((N != 128 && N != 256) || gate->R % GC != 0 || gate->c0 % GC != 0 || gate->c0 + GC > gate->R || !gate->bias_sig ||
         !gate->bias_tanh || (gate->mode != 1 && gate->mode != 2) || (gate->mode == 2 && (!gate->dz || !gate->dpre))) {
       set_error("gemm_nt_tc: bad gate configuration");
       return WNB_ERR_INVALID;
@@ -626,7 +638,7 @@ int gemm_nt_tc(const NtTcSeg* segs, int nseg, int N, float* out, int ld_out, con
     }
     for (int s = 0; s < nseg; s++) { p.seg[s].b_n0 = gate->c0; p.seg[s].b_n1 = gate->R + gate->c0; }
     p.bias = gate->bias_sig; p.bias2 = gate->bias_tanh; p.gate_dz = gate->dz;
-    p.gate_mode = gate->mode; p.gate_c0 = gate->c0; p.gate_R = gate->R;
+    p.gate_mode = gate->mode; p.gate_c0 = gate->c0; p.gate_R = gate->R; p.gate_gc = GC;
   }
   if (out2) {
     if (gate_dz || out2_col0 <= 0 || out2_col0 % 32 != 0 || out2_col0 >= N || !map3(&p.maps[9], out2, ld_out2, T, B, 32)) {
@@ -648,8 +660,8 @@ int gemm_nt_tc(const NtTcSeg* segs, int nseg, int N, float* out, int ld_out, con
   p.relu_out = relu_out; p.accumulate = accumulate;
   p.nacc = N <= 256 ? 2 : 1;
   p.mt = (opts && opts->m_tiles == 2) ? 2 : 1;
-  if (p.mt == 2 && (p.gate_mode || N > 256)) {
-    set_error("gemm_nt_tc: m_tiles = 2 is for plain epilogues with N <= 256");
+  if (p.mt == 2 && ((p.gate_mode && !gate) || N > 256)) {
+    set_error("gemm_nt_tc: m_tiles = 2 is for plain / general gate epilogues with N <= 256");
     return WNB_ERR_INVALID;
   }
   p.stg_boxes = p.mt == 2 ? 1 : 2;

@@ -466,6 +466,15 @@ static bool composed_tc_supported(int R, int S, int Ap, int ks) {
 int resblock_fwd_tc(const FwdParams& p, cudaStream_t st);
 bool resblock_fwd_tc_supported(int R, int S, int Ap, int ks);
 
+// gate channels per composed gate GEMM, and the column blocking / two-time-tile option of the plain composed GEMMs
+static int composed_gc(int R) { return (R % 128 == 0) ? 128 : 64; }
+static NtTcOpts plain_opts(int N) {
+  NtTcOpts o{1, 0, 0, 0, 1, 0};
+  if (N > 256 && N % 256 == 0) o.n_blocks = N / 256;
+  if (N / o.n_blocks <= 256) o.m_tiles = nt_default_m_tiles();
+  return o;
+}
+
 // Forward of one residual block for shapes outside the fused kernel: R/64 gate GEMMs (N = 128: 64 sigmoid + 64
 // tanh rows of W1, K = ks*R + Ap streamed) with the gate epilogue writing z, then the res GEMM (+bias, +x) and the
 // skip GEMM (+bias, store or reduce-add).  z (B,T,R) goes through p.zsave.
@@ -475,18 +484,27 @@ static int resblock_fwd_composed(const FwdParams& p, cudaStream_t st) {
   int ns = 0, rc;
   for (int j = 0; j < ks; j++) segs[ns++] = NtTcSeg{p.xin, R, -(ks - 1 - j) * p.d, R, p.w1, 2 * R, K1, j * R, 0};
   segs[ns++] = NtTcSeg{p.haux, Ap, 0, Ap, p.w1, 2 * R, K1, ks * R, 0};
-  for (int c0 = 0; c0 < R; c0 += 64) {
+  // 128 gate channels (N = 256) and two time tiles per CTA tile when R allows: the activation tile [x taps | aux] is
+  // re-read R/128 instead of R/64 times and every weight chunk serves 256 rows (these GEMMs are L2 -> SM bound)
+  const int GC = composed_gc(R);
+  const NtTcOpts og{1, 0, 0, 0, nt_default_m_tiles(), 0};
+  for (int c0 = 0; c0 < R; c0 += GC) {
     const NtTcGate g{1, c0, R, p.b1 + c0, p.b1 + R + c0, nullptr, nullptr};
-    if ((rc = gemm_nt_tc(segs, ns, 128, p.zsave, R, nullptr, nullptr, 0, nullptr, 0, 0, 0, p.B, p.T, st, nullptr, nullptr,
-                         nullptr, 0, 0, &g)) != WNB_OK)
+    if ((rc = gemm_nt_tc(segs, ns, 2 * GC, p.zsave, R, nullptr, nullptr, 0, nullptr, 0, 0, 0, p.B, p.T, st, nullptr, nullptr,
+                         nullptr, 0, 0, &g, &og)) != WNB_OK)
       return rc;
   }
   if (p.xout) {
     const NtTcSeg sr[1] = {{p.zsave, R, 0, R, p.w2, R + S, R, 0, 0}};
-    if ((rc = gemm_nt_tc(sr, 1, R, p.xout, R, p.b2, nullptr, 0, p.xin, R, 0, 0, p.B, p.T, st)) != WNB_OK) return rc;
+    const NtTcOpts o = plain_opts(R);
+    if ((rc = gemm_nt_tc(sr, 1, R / o.n_blocks, p.xout, R, p.b2, nullptr, 0, p.xin, R, 0, 0, p.B, p.T, st, nullptr, nullptr,
+                         nullptr, 0, 0, nullptr, &o)) != WNB_OK)
+      return rc;
   }
   const NtTcSeg ss[1] = {{p.zsave, R, 0, R, p.w2, R + S, R, 0, R}};
-  return gemm_nt_tc(ss, 1, S, p.skip, S, p.b2 + R, nullptr, 0, nullptr, 0, 0, p.skip_init ? 0 : 1, p.B, p.T, st);
+  const NtTcOpts o = plain_opts(S);
+  return gemm_nt_tc(ss, 1, S / o.n_blocks, p.skip, S, p.b2 + R, nullptr, 0, nullptr, 0, 0, p.skip_init ? 0 : 1, p.B, p.T, st,
+                    nullptr, nullptr, nullptr, 0, 0, nullptr, &o);
 }
 
 }  // namespace wnb
@@ -560,27 +578,36 @@ WNB_API int wnb_resblock_bwd(const float* xin, const float* haux, const float* d
   if (math_mode == WNB_MATH_TF32 && !tc_fused_shape && composed_tc_supported(R, S, Ap, ks)) {
     // ---------------- composed tensor-core backward for general shapes ----------------
     float* dz = dxin;   // (B,T,R) scratch until the dX GEMM overwrites it
+    const NtTcOpts opl = plain_opts(R);
     if (dout) {
       const NtTcSeg sz[2] = {{dout, R, 0, R, w2t, R, R + S, 0, 0}, {dskip, S, 0, S, w2t, R, R + S, R, 0}};
-      if ((rc = gemm_nt_tc(sz, 2, R, dz, R, nullptr, nullptr, 0, nullptr, 0, 0, 0, B, T, st)) != WNB_OK) return rc;
+      if ((rc = gemm_nt_tc(sz, 2, R / opl.n_blocks, dz, R, nullptr, nullptr, 0, nullptr, 0, 0, 0, B, T, st, nullptr, nullptr,
+                           nullptr, 0, 0, nullptr, &opl)) != WNB_OK)
+        return rc;
     } else {
       const NtTcSeg sz[1] = {{dskip, S, 0, S, w2t, R, R + S, R, 0}};
-      if ((rc = gemm_nt_tc(sz, 1, R, dz, R, nullptr, nullptr, 0, nullptr, 0, 0, 0, B, T, st)) != WNB_OK) return rc;
+      if ((rc = gemm_nt_tc(sz, 1, R / opl.n_blocks, dz, R, nullptr, nullptr, 0, nullptr, 0, 0, 0, B, T, st, nullptr, nullptr,
+                           nullptr, 0, 0, nullptr, &opl)) != WNB_OK)
+        return rc;
     }
     NtTcSeg sg[4];
     int ns = 0;
     for (int j = 0; j < ks; j++) sg[ns++] = NtTcSeg{xin, R, -(ks - 1 - j) * dilation, R, w1, 2 * R, K1, j * R, 0};
     sg[ns++] = NtTcSeg{haux, Ap, 0, Ap, w1, 2 * R, K1, ks * R, 0};
-    for (int c0 = 0; c0 < R; c0 += 64) {   // gate recompute + z + dpre, 64 gate channels per launch
+    const int GC = composed_gc(R);
+    const NtTcOpts og{1, 0, 0, 0, nt_default_m_tiles(), 0};
+    for (int c0 = 0; c0 < R; c0 += GC) {   // gate recompute + z + dpre, GC gate channels per launch
       const NtTcGate g{2, c0, R, b1 + c0, b1 + R + c0, dz, dpre};
-      if ((rc = gemm_nt_tc(sg, ns, 128, z, R, nullptr, nullptr, 0, nullptr, 0, 0, 0, B, T, st, nullptr, nullptr, nullptr, 0,
-                           0, &g)) != WNB_OK)
+      if ((rc = gemm_nt_tc(sg, ns, 2 * GC, z, R, nullptr, nullptr, 0, nullptr, 0, 0, 0, B, T, st, nullptr, nullptr, nullptr, 0,
+                           0, &g, &og)) != WNB_OK)
         return rc;
     }
     {  // dxin = dout + sum_j dpre(t + (ks-1-j)d) W1[:, tap j]
       NtTcSeg sx[3];
       for (int j = 0; j < ks; j++) sx[j] = NtTcSeg{dpre, 2 * R, (ks - 1 - j) * dilation, 2 * R, w1t, K1, 2 * R, 0, j * R};
-      if ((rc = gemm_nt_tc(sx, ks, R, dxin, R, nullptr, nullptr, 0, dout, R, 0, 0, B, T, st)) != WNB_OK) return rc;
+      if ((rc = gemm_nt_tc(sx, ks, R / opl.n_blocks, dxin, R, nullptr, nullptr, 0, dout, R, 0, 0, B, T, st, nullptr, nullptr,
+                           nullptr, 0, 0, nullptr, &opl)) != WNB_OK)
+        return rc;
     }
     if (dhaux) {
       const NtTcSeg sh[1] = {{dpre, 2 * R, 0, 2 * R, w1t, K1, 2 * R, 0, ks * R}};

@@ -29,9 +29,12 @@ static int pick_block(int total, const int* cands, int n) {
   return 0;
 }
 
-// WNB_STAGE_EPI=0 restores the per-lane global loads of the epilogue operands (A/B switch for the measurement)
+// WNB_STAGE_EPI=1 stages the epilogue operands (gate-backward dz slice, dX residual) through TMA tiles loaded by the producer
+// warp instead of per-lane global row loads.  Built on the ncu finding that the epilogue warps stall on L1TEX, measured
+// on B200 -- and SLOWER: gate backward 59.3 -> 66.2 us, dX 51.6 -> 58.8 us per block (one pipeline stage less and one more
+// serial job for the single producer thread cost more than the row loads).  Off by default; kept as a measured negative.
 static int stage_epi() {
-  static const int on = [] { const char* e = getenv("WNB_STAGE_EPI"); return (e && e[0] == '0') ? 0 : 1; }();
+  static const int on = [] { const char* e = getenv("WNB_STAGE_EPI"); return (e && e[0] == '1') ? 1 : 0; }();
   return on;
 }
 
