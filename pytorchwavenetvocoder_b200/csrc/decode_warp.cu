@@ -503,7 +503,10 @@ __global__ void __launch_bounds__((W / CL) * 32 + 64, 1) decode_warp_kernel(cons
         st_both<CL>(&zs[u * kR + c], sigmoidf_(a) * tanhf(g), peer_delta, xs_.peer_bar());
       }
       WNB_T(3);
-      phase_sync(NU * kR / 2);
+      // CL == 2: the K half of the residual GEMV that multiplies THIS CTA's gate channels runs while the peer's half of z
+      // is in flight; the other half follows the wait
+      phase_arrive(NU * kR / 2);
+      if constexpr (CL == 1) phase_wait();
       WNB_T(4);
       // ---------------- phase B: residual 1x1 (split K) ----------------
       float skip_b[SL];
@@ -513,7 +516,9 @@ __global__ void __launch_bounds__((W / CL) * 32 + 64, 1) decode_warp_kernel(cons
         for (int i = 0; i < NU * CH; i++) racc[i] = 0.f;
         const float* rc = ring.acquire();
 #pragma unroll
-        for (int j = 0; j < 2; j++) {
+        for (int jj = 0; jj < 2; jj++) {
+          const int j = (CL == 2) ? (jj ^ rank) : jj;
+          if (CL == 2 && jj == 1) phase_wait();
           const float4* wp = reinterpret_cast<const float4*>(rc + (size_t)(j * WP + warp) * (CH * 32)) + lane;
           float4 wv[CH / 4];
 #pragma unroll
