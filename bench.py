@@ -370,12 +370,23 @@ def run_ours(args):
                 roof_all.append({"kernel": name, "launches_timed": n, "mean_launch_ms": mean,
                                  "share_of_step": tot / ms_prof, "algorithmic_bytes_per_launch": alg[name],
                                  "achieved": a, "frac": a / hbm, "traffic": TRAFFIC_NCU_STACK.get(name)})
+            # the four per-block backward kernels against what ONE fused kernel per block would have to move
+            # (x, dout, dZ_all slice, aux in; dx out = s*(4R+Ap) per sample; DESIGN.md 3.2 says why it is not built)
+            byk = {r["kernel"]: r for r in roof_all}
+            fused_ideal = None
+            if all(k in byk for k in ("gate_bwd", "dx_gemm", "dw1", "dw2res")):
+                t_blk = (byk["gate_bwd"]["mean_launch_ms"] + byk["dx_gemm"]["mean_launch_ms"]
+                         + byk["dw1"]["mean_launch_ms"] / L + byk["dw2res"]["mean_launch_ms"] / max(L - 1, 1))
+                ideal = bt4 * (4 * R + Ap)
+                fused_ideal = {"bytes_per_block": ideal, "ms_per_block_now": t_blk,
+                               "achieved": ideal / (t_blk * 1e-3) / 1e9, "frac": ideal / (t_blk * 1e-3) / 1e9 / hbm,
+                               "note": "gate_bwd + dx + dW1/L + dW2res/(L-1) per block vs s*(4R+Ap)*B*T"}
             top = max(roof_all, key=lambda r: r["share_of_step"])
             roof = {"kernel": "%s (tf32, deferred-skip stack)" % top["kernel"], "bound": "hbm", "achieved": top["achieved"],
                     "peak": hbm, "unit": "GB/s", "frac": top["frac"], "traffic": top["traffic"], "peak_source": how,
                     "algorithmic_bytes_per_launch": top["algorithmic_bytes_per_launch"],
                     "mean_launch_ms": top["mean_launch_ms"], "launches_timed": top["launches_timed"],
-                    "share_of_step": top["share_of_step"],
+                    "share_of_step": top["share_of_step"], "fused_ideal": fused_ideal,
                     "measured_on": "%d extra steps after the timed region with per-launch CUDA events "
                                    "(%.3f ms/step there; the events stay out of the timed steps)"
                                    % (args.steps, ms_prof / args.steps)}
@@ -431,15 +442,17 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of the fused block kernel from the ncu --set full
-# capture committed under profiles/ (filled in by hand from that capture; None = not captured yet)
-# tf32: profiles/r1_ncu_resblock_fwd_tc_summary.txt launch 1 (layer 1): 448.57 MB read + 365.57 MB write
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full captures committed under profiles/
+# (filled in by hand from those captures; None = not captured)
+# per-block fused forward with skip accumulation (wnb_resblock_fwd): profiles/r1_ncu_resblock_fwd_tc_summary.txt
 TRAFFIC_NCU = {"fp32": None, "tf32": 814.14e6}
-# kernel kinds timed by wnb_profile_read (WNB_PROF_* order) and their ncu DRAM bytes per launch (None = not captured)
+# kernel kinds timed by wnb_profile_read (WNB_PROF_* order) and their ncu DRAM bytes per launch, round 2:
+# profiles/r2_ncu_fwdz_summary.txt (block forward: 70.9 MB read + 43.5 MB written -- the x(t-d) halo and part of the
+# z / xout stores live in the 126 MB L2), r2_ncu_nt_summary.txt (launch 0 skip GEMM, 5 dZ_all GEMM, 8 gate backward of a
+# block with a residual input, 9 its dX), r2_ncu_wg_summary.txt (2 dW1, 3 dW2res, 4/5 dWskip)
 STACK_KINDS = ["fwd_block", "skip_gemm", "dzall_gemm", "gate_bwd", "dx_gemm", "dw1", "dw2res", "dwskip"]
-# profiles/r1_ncu_gate_bwd_summary.txt: gate backward 165.4 MB read + 56.2 MB written (part of dout / dpre stays in
-# L2 between kernels), dx 165.3 + 39.5 MB
-TRAFFIC_NCU_STACK = {"gate_bwd": 221.58e6, "dx_gemm": 204.85e6}
+TRAFFIC_NCU_STACK = {"fwd_block": 114.46e6, "skip_gemm": 1807.5e6, "dzall_gemm": 1740.2e6, "gate_bwd": 223.97e6,
+                     "dx_gemm": 204.21e6, "dw1": 4896.0e6, "dw2res": 2741.8e6, "dwskip": 1610.2e6}
 
 
 def run_decode(args, dev, rank, world, dist):
@@ -537,7 +550,11 @@ def run_decode(args, dev, rank, world, dist):
 
 
 # ncu dram__bytes_read.sum / dram__bytes_write.sum of ONE decode launch (profiles/r2_ncu_decode_*.txt); None = not captured
-DECODE_DRAM_NCU = None
+# profiles/r2_ncu_decode_summary.txt: decode_warp_kernel<1,16,1,2>, 64 utterances x (3069 warm-up + 1000) steps, 192 ms
+DECODE_DRAM_NCU = {"dram_read_bytes": 9.99e6, "dram_write_bytes": 59.75e6, "steps": 4069, "utterances": 64,
+                   "bytes_per_utterance_step": (9.99e6 + 59.75e6) / (64 * 4069),
+                   "l2_to_sm_bytes": 36325948200 * 32.0,
+                   "note": "the 786 KB/utterance dilation queues are written back once; weights and queue reads are L2 hits"}
 
 
 def _ref_nets():
