@@ -396,7 +396,7 @@ def run_ours(args):
             "warmup": args.warmup, "ms_per_step": per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "tf32" if args.math == "tf32" else "f32", "data": "synthetic",
             "config": {"workload": ("configs[1]: arctic/sd 16kHz " if CFG == (256, 28, 64, 512, 10, 3, 2, 80) else "custom: ") +
-                                   "WaveNet%s batch %d x %d (20000 + rf window) per GPU, Adam, loss on [rf:]"
+                                   "WaveNet%s batch %d x %d (nominal batch length + rf window) per GPU, Adam, loss on [rf:]"
                                    % (str(CFG).replace(" ", ""), BATCH, int(T)),
                        "global_batch": world * BATCH, "seq_len": int(T), "parallelism": "dp%d" % world,
                        "math": args.math, "storage": "fp32 channels-last",

@@ -412,6 +412,8 @@ __global__ void __launch_bounds__((W / CL) * 32 + 64, 1) decode_warp_kernel(cons
     }
   };
   bool have_next = false;    // hcol / qtap already hold the next step's values (prefetched during the pick)
+  float uni_next = 0.f;      // sampling: the uniform of generated sample `uni_for`, drawn one step ahead
+  int uni_for = -1;
   float* my_pre = pre_s + warp * GV * NU;
   long long tacc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   long long tlast = clock64();
@@ -496,7 +498,18 @@ __global__ void __launch_bounds__((W / CL) * 32 + 64, 1) decode_warp_kernel(cons
       WNB_T(2);
       warp_reduce_scatter<NU * GV>(acc, my_pre, lane);
       __syncwarp();
-      if (lane < CH * NU) {
+      if constexpr (2 * CH * NU <= 32) {
+        // sigmoid on lanes [0, CH*NU), tanh on the next CH*NU lanes (the two transcendental chains run side by side),
+        // the product meets through one shuffle; same expressions, same rounding
+        constexpr int NG = CH * NU;
+        const int gl = lane % NG;
+        const int u = gl / CH, cc = gl % CH, c = vw * CH + cc;
+        float part = 0.f;
+        if (lane < NG) part = sigmoidf_(my_pre[u * GV + cc] + gate_bs);
+        else if (lane < 2 * NG) part = tanhf(my_pre[u * GV + CH + cc] + gate_bt);
+        const float other = __shfl_down_sync(0xffffffffu, part, NG);
+        if (lane < NG) st_both<CL>(&zs[u * kR + c], part * other, peer_delta, xs_.peer_bar());
+      } else if (lane < CH * NU) {
         const int u = lane / CH, cc = lane % CH, c = vw * CH + cc;
         const float a = my_pre[u * GV + cc] + gate_bs;
         const float g = my_pre[u * GV + CH + cc] + gate_bt;
@@ -510,7 +523,14 @@ __global__ void __launch_bounds__((W / CL) * 32 + 64, 1) decode_warp_kernel(cons
       WNB_T(4);
       // ---------------- phase B: residual 1x1 (split K) ----------------
       float skip_b[SL];
-      {
+      const bool last_block = l + 1 == L;   // its residual output is discarded (wavenet.py:230-238): no GEMV, no hand-over
+      if (last_block) {
+        if constexpr (CL == 2) phase_wait();          // the skip GEMV below still needs the peer's half of z
+        const float* rc = ring.acquire();             // (the chunk also carries the skip bias)
+#pragma unroll
+        for (int e = 0; e < SL; e++) skip_b[e] = rc[kWresFloats / CL + kR + vw * SV + lane * SL + e];
+        ring.release();
+      } else {
         float racc[NU * CH];
 #pragma unroll
         for (int i = 0; i < NU * CH; i++) racc[i] = 0.f;
@@ -552,7 +572,7 @@ __global__ void __launch_bounds__((W / CL) * 32 + 64, 1) decode_warp_kernel(cons
         }
       }
       WNB_T(5);
-      phase_arrive(NU * kR / 2);   // the residual outputs are on their way to the peer while the skip GEMV runs
+      if (!last_block) phase_arrive(NU * kR / 2);   // the residual outputs travel to the peer while the skip GEMV runs
       // ---------------- phase B': skip 1x1, lanes own outputs SV*warp + SL*lane (+e) ----------------
       if (want) {
         // (CL == 2 leaves 2 warps per scheduler: a single accumulator per output would make the K loop one dependent
@@ -603,7 +623,7 @@ __global__ void __launch_bounds__((W / CL) * 32 + 64, 1) decode_warp_kernel(cons
         }
       }
       WNB_T(6);
-      phase_wait();
+      if (!last_block) phase_wait();     // (after the last block the post network's first hand-over is the barrier)
       WNB_T(7);
     }
 
@@ -674,9 +694,9 @@ __global__ void __launch_bounds__((W / CL) * 32 + 64, 1) decode_warp_kernel(cons
       {
         // logit o = QV*warp + (lane % QV); when QV == 16 the two half-warps split K (even / odd k)
         const int lo = lane % QV, ksel = lane / QV;
-        float s[NU];
+        float s[NU], s_b[NU];
 #pragma unroll
-        for (int u = 0; u < NU; u++) s[u] = 0.f;
+        for (int u = 0; u < NU; u++) { s[u] = 0.f; s_b[u] = 0.f; }
 #pragma unroll 1
         for (int c = 0; c < kS / (2 * KPC); c++) {
           const float* pc = ring.acquire() + warp * QV + lo;
@@ -692,7 +712,8 @@ __global__ void __launch_bounds__((W / CL) * 32 + 64, 1) decode_warp_kernel(cons
 #pragma unroll
                 for (int u = 0; u < NU; u++) {
                   const float x = kk == 0 ? xv[u].x : kk == 1 ? xv[u].y : kk == 2 ? xv[u].z : xv[u].w;
-                  s[u] = fmaf(wv, x, s[u]);
+                  if (CL == 2 && (kk & 2)) s_b[u] = fmaf(wv, x, s_b[u]);   // (second accumulator: see the skip GEMV)
+                  else s[u] = fmaf(wv, x, s[u]);
                 }
               }
             }
@@ -702,7 +723,7 @@ __global__ void __launch_bounds__((W / CL) * 32 + 64, 1) decode_warp_kernel(cons
         const float bv = post_b2;
 #pragma unroll
         for (int u = 0; u < NU; u++) {
-          float v = s[u];
+          float v = (CL == 2) ? s[u] + s_b[u] : s[u];
           if (KS == 2) v += __shfl_xor_sync(0xffffffffu, v, 16);
           v += bv;
           if (ksel == 0) {
@@ -721,12 +742,19 @@ __global__ void __launch_bounds__((W / CL) * 32 + 64, 1) decode_warp_kernel(cons
       have_next = pos < last_pos && kCons > 32 * NU;
       if (warp < NU) {
         const int u = warp;
-        const float* lg = logit + u * kQ;
         const int q0 = lane * 8, q1 = q0 + 8;
+        float lg8[8];   // this lane's 8 logits: two 16-byte shared-memory loads, kept in registers for all passes
+        {
+          const float4 l0 = *reinterpret_cast<const float4*>(logit + u * kQ + q0);
+          const float4 l1 = *reinterpret_cast<const float4*>(logit + u * kQ + q0 + 4);
+          lg8[0] = l0.x; lg8[1] = l0.y; lg8[2] = l0.z; lg8[3] = l0.w;
+          lg8[4] = l1.x; lg8[5] = l1.y; lg8[6] = l1.z; lg8[7] = l1.w;
+        }
         float best = -INFINITY;
         int bi = 0x7fffffff;
-        for (int q = q0; q < q1; q++)
-          if (lg[q] > best) { best = lg[q]; bi = q; }
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+          if (lg8[k] > best) { best = lg8[k]; bi = q0 + k; }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
           const float ob = __shfl_xor_sync(0xffffffffu, best, o);
@@ -738,13 +766,17 @@ __global__ void __launch_bounds__((W / CL) * 32 + 64, 1) decode_warp_kernel(cons
           float uni;
           if (p.uniforms) {
             uni = p.uniforms[(size_t)min(u0 + u, p.B - 1) * p.max_n + min(i, p.max_n - 1)];
+          } else if (uni_for == i) {
+            uni = uni_next;            // drawn during the previous step's pick, off the critical path
           } else {
             uint32_t rr[4];
             philox4x32_10((uint32_t)i, (uint32_t)(u0 + u), 0u, 0u, (uint32_t)p.seed, (uint32_t)(p.seed >> 32), rr);
             uni = (float)(rr[0] >> 8) * (1.0f / 16777216.0f);
           }
+          float ex[8];
           float lsum = 0.f;
-          for (int q = q0; q < q1; q++) lsum += expf(lg[q] - best);
+#pragma unroll
+          for (int k = 0; k < 8; k++) { ex[k] = expf(lg8[k] - best); lsum += ex[k]; }
           float incl = lsum;
 #pragma unroll
           for (int o = 1; o < 32; o <<= 1) {
@@ -758,10 +790,14 @@ __global__ void __launch_bounds__((W / CL) * 32 + 64, 1) decode_warp_kernel(cons
           if (target < incl && target >= excl) {
             float c = excl;
             cand = q1 - 1;
-            for (int q = q0; q < q1; q++) {
-              c += expf(lg[q] - best);
-              if (c > target) { cand = q; break; }
+#pragma unroll
+            for (int k = 7; k >= 0; k--) {      // first k (ascending) whose running sum passes the target
+              float ck = excl;
+#pragma unroll
+              for (int m = 0; m <= k; m++) ck += ex[m];
+              if (ck > target) cand = q0 + k;
             }
+            (void)c;
           }
 #pragma unroll
           for (int o = 16; o > 0; o >>= 1) cand = min(cand, __shfl_xor_sync(0xffffffffu, cand, o));
@@ -770,6 +806,12 @@ __global__ void __launch_bounds__((W / CL) * 32 + 64, 1) decode_warp_kernel(cons
         // (CL == 2: both CTAs hold the same 256 logits and make the same pick; each writes it -- same value -- so
         //  that its own next prologue reads what it wrote, no cross-CTA dependency on global memory)
         if (lane == 0 && u0 + u < p.B && i < s_n[u]) p.xs[(size_t)(u0 + u) * stride_xs + pos + 1] = pick;
+        if (p.mode == WNB_MODE_SAMPLING && !p.uniforms) {   // next step's uniform, while the other warps fetch its taps
+          uint32_t rr[4];
+          philox4x32_10((uint32_t)(i + 1), (uint32_t)(u0 + u), 0u, 0u, (uint32_t)p.seed, (uint32_t)(p.seed >> 32), rr);
+          uni_next = (float)(rr[0] >> 8) * (1.0f / 16777216.0f);
+          uni_for = i + 1;
+        }
       }
       cons_sync_w<WP>();
       WNB_T(10);
