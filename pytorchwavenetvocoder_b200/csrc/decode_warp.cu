@@ -498,18 +498,7 @@ __global__ void __launch_bounds__((W / CL) * 32 + 64, 1) decode_warp_kernel(cons
       WNB_T(2);
       warp_reduce_scatter<NU * GV>(acc, my_pre, lane);
       __syncwarp();
-      if constexpr (2 * CH * NU <= 32) {
-        // sigmoid on lanes [0, CH*NU), tanh on the next CH*NU lanes (the two transcendental chains run side by side),
-        // the product meets through one shuffle; same expressions, same rounding
-        constexpr int NG = CH * NU;
-        const int gl = lane % NG;
-        const int u = gl / CH, cc = gl % CH, c = vw * CH + cc;
-        float part = 0.f;
-        if (lane < NG) part = sigmoidf_(my_pre[u * GV + cc] + gate_bs);
-        else if (lane < 2 * NG) part = tanhf(my_pre[u * GV + CH + cc] + gate_bt);
-        const float other = __shfl_down_sync(0xffffffffu, part, NG);
-        if (lane < NG) st_both<CL>(&zs[u * kR + c], part * other, peer_delta, xs_.peer_bar());
-      } else if (lane < CH * NU) {
+      if (lane < CH * NU) {   // (splitting sigmoid / tanh over two lane groups was measured: divergence serialises them)
         const int u = lane / CH, cc = lane % CH, c = vw * CH + cc;
         const float a = my_pre[u * GV + cc] + gate_bs;
         const float g = my_pre[u * GV + CH + cc] + gate_bt;
@@ -523,14 +512,7 @@ __global__ void __launch_bounds__((W / CL) * 32 + 64, 1) decode_warp_kernel(cons
       WNB_T(4);
       // ---------------- phase B: residual 1x1 (split K) ----------------
       float skip_b[SL];
-      const bool last_block = l + 1 == L;   // its residual output is discarded (wavenet.py:230-238): no GEMV, no hand-over
-      if (last_block) {
-        if constexpr (CL == 2) phase_wait();          // the skip GEMV below still needs the peer's half of z
-        const float* rc = ring.acquire();             // (the chunk also carries the skip bias)
-#pragma unroll
-        for (int e = 0; e < SL; e++) skip_b[e] = rc[kWresFloats / CL + kR + vw * SV + lane * SL + e];
-        ring.release();
-      } else {
+      {
         float racc[NU * CH];
 #pragma unroll
         for (int i = 0; i < NU * CH; i++) racc[i] = 0.f;
@@ -572,7 +554,7 @@ __global__ void __launch_bounds__((W / CL) * 32 + 64, 1) decode_warp_kernel(cons
         }
       }
       WNB_T(5);
-      if (!last_block) phase_arrive(NU * kR / 2);   // the residual outputs travel to the peer while the skip GEMV runs
+      phase_arrive(NU * kR / 2);   // the residual outputs travel to the peer while the skip GEMV runs
       // ---------------- phase B': skip 1x1, lanes own outputs SV*warp + SL*lane (+e) ----------------
       if (want) {
         // (CL == 2 leaves 2 warps per scheduler: a single accumulator per output would make the K loop one dependent
@@ -623,7 +605,7 @@ __global__ void __launch_bounds__((W / CL) * 32 + 64, 1) decode_warp_kernel(cons
         }
       }
       WNB_T(6);
-      if (!last_block) phase_wait();     // (after the last block the post network's first hand-over is the barrier)
+      phase_wait();
       WNB_T(7);
     }
 
