@@ -333,7 +333,10 @@ __global__ void __launch_bounds__((W / CL) * 32 + 64, 1) decode_warp_kernel(cons
         for (int l = 0; l < L; l++) {
           const float* base = my_stream + (size_t)l * kLayerF;
           if (kW1One) {
-            ring.push(base, (5 * kJBlock + kB1Floats) * 4);                // W1 j = 0..4, then b1: one chunk
+            // W1 j = 0..4 | b1 | W2res | b2: ONE 51.8 KB chunk per block (they are contiguous in the stream), so that the
+            // three 64 KB slots hold [this block's gate+res][this block's skip][NEXT block's gate+res]: the stream runs
+            // half a block further ahead than with a slot each for W1 and W2res
+            ring.push(base, (5 * kJBlock + kB1Floats + kWresFloats / CL + kB2Floats) * 4);
           } else {
             if (BIG) {
               ring.push(base, 4 * kJBlock * 4);                            // W1 j = 0..3
@@ -344,7 +347,7 @@ __global__ void __launch_bounds__((W / CL) * 32 + 64, 1) decode_warp_kernel(cons
             ring.push(base + 4 * kJBlock, (kJBlock + kB1Floats) * 4);      // W1 j = 4, then b1
           }
           const float* wres = base + 5 * kJBlock + kB1Floats;
-          ring.push(wres, (kWresFloats / CL + kB2Floats) * 4);             // W2res, then b2
+          if (!kW1One) ring.push(wres, (kWresFloats / CL + kB2Floats) * 4);   // W2res, then b2
           if (want)
             for (int c = 0; c < 64 / KPC; c++)
               ring.push(wres + kWresFloats / CL + kB2Floats + c * (KPC * kSrow), KPC * kSrow * 4);
@@ -364,7 +367,7 @@ __global__ void __launch_bounds__((W / CL) * 32 + 64, 1) decode_warp_kernel(cons
   if (warp == WP + 1) {
     // ================================ gatekeeper warp ================================
     if (lane == 0) {
-      const int per_layer_warm = (kW1One ? 1 : (BIG ? 2 : 3)) + 1, per_layer_skip = 64 / KPC;
+      const int per_layer_warm = kW1One ? 1 : ((BIG ? 2 : 3) + 1), per_layer_skip = 64 / KPC;
       const int post_chunks = 1 + kS / KPC + kS / (2 * KPC);
       for (int pos = 0; pos <= last_pos; pos++) {
         const bool want = pos >= p.P - 1;
@@ -493,7 +496,7 @@ __global__ void __launch_bounds__((W / CL) * 32 + 64, 1) decode_warp_kernel(cons
           gate_bs = chunk[(kW1One ? 5 : 1) * kJBlock + c];
           gate_bt = chunk[(kW1One ? 5 : 1) * kJBlock + 64 + c];
         }
-        if (kW1One ? (j == 4) : ((!BIG && j == 1) || j == 3 || j == 4)) ring.release();
+        if (!kW1One && ((!BIG && j == 1) || j == 3 || j == 4)) ring.release();   // (kW1One: released after phase B)
       }
       WNB_T(2);
       warp_reduce_scatter<NU * GV>(acc, my_pre, lane);
@@ -516,7 +519,7 @@ __global__ void __launch_bounds__((W / CL) * 32 + 64, 1) decode_warp_kernel(cons
         float racc[NU * CH];
 #pragma unroll
         for (int i = 0; i < NU * CH; i++) racc[i] = 0.f;
-        const float* rc = ring.acquire();
+        const float* rc = kW1One ? chunk + 5 * kJBlock + kB1Floats : ring.acquire();   // (kW1One: same chunk as W1)
 #pragma unroll
         for (int jj = 0; jj < 2; jj++) {
           const int j = (CL == 2) ? (jj ^ rank) : jj;
