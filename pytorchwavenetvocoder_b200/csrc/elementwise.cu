@@ -198,6 +198,30 @@ __global__ void front_embed_fwd_kernel(const int64_t* __restrict__ x, const floa
     out[i] = v;
   }
 }
+// R % 4 == 0: one thread per 4 channels (16-byte gathers from the L2-resident table, 16-byte coalesced stores), 32-bit
+// index arithmetic on the row, no per-element 64-bit division
+__global__ void __launch_bounds__(256) front_embed_fwd_v4_kernel(const int64_t* __restrict__ x, const float4* __restrict__ wf,
+                                                                 const float4* __restrict__ bias, float4* __restrict__ out,
+                                                                 int B, int T, int Q, int R4, int ks) {
+  const int rows_per_blk = blockDim.x / R4;                 // host guarantees blockDim.x % R4 == 0
+  const int lr = threadIdx.x / R4, r4 = threadIdx.x - lr * R4;
+  const int64_t nrows = (int64_t)B * T;
+  const float4 bv = __ldg(bias + r4);
+  for (int64_t row = (int64_t)blockIdx.x * rows_per_blk + lr; row < nrows; row += (int64_t)gridDim.x * rows_per_blk) {
+    const int t = (int)(row % T);
+    float4 v = bv;
+    for (int k = 0; k < ks; k++) {
+      const int s_ = ks - 1 - k;
+      if (t - s_ >= 0) {
+        int64_t q = x[row - s_] % Q;
+        if (q < 0) q += Q;
+        const float4 w = __ldg(wf + ((size_t)k * Q + q) * R4 + r4);
+        v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
+      }
+    }
+    out[row * R4 + r4] = v;
+  }
+}
 
 // dwf[k][q][r] += dout[b][t][r] for q = x[b][t-(ks-1-k)];  dbias[r] += sum dout
 __global__ void front_embed_bwd_kernel(const int64_t* __restrict__ x, const float* __restrict__ dout,
@@ -224,6 +248,46 @@ __global__ void front_embed_bwd_kernel(const int64_t* __restrict__ x, const floa
     atomicAdd(dbias + r, bsum);
   }
 }
+// The whole (ks, Q, R) gradient table fits in shared memory (128 KB at 2 x 256 x 64): every CTA scatter-adds its rows
+// into a private copy with shared-memory atomics (channels of a row hit distinct banks), then flushes the copy once
+// with 16-byte vector reductions.  The per-row global atomics of the kernel above (23.6 M onto 32 K addresses at the
+// bench shape) were 96 us of a 9 ms step.
+__global__ void __launch_bounds__(256) front_embed_bwd_smem_kernel(const int64_t* __restrict__ x, const float* __restrict__ dout,
+                                                                   float* __restrict__ dwf, float* __restrict__ dbias, int B,
+                                                                   int T, int Q, int R, int ks) {
+  extern __shared__ float tab[];                              // [ks][Q][R] then [R] bias sums
+  const int ntab = ks * Q * R;
+  for (int i = threadIdx.x; i < ntab + R; i += blockDim.x) tab[i] = 0.f;
+  __syncthreads();
+  const int rows_per_it = blockDim.x / R;                     // host guarantees blockDim.x % R == 0
+  const int lr = threadIdx.x / R, r = threadIdx.x - lr * R;
+  const int64_t nrows = (int64_t)B * T;
+  const int64_t per = (nrows + gridDim.x - 1) / gridDim.x;
+  const int64_t row_begin = (int64_t)blockIdx.x * per, row_end = min(nrows, row_begin + per);
+  float bsum = 0.f;
+  for (int64_t row = row_begin + lr; row < row_end; row += rows_per_it) {
+    const float g = __ldg(dout + row * R + r);
+    bsum += g;
+    const int t = (int)(row % T);
+    for (int k = 0; k < ks; k++) {
+      const int s_ = ks - 1 - k;
+      if (t - s_ >= 0) {
+        int64_t q = x[row - s_] % Q;
+        if (q < 0) q += Q;
+        atomicAdd(tab + ((size_t)k * Q + q) * R + r, g);
+      }
+    }
+  }
+  atomicAdd(tab + ntab + r, bsum);
+  __syncthreads();
+  for (int i = threadIdx.x * 4; i < ntab; i += blockDim.x * 4) {   // ntab % 4 == 0 (R % 4 == 0)
+    const float4 v = *reinterpret_cast<const float4*>(tab + i);
+    if (v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f)
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dwf + i), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                   : "memory");
+  }
+  for (int i = threadIdx.x; i < R; i += blockDim.x) atomicAdd(dbias + i, tab[ntab + i]);
+}
 
 // ------------------------------------------------------------------------------------------------
 // aux up-sampling + layout change (wavenet.py:124-154)
@@ -235,10 +299,10 @@ __global__ void aux_upsample_fwd_kernel(const float* __restrict__ h, const float
   const int64_t total = (int64_t)B * T * Ap;
   const float bv = (U > 0) ? bias[0] : 0.f;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int a = (int)(i % Ap);
     const int64_t bt = i / Ap;
-    const int t = (int)(bt % T);
+    const int a = (int)(i - bt * Ap);
     const int b = (int)(bt / T);
+    const int t = (int)(bt - (int64_t)b * T);
     float v = 0.f;
     if (a < A) {
       if (U > 0) {
@@ -257,27 +321,52 @@ __global__ void aux_upsample_fwd_kernel(const float* __restrict__ h, const float
 __global__ void aux_upsample_bwd_kernel(const float* __restrict__ h, const float* __restrict__ dhaux,
                                         float* __restrict__ dw, float* __restrict__ dbias, int B, int A, int Ap,
                                         int Tf, int U) {
+  // Warp w of a block owns the sub-sample offsets j = w, w + nwarps, ... and keeps their partial sums in REGISTERS over
+  // all the (b, tf) items of the block (lanes = aux channels); one atomic per (block, j) at the end.  (One atomic per
+  // dhaux row onto the U addresses of dw -- 184 320 atomics onto 80 words at the bench shape -- took 129 us.)
+  constexpr int kMaxJ = 16;                                   // j values per warp and pass (128 per pass with 8 warps)
+  constexpr int kAC = 8;                                      // aux channels per lane: A <= 256
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   __shared__ float sb[32];
   float btot = 0.f;
-  for (int64_t item = blockIdx.x; item < (int64_t)B * Tf; item += gridDim.x) {
-    const int b = (int)(item / Tf), tf = (int)(item % Tf);
-    for (int j = warp; j < U; j += nwarps) {
-      const float* row = dhaux + ((size_t)b * Tf * U + (size_t)tf * U + j) * Ap;
-      float acc = 0.f, bacc = 0.f;
-      for (int a = lane; a < A; a += 32) {
-        const float g = row[a];
-        acc = fmaf(g, __ldg(h + ((size_t)b * A + a) * Tf + tf), acc);
-        bacc += g;
+  for (int jbase = 0; jbase < U; jbase += kMaxJ * nwarps) {   // (one pass for U <= 128; 256 = ljspeech-melspc: two)
+    float acc[kMaxJ];
+#pragma unroll
+    for (int i = 0; i < kMaxJ; i++) acc[i] = 0.f;
+    for (int64_t item = blockIdx.x; item < (int64_t)B * Tf; item += gridDim.x) {
+      const int b = (int)(item / Tf), tf = (int)(item % Tf);
+      float hv[kAC];                                          // h[b][a][tf] for a = lane, lane + 32, ...
+#pragma unroll
+      for (int c = 0; c < kAC; c++) {
+        const int a = lane + 32 * c;
+        hv[c] = (a < A) ? __ldg(h + ((size_t)b * A + a) * Tf + tf) : 0.f;
       }
-      acc = warp_sum(acc);
-      bacc = warp_sum(bacc);
-      if (lane == 0) {
-        atomicAdd(dw + j, acc);
-        btot += bacc;
+      const float* base = dhaux + ((size_t)b * Tf * U + (size_t)tf * U) * Ap;
+#pragma unroll
+      for (int i = 0; i < kMaxJ; i++) {
+        const int j = jbase + warp + i * nwarps;
+        if (j < U) {
+          const float* row = base + (size_t)j * Ap;
+#pragma unroll
+          for (int c = 0; c < kAC; c++) {
+            const int a = lane + 32 * c;
+            if (a < A) {
+              const float g = __ldg(row + a);
+              acc[i] = fmaf(g, hv[c], acc[i]);
+              btot += g;
+            }
+          }
+        }
       }
     }
+#pragma unroll
+    for (int i = 0; i < kMaxJ; i++) {
+      const int j = jbase + warp + i * nwarps;
+      const float v = warp_sum(acc[i]);
+      if (j < U && lane == 0) atomicAdd(dw + j, v);
+    }
   }
+  btot = warp_sum(btot);
   if (lane == 0) sb[warp] = btot;
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -329,6 +418,66 @@ __global__ void cross_entropy_kernel(const float* logits, const int64_t* __restr
         if (q == tg) p -= 1.0f;
         dl[q] = p * inv_n;
       }
+    }
+  }
+  __shared__ double sl[32];
+  if (lane == 0) sl[warp] = local;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int i = 0; i < nwarps; i++) s += sl[i];
+    atomicAdd(loss_sum, s * (double)inv_n);
+  }
+}
+
+// Q == 256 fast path: the row lives in registers (two 16-byte loads per lane), one pass for max / exp / sum, two 16-byte
+// stores for the gradient -- instead of three passes of 4-byte loads over the row.
+__global__ void __launch_bounds__(256) cross_entropy_q256_kernel(const float* logits, const int64_t* __restrict__ target,
+                                                                 double* __restrict__ loss_sum, float* dlogits, int B, int T,
+                                                                 int start, float inv_n) {
+  constexpr int Q = 256;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int64_t nrows = (int64_t)B * T;
+  double local = 0.0;
+  for (int64_t row = (int64_t)blockIdx.x * nwarps + warp; row < nrows; row += (int64_t)gridDim.x * nwarps) {
+    const int t = (int)(row % T);
+    const float4* lg4 = reinterpret_cast<const float4*>(logits + row * Q);
+    float4* dl4 = dlogits ? reinterpret_cast<float4*>(dlogits + row * Q) : nullptr;
+    if (t < start) {
+      if (dl4) { dl4[lane] = make_float4(0.f, 0.f, 0.f, 0.f); dl4[32 + lane] = make_float4(0.f, 0.f, 0.f, 0.f); }
+      continue;
+    }
+    const float4 a = lg4[lane], b = lg4[32 + lane];     // columns 4*lane .. +3 and 128 + 4*lane .. +3
+    float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    float m = v[0];
+#pragma unroll
+    for (int k = 1; k < 8; k++) m = fmaxf(m, v[k]);
+    m = warp_max(m);
+    float e[8], sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; k++) { e[k] = expf(v[k] - m); sum += e[k]; }
+    sum = warp_sum(sum);
+    const float lse = m + logf(sum);
+    int64_t tg = target[row];
+    if (tg < 0 || tg >= Q) {
+      if (lane == 0) local += (double)NAN;
+      tg = 0;
+    }
+    const float ltg = logits[row * Q + tg];
+    if (lane == 0) local += (double)(lse - ltg);
+    if (dl4) {
+      const float inv_s = 1.0f / sum;
+      __syncwarp();
+      float o[8];
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        const int q = (k < 4 ? 4 * lane + k : 128 + 4 * lane + (k - 4));
+        float pr = e[k] * inv_s;
+        if (q == (int)tg) pr -= 1.0f;
+        o[k] = pr * inv_n;
+      }
+      dl4[lane] = make_float4(o[0], o[1], o[2], o[3]);
+      dl4[32 + lane] = make_float4(o[4], o[5], o[6], o[7]);
     }
   }
   __shared__ double sl[32];
@@ -423,8 +572,17 @@ WNB_API int wnb_lut_i16(const int32_t* idx, const int16_t* table, int16_t* out, 
 WNB_API int wnb_front_embed_fwd(const int64_t* x, const float* wf, const float* bias, float* out, int B, int T, int Q,
                         int R, int ks, void* stream) {
   WNB_REQUIRE(B > 0 && T > 0 && Q > 0 && R > 0 && ks >= 1, "front_embed_fwd: bad shape");
-  front_embed_fwd_kernel<<<grid_for((int64_t)B * T * R, 256), 256, 0, (cudaStream_t)stream>>>(x, wf, bias, out, B, T,
-                                                                                              Q, R, ks);
+  const bool v4 = R % 4 == 0 && 256 % (R / 4) == 0 &&
+                  ((reinterpret_cast<uintptr_t>(wf) | reinterpret_cast<uintptr_t>(bias) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+  if (v4) {
+    const int rows_per_blk = 256 / (R / 4);
+    front_embed_fwd_v4_kernel<<<grid_for(cdiv64((int64_t)B * T, rows_per_blk) * 256, 256), 256, 0, (cudaStream_t)stream>>>(
+        x, reinterpret_cast<const float4*>(wf), reinterpret_cast<const float4*>(bias), reinterpret_cast<float4*>(out), B, T,
+        Q, R / 4, ks);
+  } else {
+    front_embed_fwd_kernel<<<grid_for((int64_t)B * T * R, 256), 256, 0, (cudaStream_t)stream>>>(x, wf, bias, out, B, T,
+                                                                                                Q, R, ks);
+  }
   WNB_CHECK_LAUNCH("front_embed_fwd");
   return WNB_OK;
 }
@@ -432,11 +590,18 @@ WNB_API int wnb_front_embed_fwd(const int64_t* x, const float* wf, const float* 
 WNB_API int wnb_front_embed_bwd(const int64_t* x, const float* dout, float* dwf, float* dbias, int B, int T, int Q, int R,
                         int ks, void* stream) {
   WNB_REQUIRE(B > 0 && T > 0 && Q > 0 && R > 0 && ks >= 1, "front_embed_bwd: bad shape");
-  const int rows_per_block = 64;
   const int64_t nrows = (int64_t)B * T;
-  const int threads = R >= 256 ? 256 : ((R + 31) / 32) * 32;
-  front_embed_bwd_kernel<<<(int)cdiv64(nrows, rows_per_block), threads, 0, (cudaStream_t)stream>>>(
-      x, dout, dwf, dbias, B, T, Q, R, ks, rows_per_block);
+  const size_t smem = ((size_t)ks * Q * R + R) * sizeof(float);
+  if (R % 4 == 0 && 256 % R == 0 && smem <= 200 * 1024 && (reinterpret_cast<uintptr_t>(dwf) & 15) == 0 && nrows >= 4096) {
+    WNB_CUDA(ensure_dynamic_smem(reinterpret_cast<const void*>(front_embed_bwd_smem_kernel), smem));
+    const int sms = device_sms();
+    front_embed_bwd_smem_kernel<<<sms, 256, smem, (cudaStream_t)stream>>>(x, dout, dwf, dbias, B, T, Q, R, ks);
+  } else {
+    const int rows_per_block = 64;
+    const int threads = R >= 256 ? 256 : ((R + 31) / 32) * 32;
+    front_embed_bwd_kernel<<<(int)cdiv64(nrows, rows_per_block), threads, 0, (cudaStream_t)stream>>>(
+        x, dout, dwf, dbias, B, T, Q, R, ks, rows_per_block);
+  }
   WNB_CHECK_LAUNCH("front_embed_bwd");
   return WNB_OK;
 }
@@ -455,8 +620,9 @@ WNB_API int wnb_aux_upsample_fwd(const float* h, const float* w, const float* bi
 WNB_API int wnb_aux_upsample_bwd(const float* h, const float* dhaux, float* dw, float* dbias, int B, int A, int Ap, int Tf,
                          int U, void* stream) {
   WNB_REQUIRE(B > 0 && A > 0 && Ap >= A && Tf > 0 && U > 0, "aux_upsample_bwd: bad shape");
+  WNB_REQUIRE(A <= 256, "aux_upsample_bwd: n_aux <= 256 (got %d)", A);
   int64_t items = (int64_t)B * Tf;
-  int grid = (int)(items < 148 * 8 ? items : 148 * 8);
+  int grid = (int)(items < 148 * 4 ? items : 148 * 4);
   aux_upsample_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(h, dhaux, dw, dbias, B, A, Ap, Tf, U);
   WNB_CHECK_LAUNCH("aux_upsample_bwd");
   return WNB_OK;
@@ -469,8 +635,12 @@ WNB_API int wnb_cross_entropy(const float* logits, const int64_t* target, double
   const int64_t n = (int64_t)B * (T - start);
   const int64_t nrows = (int64_t)B * T;
   int grid = (int)(cdiv64(nrows, 8) < 148 * 8 ? cdiv64(nrows, 8) : 148 * 8);
-  cross_entropy_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(logits, target, loss_sum, dlogits, B, T, Q, start,
-                                                              1.0f / (float)n);
+  if (Q == 256 && ((reinterpret_cast<uintptr_t>(logits) | reinterpret_cast<uintptr_t>(dlogits)) & 15) == 0)
+    cross_entropy_q256_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(logits, target, loss_sum, dlogits, B, T, start,
+                                                                     1.0f / (float)n);
+  else
+    cross_entropy_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(logits, target, loss_sum, dlogits, B, T, Q, start,
+                                                                1.0f / (float)n);
   WNB_CHECK_LAUNCH("cross_entropy");
   return WNB_OK;
 }

@@ -421,37 +421,47 @@ static int wgrad_tc_split(const float* a, int CA, int M, const float* b, int CB,
 // M-blocks of 128 rows are batched per launch as far as TMEM allows; N goes in chunks of <= 224 columns.
 static int wgrad_tc_concat(const float* a0, int C0, const float* a1, int C1, int M, const float* b, int CB, int N,
                            int shift, float* c, int ldc, float* db, int B, int T, cudaStream_t st) {
+  // The N axis is split into column groups handled by different CTAs of ONE launch (WgOpts::n_split, as wgrad_tc_split
+  // does): every launch then streams its M-blocks of A once and B once, with the B columns shared through L2 -- instead
+  // of one launch per (<= 224-column chunk) x (M-block pair) that re-reads the A tensor for every chunk (the recipes'
+  // 512 / 256 shape spent 41 % of its step in 897 such launches).
   int rc;
-  for (int n0 = 0; n0 < N; n0 += 224) {
-    const int ncols = (N - n0) < 224 ? (N - n0) : 224;
-    const bool with_db = db && n0 == 0;
-    int per_launch = 512 / (ncols + (with_db ? 32 : 0));
-    if (per_launch > 5) per_launch = 5;
-    const WgOperand bo[1] = {{b, CB, n0, ncols / 32, shift}};
-    WgBlock blk[5];
-    int nblk = 0;
-    for (int m0 = 0; m0 < M; m0 += 128) {
-      WgBlock& bk = blk[nblk];
-      bk.m_valid = (M - m0) < 128 ? (M - m0) : 128;
-      bk.c = c + (size_t)m0 * ldc + n0;
-      bk.db = with_db ? db + m0 : nullptr;
-      // rows m0..m0+127 of the concatenation, in groups of 32 channels
-      if (m0 + 128 <= C0 || !a1) {
-        bk.nops = 1;
-        bk.ops[0] = WgOperand{a0, C0, m0, 4, 0};            // (groups past C0 are TMA zero fill)
-      } else if (m0 >= C0) {
-        bk.nops = 1;
-        bk.ops[0] = WgOperand{a1, C1, m0 - C0, 4, 0};
-      } else {
-        const int g0 = (C0 - m0) / 32;                       // groups still inside a0
-        bk.nops = 2;
-        bk.ops[0] = WgOperand{a0, C0, m0, g0, 0};
-        bk.ops[1] = WgOperand{a1, C1, 0, 4 - g0, 0};
-      }
-      if (++nblk == per_launch || m0 + 128 >= M) {
-        if ((rc = wgrad_tc_blocks(blk, nblk, bo, 1, ldc, B, T, st)) != WNB_OK) return rc;
-        nblk = 0;
-      }
+  const int groups = N / 32;
+  if (N % 32 != 0 || groups < 1) { set_error("wgrad_tc_concat: N must be a multiple of 32"); return WNB_ERR_INVALID; }
+  // column groups of <= 128 columns per CTA (largest divisor of N/32 up to 4): three M-blocks (+ bias column group) then
+  // share the 512 TMEM columns, the tile [384 x 128] is close to square
+  int nB = 1;
+  for (int g = 4; g >= 1; g--)
+    if (groups % g == 0 && groups / g <= 128) { nB = g; break; }
+  const int cols = 32 * (nB + (db ? 1 : 0));
+  int per_launch = 512 / cols;
+  if (per_launch > 5) per_launch = 5;
+  const int n_split = groups / nB;
+  const WgOperand bo[1] = {{b, CB, 0, nB, shift}};
+  const WgOpts o{n_split};
+  WgBlock blk[5];
+  int nblk = 0;
+  for (int m0 = 0; m0 < M; m0 += 128) {
+    WgBlock& bk = blk[nblk];
+    bk.m_valid = (M - m0) < 128 ? (M - m0) : 128;
+    bk.c = c + (size_t)m0 * ldc;
+    bk.db = db ? db + m0 : nullptr;
+    // rows m0..m0+127 of the concatenation, in groups of 32 channels
+    if (m0 + 128 <= C0 || !a1) {
+      bk.nops = 1;
+      bk.ops[0] = WgOperand{a0, C0, m0, 4, 0};            // (groups past C0 are TMA zero fill)
+    } else if (m0 >= C0) {
+      bk.nops = 1;
+      bk.ops[0] = WgOperand{a1, C1, m0 - C0, 4, 0};
+    } else {
+      const int g0 = (C0 - m0) / 32;                       // groups still inside a0
+      bk.nops = 2;
+      bk.ops[0] = WgOperand{a0, C0, m0, g0, 0};
+      bk.ops[1] = WgOperand{a1, C1, 0, 4 - g0, 0};
+    }
+    if (++nblk == per_launch || m0 + 128 >= M) {
+      if ((rc = wgrad_tc_blocks(blk, nblk, bo, 1, ldc, B, T, st, n_split > 1 ? &o : nullptr)) != WNB_OK) return rc;
+      nblk = 0;
     }
   }
   return WNB_OK;

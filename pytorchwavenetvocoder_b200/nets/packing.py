@@ -132,7 +132,7 @@ class StackPlan(object):
         cp(ptr("conv_post_2.weight"), P.off["wp2t"], (1, Q, S), (0, S, 1), (0, 1, Q))
         cp(ptr("conv_post_2.bias"), P.off["bp2"], (1, 1, Q), (0, 0, 1), (0, 0, 1))
         self.pack_table = self._upload(pk)
-        self.n_pack = len(pk)
+        self.n_pack = self.pack_table.numel() // DESC.itemsize
 
         # ---- unpack: G -> flat gradient buffer (one 16-byte aligned slice per parameter, parameters() order) ----
         self.grad_off, self.grad_names = {}, []
@@ -174,9 +174,40 @@ class StackPlan(object):
         up(G.off["Wp2"], "conv_post_2.weight", (1, 1, Q * S), (0, 0, 1), (0, 0, 1))
         up(G.off["bp2"], "conv_post_2.bias", (1, 1, Q), (0, 0, 1), (0, 0, 1))
         self.unpack_table = self._upload(pk)
-        self.n_unpack = len(pk)
+        self.n_unpack = self.unpack_table.numel() // DESC.itemsize
+
+    @staticmethod
+    def _split(rows, limit=16384):
+        """Break large entries into pieces of <= `limit` elements along their outermost non-trivial dimension, so that the
+        work per block row of pack_kernel is even (one 262 144-element entry otherwise sets the kernel time)."""
+        out = []
+        for r in rows:
+            src, src2, dst, n0, n1, n2, ss0, ss1, ss2, ds0, ds1, ds2, op, flags, nsum = r
+            if n0 * n1 * n2 <= limit or op == SUMPTR:
+                out.append(r)
+                continue
+            if n0 > 1:
+                step = max(1, limit // (n1 * n2))
+                for a in range(0, n0, step):
+                    m = min(step, n0 - a)
+                    out.append((src + (a * ss0) * (4 if flags & SRC_ABS else 1), src2 + ((a * ss0) * 4 if src2 else 0),
+                                dst + a * ds0, m, n1, n2, ss0, ss1, ss2, ds0, ds1, ds2, op, flags, nsum))
+            else:
+                if n1 > 1:
+                    step = max(1, limit // n2)
+                    for a in range(0, n1, step):
+                        m = min(step, n1 - a)
+                        out.append((src + (a * ss1) * (4 if flags & SRC_ABS else 1), src2 + ((a * ss1) * 4 if src2 else 0),
+                                    dst + a * ds1, 1, m, n2, ss0, ss1, ss2, ds0, ds1, ds2, op, flags, nsum))
+                else:
+                    for a in range(0, n2, limit):
+                        m = min(limit, n2 - a)
+                        out.append((src + (a * ss2) * (4 if flags & SRC_ABS else 1), src2 + ((a * ss2) * 4 if src2 else 0),
+                                    dst + a * ds2, 1, 1, m, ss0, ss1, ss2, ds0, ds1, ds2, op, flags, nsum))
+        return out
 
     def _upload(self, rows):
+        rows = self._split(rows)
         arr = np.zeros(len(rows), dtype=DESC)
         for i, r in enumerate(rows):
             arr[i] = r
