@@ -248,45 +248,44 @@ __global__ void front_embed_bwd_kernel(const int64_t* __restrict__ x, const floa
     atomicAdd(dbias + r, bsum);
   }
 }
-// The whole (ks, Q, R) gradient table fits in shared memory (128 KB at 2 x 256 x 64): every CTA scatter-adds its rows
-// into a private copy with shared-memory atomics (channels of a row hit distinct banks), then flushes the copy once
-// with 16-byte vector reductions.  The per-row global atomics of the kernel above (23.6 M onto 32 K addresses at the
-// bench shape) were 96 us of a 9 ms step.
-__global__ void __launch_bounds__(256) front_embed_bwd_smem_kernel(const int64_t* __restrict__ x, const float* __restrict__ dout,
-                                                                   float* __restrict__ dwf, float* __restrict__ dbias, int B,
-                                                                   int T, int Q, int R, int ks) {
-  extern __shared__ float tab[];                              // [ks][Q][R] then [R] bias sums
-  const int ntab = ks * Q * R;
-  for (int i = threadIdx.x; i < ntab + R; i += blockDim.x) tab[i] = 0.f;
-  __syncthreads();
-  const int rows_per_it = blockDim.x / R;                     // host guarantees blockDim.x % R == 0
-  const int lr = threadIdx.x / R, r = threadIdx.x - lr * R;
+// One thread per (row, 4 channels): a 16-byte load of dout and ONE 16-byte vector reduction per tap into the
+// (ks, Q, R) table (a quarter of the L2 atomic operations of the scalar kernel above: 96 -> ~30 us at the bench shape);
+// the bias gradient is summed in registers over the rows a thread owns and reduced once per block.
+// (A shared-memory private table per CTA was tried: float atomics in shared memory are CAS loops -- 435 us.)
+__global__ void __launch_bounds__(256) front_embed_bwd_v4_kernel(const int64_t* __restrict__ x, const float4* __restrict__ dout,
+                                                                 float* __restrict__ dwf, float* __restrict__ dbias, int B,
+                                                                 int T, int Q, int R4, int ks) {
+  const int rows_per_blk = blockDim.x / R4;                 // host guarantees blockDim.x % R4 == 0, R4 <= 64
+  const int lr = threadIdx.x / R4, r4 = threadIdx.x - lr * R4;
   const int64_t nrows = (int64_t)B * T;
-  const int64_t per = (nrows + gridDim.x - 1) / gridDim.x;
-  const int64_t row_begin = (int64_t)blockIdx.x * per, row_end = min(nrows, row_begin + per);
-  float bsum = 0.f;
-  for (int64_t row = row_begin + lr; row < row_end; row += rows_per_it) {
-    const float g = __ldg(dout + row * R + r);
-    bsum += g;
+  float4 bs = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int64_t row = (int64_t)blockIdx.x * rows_per_blk + lr; row < nrows; row += (int64_t)gridDim.x * rows_per_blk) {
+    const float4 g = __ldg(dout + row * R4 + r4);
+    bs.x += g.x; bs.y += g.y; bs.z += g.z; bs.w += g.w;
     const int t = (int)(row % T);
     for (int k = 0; k < ks; k++) {
       const int s_ = ks - 1 - k;
       if (t - s_ >= 0) {
         int64_t q = x[row - s_] % Q;
         if (q < 0) q += Q;
-        atomicAdd(tab + ((size_t)k * Q + q) * R + r, g);
+        float* dst = dwf + (((size_t)k * Q + q) * R4 + r4) * 4;
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(g.x), "f"(g.y), "f"(g.z), "f"(g.w)
+                     : "memory");
       }
     }
   }
-  atomicAdd(tab + ntab + r, bsum);
+  __shared__ float4 sbs[256];
+  sbs[threadIdx.x] = bs;
   __syncthreads();
-  for (int i = threadIdx.x * 4; i < ntab; i += blockDim.x * 4) {   // ntab % 4 == 0 (R % 4 == 0)
-    const float4 v = *reinterpret_cast<const float4*>(tab + i);
-    if (v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f)
-      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dwf + i), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
-                   : "memory");
+  if (threadIdx.x < R4) {
+    float4 t4 = sbs[threadIdx.x];
+    for (int j = 1; j < rows_per_blk; j++) {
+      const float4 o = sbs[j * R4 + threadIdx.x];
+      t4.x += o.x; t4.y += o.y; t4.z += o.z; t4.w += o.w;
+    }
+    atomicAdd(dbias + 4 * threadIdx.x, t4.x); atomicAdd(dbias + 4 * threadIdx.x + 1, t4.y);
+    atomicAdd(dbias + 4 * threadIdx.x + 2, t4.z); atomicAdd(dbias + 4 * threadIdx.x + 3, t4.w);
   }
-  for (int i = threadIdx.x; i < R; i += blockDim.x) atomicAdd(dbias + i, tab[ntab + i]);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -313,6 +312,32 @@ __global__ void aux_upsample_fwd_kernel(const float* __restrict__ h, const float
       }
     }
     haux[i] = v;
+  }
+}
+
+// Ap % 4 == 0: one thread per 4 aux channels of a row, 16-byte stores
+__global__ void __launch_bounds__(256) aux_upsample_fwd_v4_kernel(const float* __restrict__ h, const float* __restrict__ w,
+                                                                  const float* __restrict__ bias, float4* __restrict__ haux,
+                                                                  int B, int A, int Ap4, int Tf, int U) {
+  const int T = (U > 0) ? Tf * U : Tf;
+  const int64_t total = (int64_t)B * T * Ap4;
+  const float bv = (U > 0) ? bias[0] : 0.f;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t bt = i / Ap4;
+    const int a0 = (int)(i - bt * Ap4) * 4;
+    const int b = (int)(bt / T);
+    const int t = (int)(bt - (int64_t)b * T);
+    const int tf = (U > 0) ? t / U : t;
+    const float wj = (U > 0) ? __ldg(w + (t - tf * U)) : 1.f;
+    float v[4];
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+      const int a = a0 + c;
+      v[c] = (a < A) ? ((U > 0) ? fmaf(__ldg(h + ((size_t)b * A + a) * Tf + tf), wj, bv)
+                                : __ldg(h + ((size_t)b * A + a) * Tf + tf))
+                     : 0.f;
+    }
+    haux[i] = make_float4(v[0], v[1], v[2], v[3]);
   }
 }
 
@@ -591,11 +616,11 @@ WNB_API int wnb_front_embed_bwd(const int64_t* x, const float* dout, float* dwf,
                         int ks, void* stream) {
   WNB_REQUIRE(B > 0 && T > 0 && Q > 0 && R > 0 && ks >= 1, "front_embed_bwd: bad shape");
   const int64_t nrows = (int64_t)B * T;
-  const size_t smem = ((size_t)ks * Q * R + R) * sizeof(float);
-  if (R % 4 == 0 && 256 % R == 0 && smem <= 200 * 1024 && (reinterpret_cast<uintptr_t>(dwf) & 15) == 0 && nrows >= 4096) {
-    WNB_CUDA(ensure_dynamic_smem(reinterpret_cast<const void*>(front_embed_bwd_smem_kernel), smem));
-    const int sms = device_sms();
-    front_embed_bwd_smem_kernel<<<sms, 256, smem, (cudaStream_t)stream>>>(x, dout, dwf, dbias, B, T, Q, R, ks);
+  if (R % 4 == 0 && 256 % (R / 4) == 0 &&
+      ((reinterpret_cast<uintptr_t>(dwf) | reinterpret_cast<uintptr_t>(dout)) & 15) == 0) {
+    const int rows_per_blk = 256 / (R / 4);
+    front_embed_bwd_v4_kernel<<<grid_for(cdiv64(nrows, rows_per_blk) * 256, 256), 256, 0, (cudaStream_t)stream>>>(
+        x, reinterpret_cast<const float4*>(dout), dwf, dbias, B, T, Q, R / 4, ks);
   } else {
     const int rows_per_block = 64;
     const int threads = R >= 256 ? 256 : ((R + 31) / 32) * 32;
@@ -611,8 +636,12 @@ WNB_API int wnb_aux_upsample_fwd(const float* h, const float* w, const float* bi
   WNB_REQUIRE(B > 0 && A > 0 && Ap >= A && Tf > 0 && U >= 0, "aux_upsample_fwd: bad shape");
   WNB_REQUIRE(U == 0 || (w && bias), "aux_upsample_fwd: U>0 needs w and bias");
   const int64_t T = U > 0 ? (int64_t)Tf * U : Tf;
-  aux_upsample_fwd_kernel<<<grid_for((int64_t)B * T * Ap, 256), 256, 0, (cudaStream_t)stream>>>(h, w, bias, haux, B,
-                                                                                                A, Ap, Tf, U);
+  if (Ap % 4 == 0 && (reinterpret_cast<uintptr_t>(haux) & 15) == 0)
+    aux_upsample_fwd_v4_kernel<<<grid_for((int64_t)B * T * (Ap / 4), 256), 256, 0, (cudaStream_t)stream>>>(
+        h, w, bias, reinterpret_cast<float4*>(haux), B, A, Ap / 4, Tf, U);
+  else
+    aux_upsample_fwd_kernel<<<grid_for((int64_t)B * T * Ap, 256), 256, 0, (cudaStream_t)stream>>>(h, w, bias, haux, B,
+                                                                                                  A, Ap, Tf, U);
   WNB_CHECK_LAUNCH("aux_upsample_fwd");
   return WNB_OK;
 }
