@@ -353,6 +353,13 @@ static int pick_tchunk(int B, int T, int tiles) {
 
 // N == 512 GEMMs of the post network run as two 256-column blocks: the accumulators are then double-buffered and the
 // epilogue of one tile overlaps the mainloop of the next (-0.2 ms on the 10 ms step); WNB_POST_SPLIT=0 switches it off
+// two time tiles per weight chunk in the post-network GEMMs (K = 256 / 512: short main loops, mask epilogues);
+// WNB_POST_MT=1 selects one tile with double-buffered accumulators instead (A/B switch)
+static int post_m_tiles() {
+  static const int mt = [] { const char* e = getenv("WNB_POST_MT"); return (e && e[0] == '1') ? 1 : ((e && e[0] == '2') ? 2 : 0); }();
+  return mt ? mt : nt_default_m_tiles();
+}
+
 static bool post_split(int S) {
   static int on = -1;
   if (on < 0) { const char* e = getenv("WNB_POST_SPLIT"); on = (e && e[0] == '0') ? 0 : 1; }
@@ -436,6 +443,10 @@ static int wgrad_tc_concat(const float* a0, int C0, const float* a1, int C1, int
   const int cols = 32 * (nB + (db ? 1 : 0));
   int per_launch = 512 / cols;
   if (per_launch > 5) per_launch = 5;
+  {  // same number of launches, evenly filled (4 M-blocks: 2 + 2 rather than 3 + 1)
+    const int mblocks = (M + 127) / 128, launches = (mblocks + per_launch - 1) / per_launch;
+    per_launch = (mblocks + launches - 1) / launches;
+  }
   const int n_split = groups / nB;
   const WgOperand bo[1] = {{b, CB, 0, nB, shift}};
   const WgOpts o{n_split};
@@ -767,13 +778,13 @@ WNB_API int wnb_post_fwd(float* skip, const float* wp1, const float* bp1, const 
     }
     const NtTcSeg s1[1] = {{skip, S, 0, S, wp1, S, S, 0, 0}};
     if (post_split(S)) {   // two 256-column blocks: double-buffered accumulators, epilogue overlapped with the next tile
-      const NtTcOpts o{2, 0, 0, 0, nt_default_m_tiles()};
+      const NtTcOpts o{2, 0, 0, 0, post_m_tiles()};
       if ((rc = gemm_nt_tc(s1, 1, S / 2, r1, S, bp1, nullptr, 0, nullptr, 0, 1, 0, B, T, st, nullptr, nullptr, nullptr, 0, 0,
                            nullptr, &o)) != WNB_OK)
         return rc;
     } else if ((rc = gemm_nt_tc(s1, 1, S, r1, S, bp1, nullptr, 0, nullptr, 0, 1, 0, B, T, st)) != WNB_OK) return rc;
     const NtTcSeg s2[1] = {{r1, S, 0, S, wp2, Q, S, 0, 0}};
-    const NtTcOpts o2{1, 0, 0, 0, Q <= 256 ? nt_default_m_tiles() : 1};
+    const NtTcOpts o2{1, 0, 0, 0, Q <= 256 ? post_m_tiles() : 1};
     return gemm_nt_tc(s2, 1, Q, logits, Q, bp2, nullptr, 0, nullptr, 0, 0, 0, B, T, st, nullptr, nullptr, nullptr, 0, 0,
                       nullptr, &o2);
   }
@@ -807,7 +818,7 @@ WNB_API int wnb_post_bwd(const float* skip, const float* r1, const float* dlogit
     const NtTcSeg s1[1] = {{dlogits, Q, 0, Q, wp2t, S, Q, 0, 0}};
     const NtTcSeg s2[1] = {{dh1, S, 0, S, wp1t, S, S, 0, 0}};
     if (post_split(S)) {
-      const NtTcOpts o{2, 0, 0, 0, nt_default_m_tiles()};
+      const NtTcOpts o{2, 0, 0, 0, post_m_tiles()};
       if ((rc = gemm_nt_tc(s1, 1, S / 2, dh1, S, nullptr, r1, S, nullptr, 0, 0, 0, B, T, st, nullptr, nullptr, nullptr, 0, 0,
                            nullptr, &o)) != WNB_OK)
         return rc;
@@ -818,8 +829,14 @@ WNB_API int wnb_post_bwd(const float* skip, const float* r1, const float* dlogit
       if ((rc = gemm_nt_tc(s1, 1, S, dh1, S, nullptr, r1, S, nullptr, 0, 0, 0, B, T, st)) != WNB_OK) return rc;
       if ((rc = gemm_nt_tc(s2, 1, S, dskip, S, nullptr, skip, S, nullptr, 0, 0, 0, B, T, st)) != WNB_OK) return rc;
     }
-    if ((rc = wgrad_tc_split(dlogits, Q, Q, r1, S, S, dwp2, S, dbp2, B, T, st)) != WNB_OK) return rc;
-    return wgrad_tc_split(dh1, S, S, skip, S, S, dwp1, S, dbp1, B, T, st);
+    static const bool old_split = [] { const char* e = getenv("WNB_POST_WG_OLD"); return e && e[0] == '1'; }();
+    if (old_split) {
+      if ((rc = wgrad_tc_split(dlogits, Q, Q, r1, S, S, dwp2, S, dbp2, B, T, st)) != WNB_OK) return rc;
+      return wgrad_tc_split(dh1, S, S, skip, S, S, dwp1, S, dbp1, B, T, st);
+    }
+    // (2 M-blocks x 128-column groups per launch: a squarer tile than 4 M-blocks x 64 columns -- dWp1 320 -> ? us)
+    if ((rc = wgrad_tc_concat(dlogits, Q, nullptr, 0, Q, r1, S, S, 0, dwp2, S, dbp2, B, T, st)) != WNB_OK) return rc;
+    return wgrad_tc_concat(dh1, S, nullptr, 0, S, skip, S, S, 0, dwp1, S, dbp1, B, T, st);
   }
   {  // dh1[t][c] = (sum_q wp2[q][c] dlogits[t][q]) * (r1 > 0)
     NtParams p{};
