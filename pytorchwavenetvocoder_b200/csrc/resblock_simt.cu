@@ -353,11 +353,14 @@ static int pick_tchunk(int B, int T, int tiles) {
 
 // N == 512 GEMMs of the post network run as two 256-column blocks: the accumulators are then double-buffered and the
 // epilogue of one tile overlaps the mainloop of the next (-0.2 ms on the 10 ms step); WNB_POST_SPLIT=0 switches it off
-// two time tiles per weight chunk in the post-network GEMMs (K = 256 / 512: short main loops, mask epilogues);
-// WNB_POST_MT=1 selects one tile with double-buffered accumulators instead (A/B switch)
+// Time tiles per weight chunk in the post-network GEMMs.  Measured on B200 (one run, 8.6-8.9 ms steps): ONE tile with
+// double-buffered accumulators beats two tiles by 0.4 ms per step here -- K is 256 / 512 (short main loops) and the
+// epilogues are heavy (bias + ReLU, sign masks read from memory), so overlapping the epilogue with the next tile's main
+// loop is worth more than halving the weight traffic; the K = 1920 skip GEMM and the store-only dZ_all GEMM are the
+// opposite case.  WNB_POST_MT=2 selects the two-tile form.
 static int post_m_tiles() {
-  static const int mt = [] { const char* e = getenv("WNB_POST_MT"); return (e && e[0] == '1') ? 1 : ((e && e[0] == '2') ? 2 : 0); }();
-  return mt ? mt : nt_default_m_tiles();
+  static const int mt = [] { const char* e = getenv("WNB_POST_MT"); return (e && e[0] == '2') ? 2 : 1; }();
+  return mt;
 }
 
 static bool post_split(int S) {
@@ -492,7 +495,8 @@ static int composed_gc(int R) { return (R % 128 == 0) ? 128 : 64; }
 static NtTcOpts plain_opts(int N) {
   NtTcOpts o{1, 0, 0, 0, 1, 0};
   if (N > 256 && N % 256 == 0) o.n_blocks = N / 256;
-  if (N / o.n_blocks <= 256) o.m_tiles = nt_default_m_tiles();
+  static const int cmt = [] { const char* e = getenv("WNB_COMPOSED_MT"); return (e && e[0] == '1') ? 1 : 2; }();
+  if (N / o.n_blocks <= 256) o.m_tiles = cmt == 1 ? 1 : nt_default_m_tiles();
   return o;
 }
 
@@ -829,12 +833,12 @@ WNB_API int wnb_post_bwd(const float* skip, const float* r1, const float* dlogit
       if ((rc = gemm_nt_tc(s1, 1, S, dh1, S, nullptr, r1, S, nullptr, 0, 0, 0, B, T, st)) != WNB_OK) return rc;
       if ((rc = gemm_nt_tc(s2, 1, S, dskip, S, nullptr, skip, S, nullptr, 0, 0, 0, B, T, st)) != WNB_OK) return rc;
     }
-    static const bool old_split = [] { const char* e = getenv("WNB_POST_WG_OLD"); return e && e[0] == '1'; }();
+    // (4 M-blocks x 64-column groups per launch; 2 x (2 M-blocks x 128 columns) was measured 0.09 ms slower per step)
+    static const bool old_split = [] { const char* e = getenv("WNB_POST_WG_OLD"); return !(e && e[0] == '0'); }();
     if (old_split) {
       if ((rc = wgrad_tc_split(dlogits, Q, Q, r1, S, S, dwp2, S, dbp2, B, T, st)) != WNB_OK) return rc;
       return wgrad_tc_split(dh1, S, S, skip, S, S, dwp1, S, dbp1, B, T, st);
     }
-    // (2 M-blocks x 128-column groups per launch: a squarer tile than 4 M-blocks x 64 columns -- dWp1 320 -> ? us)
     if ((rc = wgrad_tc_concat(dlogits, Q, nullptr, 0, Q, r1, S, S, 0, dwp2, S, dbp2, B, T, st)) != WNB_OK) return rc;
     return wgrad_tc_concat(dh1, S, nullptr, 0, S, skip, S, S, 0, dwp1, S, dbp1, B, T, st);
   }
