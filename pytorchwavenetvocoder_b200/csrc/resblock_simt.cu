@@ -353,8 +353,8 @@ static int pick_tchunk(int B, int T, int tiles) {
 
 // N == 512 GEMMs of the post network run as two 256-column blocks: the accumulators are then double-buffered and the
 // epilogue of one tile overlaps the mainloop of the next (-0.2 ms on the 10 ms step); WNB_POST_SPLIT=0 switches it off
-// Time tiles per weight chunk in the post-network GEMMs.  Measured on B200 (one run, 8.6-8.9 ms steps): ONE tile with
-// double-buffered accumulators beats two tiles by 0.4 ms per step here -- K is 256 / 512 (short main loops) and the
+// Time tiles per weight chunk in the post-network GEMMs.  Measured on B200 (same box, 20 steps each): ONE tile with
+// double-buffered accumulators beats two tiles by 0.12-0.16 ms per step here -- K is 256 / 512 (short main loops) and the
 // epilogues are heavy (bias + ReLU, sign masks read from memory), so overlapping the epilogue with the next tile's main
 // loop is worth more than halving the weight traffic; the K = 1920 skip GEMM and the store-only dZ_all GEMM are the
 // opposite case.  WNB_POST_MT=2 selects the two-tile form.
@@ -833,8 +833,9 @@ WNB_API int wnb_post_bwd(const float* skip, const float* r1, const float* dlogit
       if ((rc = gemm_nt_tc(s1, 1, S, dh1, S, nullptr, r1, S, nullptr, 0, 0, 0, B, T, st)) != WNB_OK) return rc;
       if ((rc = gemm_nt_tc(s2, 1, S, dskip, S, nullptr, skip, S, nullptr, 0, 0, 0, B, T, st)) != WNB_OK) return rc;
     }
-    // (4 M-blocks x 64-column groups per launch; 2 x (2 M-blocks x 128 columns) was measured 0.09 ms slower per step)
-    static const bool old_split = [] { const char* e = getenv("WNB_POST_WG_OLD"); return !(e && e[0] == '0'); }();
+    // 2 launches of (2 M-blocks x 128-column groups) for dWp1: a squarer tile than 4 M-blocks x 64 columns; same-box
+    // A/B (two repetitions each): 8.90 / 8.95 ms per step against 8.97 / 8.97 (WNB_POST_WG_OLD=1 selects the old split)
+    static const bool old_split = [] { const char* e = getenv("WNB_POST_WG_OLD"); return e && e[0] == '1'; }();
     if (old_split) {
       if ((rc = wgrad_tc_split(dlogits, Q, Q, r1, S, S, dwp2, S, dbp2, B, T, st)) != WNB_OK) return rc;
       return wgrad_tc_split(dh1, S, S, skip, S, S, dwp1, S, dbp1, B, T, st);
