@@ -85,9 +85,11 @@ def test_pack_and_unpack_tables(cfg_t):
             assert v is None and p.grad is None, name
             continue
         np.testing.assert_allclose(v.numpy(), 0.5 * p.grad.numpy(), rtol=1e-6, atol=1e-6, err_msg=name)
-    # views are 16-byte aligned slices in parameters() order
+    # gap-free slices; every parameter whose size is a multiple of 4 floats starts 16-byte aligned
     offs = [plan.grad_off[n] for n in plan.grad_names]
-    assert offs == sorted(offs) and all(o % 4 == 0 for o in offs)
+    sizes = [dict(plan.params)[n].numel() for n in plan.grad_names]
+    assert offs == sorted(offs) and offs[0] == 0 and all(o + s == o2 for o, s, o2 in zip(offs, sizes, offs[1:] + [plan.grad_size]))
+    assert all(o % 4 == 0 for o, s in zip(offs, sizes) if s % 4 == 0)
 
 
 def test_decode_cluster_stream_is_a_split_of_the_single_cta_stream():
