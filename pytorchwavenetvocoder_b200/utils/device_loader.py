@@ -71,6 +71,29 @@ def _f32_scaler_mode():
     raise _lib.WnbError("unrecognised StandardScaler float32 arithmetic: use --host_loader true")
 
 
+class _PinnedSlot(object):
+    """One reusable pinned staging buffer of a reader thread.  Pinned memory is allocated ONCE per slot (and again only
+    when an utterance is larger than anything seen): `pin_memory()` per utterance goes through cudaHostAlloc whenever
+    the host allocator has no free block, which takes the driver lock the training loop's launches need."""
+
+    def __init__(self):
+        self.x = self.h = None
+        self.event = None          # H2D copies of the last use of this slot (set by the consumer)
+
+    def fill(self, x, h):
+        if self.event is not None:
+            self.event.synchronize()           # the previous contents have left for the device
+        n, nf = x.shape[0], h.shape[0]
+        if self.x is None or self.x.numel() < n:
+            self.x = torch.empty(max(n, 1) * 5 // 4, dtype=torch.float32).pin_memory()
+        ht = torch.from_numpy(h)
+        if self.h is None or self.h.dtype != ht.dtype or self.h.shape[0] < nf or self.h.shape[1:] != ht.shape[1:]:
+            self.h = torch.empty((max(nf, 1) * 5 // 4,) + tuple(ht.shape[1:]), dtype=ht.dtype).pin_memory()
+        self.x[:n].copy_(torch.from_numpy(x))
+        self.h[:nf].copy_(ht)
+        return self.x[:n], self.h[:nf]
+
+
 class WindowPlanner(object):
     """The reference's window / batch bookkeeping (train.py:117, 160-185, 202-230) on stream positions only: cut every
     window the buffer allows after each appended utterance, B consecutive windows make a batch, and at the end of an epoch
@@ -173,16 +196,19 @@ class DeviceTrainGenerator(object):
         import time
         try:
             pos = k
+            slots = [_PinnedSlot() for _ in range(self.queues[k].maxsize + 3)]   # more slots than can be in flight
+            i = 0
             while True:
                 w, f, last_of_epoch = self._utterance(pos)
                 t0 = time.time()
                 x, h = load_pair_frames(w, f, self.feature_type, self.U, self.use_up, self.use_spk)
-                xp = torch.from_numpy(x).pin_memory()
-                hp = torch.from_numpy(h).pin_memory()
+                slot = slots[i % len(slots)]
+                xp, hp = slot.fill(x, h)
                 self.stats["reader_s"] += time.time() - t0
                 self.stats["utts"] += 1
-                self.queues[k].put((xp, hp, last_of_epoch))
+                self.queues[k].put((xp, hp, last_of_epoch, slot))
                 pos += self.n_readers
+                i += 1
         except BaseException as e:     # noqa: BLE001 -- surface reader failures in the consumer
             self.queues[k].put(e)
 
@@ -205,7 +231,7 @@ class DeviceTrainGenerator(object):
         if first < n:
             ring[:n - first].copy_(src[first:], non_blocking=True)
 
-    def _append(self, xp, hp, last_of_epoch=False):
+    def _append(self, xp, hp, last_of_epoch=False, slot=None):
         n, nf = xp.shape[0], hp.shape[0]
         if n == 0:
             self.plan.append(0, last_of_epoch)
@@ -241,6 +267,8 @@ class DeviceTrainGenerator(object):
             ev = torch.cuda.Event()
             ev.record(self.copy_stream)
         self.append_event = ev
+        if slot is not None:
+            slot.event = ev                                # the reader may refill the slot once these copies are done
         self.tail_s += n
         self.tail_f += nf
         self.plan.append(n, last_of_epoch)
