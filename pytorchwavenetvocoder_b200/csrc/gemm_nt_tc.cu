@@ -8,7 +8,10 @@
 // a swizzled per-warp staging box and a TMA store or TMA reduce-add (.add.f32) into the (B,T,N) output; gate forward /
 // backward epilogues for the residual blocks.  The kernel is instantiated per epilogue kind (EPI_*) so each variant
 // gets its own register allocation.  Options: column blocks (tiles ordered block-fastest so the A tile is shared
-// through L2), split output, programmatic dependent launch.
+// through L2), split output, programmatic dependent launch; round 2: two 128-row time tiles per weight chunk
+// (NtTcOpts::m_tiles: the K >= 512 GEMMs were bound by the L2 -> SM weight stream, not by HBM or the tensor pipe), gate
+// epilogues over 64 or 128 gate channels per tile (composed path), epilogue operands staged by the producer as TMA tiles
+// (NtTcOpts::stage_epilogue_operand: measured slower, off by default).
 // Used for: the post network forward (wavenet.py:518-523) and backward, the hoisted skip GEMMs, the gate backward,
 // the residual-stream data gradient dX (two time-shifted segments) with the aux gradient dhaux (reduce-add).
 #include <cuda.h>
