@@ -33,7 +33,8 @@ constexpr int kEpiWarpsN = 8;            // two per SM sub-partition: (TMEM lane
 constexpr int kThreadsN = 32 * (2 + kEpiWarpsN);
 constexpr int kMaxSeg = 4;
 
-struct Seg { int amap; int shift; int K; int bmap; int b_k0; int b_n0; int b_n1; };  // b_n1 >= 0: rows of the 2nd half of N
+struct Seg { int amap; int shift; int K; int bmap; int b_k0; int b_n0; int b_n1;   // b_n1 >= 0: rows of the 2nd half of N
+             int n_lo, n_cnt, fresh; };   // resident weights: accumulator columns [n_lo, n_lo + n_cnt), first MMA overwrites
 struct alignas(64) Params {
   CUtensorMap maps[11];   // [0..3] A tensors, [4..7] weight matrices, [8] output, [9] second output, [10] epilogue tile
   Seg seg[kMaxSeg];
@@ -63,6 +64,15 @@ struct alignas(64) Params {
   // time tile (maps[10], two swizzled sub-tiles) instead of per-lane row loads from global memory: the epilogue warps
   // pace these kernels and were stalled on exactly those loads (ncu: 51 % long-scoreboard on L1TEX).
   int etile;
+  // wres != 0 (NtTcOpts::resident_weights): every weight chunk of every segment is loaded ONCE per CTA into shared memory
+  // (wres_bytes, in front of the ring) and the ring carries activations only -- the residual-block kernels (gate backward,
+  // dX) were paced by the per-SM L2 -> SM ingest, 61 % / 43 % of which was the same 172 / 96 KB of weights again for every
+  // 128-row tile.  Segments name the accumulator columns they touch (zero blocks of a block matrix are skipped).
+  int wres, wres_bytes;
+  // pf > 0: the producer L2-prefetches the activation boxes of the tile `pf` rounds ahead (no shared memory needed): with
+  // 64-80 KB of ring per SM the block kernels were bound by DRAM latency x bytes in flight.  epf: also the epilogue's
+  // per-row operand tile (1: dz slice, 2: residual add) through maps[10].
+  int pf, epf;
 };
 
 // barrier layout in smem: full[nstages] empty[nstages] dfull[2] dempty[2]
@@ -93,8 +103,9 @@ __global__ void __launch_bounds__(kThreadsN, 1) gemm_nt_tc_kernel(const __grid_c
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int N = p.N;
   const int a_bytes = p.mt * kASub;
-  const int stage_bytes = a_bytes + N * 128;
-  unsigned char* stg_base = smem + (size_t)p.nstages * stage_bytes;
+  const int stage_bytes = a_bytes + (p.wres ? 0 : N * 128);
+  unsigned char* ring = smem + p.wres_bytes;
+  unsigned char* stg_base = ring + (size_t)p.nstages * stage_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(stg_base + kEpiWarpsN * p.stg_boxes * kStg + (p.etile ? 2 * kASub : 0));
   uint64_t* full = bars;
   uint64_t* empty = bars + p.nstages;
@@ -102,7 +113,8 @@ __global__ void __launch_bounds__(kThreadsN, 1) gemm_nt_tc_kernel(const __grid_c
   uint64_t* dempty = dfull + 2;
   uint64_t* efull = dempty + 2;       // epilogue-operand tile landed / consumed (etile)
   uint64_t* eempty = efull + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(eempty + 1);
+  uint64_t* wfull = eempty + 1;       // resident weights landed (wres)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull + 1);
   unsigned char* ebuf = stg_base + kEpiWarpsN * p.stg_boxes * kStg;   // 2 x [128 x 32] sub-tiles when etile
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rows_per_tile = kTM * p.mt;
@@ -122,6 +134,7 @@ __global__ void __launch_bounds__(kThreadsN, 1) gemm_nt_tc_kernel(const __grid_c
     }
     ptx::mbar_init(efull, 1);
     ptx::mbar_init(eempty, 32 * kEpiWarpsN);
+    ptx::mbar_init(wfull, 1);
     ptx::fence_barrier_init();
   }
   if (warp == 1) ptx::tmem_alloc<512>(tmem_slot);
@@ -141,9 +154,32 @@ __global__ void __launch_bounds__(kThreadsN, 1) gemm_nt_tc_kernel(const __grid_c
     if (ptx::elect_one()) {
       for (int i = 0; i < 11; i++) ptx::prefetch_tmap(&p.maps[i]);
       uint32_t st = 0, ph = 0, pit = 0;
+      if (p.wres) {   // all weight chunks, once
+        ptx::mbar_arrive_expect_tx(wfull, p.wres_bytes);
+        unsigned char* dst = smem;
+        for (int s = 0; s < p.nseg; s++) {
+          const Seg sg = p.seg[s];
+          for (int kc = 0; kc < sg.K / 32; kc++, dst += sg.n_cnt * 128)
+            ptx::tma_load_2d(dst, &p.maps[sg.bmap], wfull, sg.b_k0 + kc * 32, sg.b_n0 + sg.n_lo);
+        }
+      }
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, pit++) {
         const int tt = tile / p.nblk, ncol0 = (tile - tt * p.nblk) * N;
         const int b = tt / tiles_per_b, t0 = (tt - b * tiles_per_b) * rows_per_tile;
+        if (p.pf) {
+          const int ptile = tile + p.pf * (int)gridDim.x;
+          if (ptile < ntiles) {
+            const int ptt = ptile / p.nblk, pb = ptt / tiles_per_b, pt0 = (ptt - pb * tiles_per_b) * rows_per_tile;
+            for (int s = 0; s < p.nseg; s++)
+              for (int kc = 0; kc < p.seg[s].K / 32; kc++)
+                for (int mh = 0; mh < p.mt; mh++)
+                  ptx::tma_prefetch_3d(&p.maps[p.seg[s].amap], kc * 32, pt0 + mh * kTM + p.seg[s].shift, pb);
+            if (p.epf) {
+              ptx::tma_prefetch_3d(&p.maps[10], 0, pt0, pb);
+              ptx::tma_prefetch_3d(&p.maps[10], 32, pt0, pb);
+            }
+          }
+        }
         if (p.etile) {   // the epilogue's operand tile of this time tile goes first: it is needed as soon as the accumulator is
           wait(eempty, (pit & 1) ^ 1, NP_P_EMPTY);
           ptx::mbar_arrive_expect_tx(efull, 2 * kASub);
@@ -155,8 +191,12 @@ __global__ void __launch_bounds__(kThreadsN, 1) gemm_nt_tc_kernel(const __grid_c
           for (int kc = 0; kc < sg.K / 32; kc++) {
             wait(&empty[st], ph ^ 1, NP_P_EMPTY);
             ptx::mbar_arrive_expect_tx(&full[st], stage_bytes);
-            unsigned char* dst = smem + (size_t)st * stage_bytes;
+            unsigned char* dst = ring + (size_t)st * stage_bytes;
             ptx::tma_load_3d(dst, &p.maps[sg.amap], &full[st], kc * 32, t0 + sg.shift, b);
+            if (p.wres) {
+              if (++st == (uint32_t)p.nstages) { st = 0; ph ^= 1; }
+              continue;
+            }
             if (p.mt == 2)   // (rows past T are zero-filled by TMA, the matching stores are clipped)
               ptx::tma_load_3d(dst + kASub, &p.maps[sg.amap], &full[st], kc * 32, t0 + kTM + sg.shift, b);
             if (sg.b_n1 >= 0) {   // N = two row ranges of N/2 each (sigmoid rows, tanh rows)
@@ -175,8 +215,10 @@ __global__ void __launch_bounds__(kThreadsN, 1) gemm_nt_tc_kernel(const __grid_c
     if (ptx::elect_one()) {
       const int nmma = N > 256 ? 256 : N;
       const uint32_t idesc = ptx::idesc_tf32(128, nmma);
-      const uint32_t s_lo0 = ptx::desc_lo(ptx::smem_u32(smem), 16);
+      const uint32_t s_lo0 = ptx::desc_lo(ptx::smem_u32(ring), 16);
+      const uint32_t w_lo0 = ptx::desc_lo(ptx::smem_u32(smem), 16);
       constexpr uint32_t hi = ptx::kDescHiKSw128;
+      if (p.wres) wait(wfull, 0, NP_M_FULL);
       const uint32_t stage_step = (uint32_t)stage_bytes >> 4;
       uint32_t st = 0, ph = 0, it = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
@@ -207,6 +249,26 @@ __global__ void __launch_bounds__(kThreadsN, 1) gemm_nt_tc_kernel(const __grid_c
         wait(&dempty[buf], (use & 1) ^ 1, NP_M_DEMPTY);
         ptx::tc_fence_after();
         const uint32_t dcol = buf * N;
+        if (p.wres) {
+          uint32_t b_lo = w_lo0;
+          for (int s = 0; s < p.nseg; s++) {
+            const Seg sg = p.seg[s];
+            const uint32_t idesc_s = ptx::idesc_tf32(128, sg.n_cnt);
+            for (int kc = 0; kc < sg.K / 32; kc++, b_lo += (uint32_t)(sg.n_cnt * 128) >> 4) {
+              wait(&full[st], ph, NP_M_FULL);
+              ptx::tc_fence_after();
+              const uint32_t a_lo = s_lo0 + st * stage_step;
+#pragma unroll
+              for (int k = 0; k < 4; k++)
+                ptx::mma_tf32_ss(tmem + dcol + sg.n_lo, ptx::desc64(a_lo + 2 * k, hi), ptx::desc64(b_lo + 2 * k, hi), idesc_s,
+                                 !(sg.fresh && (kc | k) == 0));
+              ptx::tc_commit(&empty[st]);
+              if (++st == (uint32_t)p.nstages) { st = 0; ph ^= 1; }
+            }
+          }
+          ptx::tc_commit(&dfull[buf]);
+          continue;
+        }
         for (int kc = 0; kc < kchunks; kc++) {
           wait(&full[st], ph, NP_M_FULL);
           ptx::tc_fence_after();
@@ -244,19 +306,35 @@ __global__ void __launch_bounds__(kThreadsN, 1) gemm_nt_tc_kernel(const __grid_c
       const uint32_t use = (p.mt == 2) ? it : ((p.nacc == 2) ? (it >> 1) : it);
       // operands of the epilogue that do not depend on the accumulator are requested before waiting for it, so
       // their DRAM latency overlaps the mainloop of this tile: dz of the gate backward, `add` of the first chunk
+      // They are loaded COALESCED -- load i of the warp covers rows 4i .. 4i+3 of its 32-row slab, 8 lanes x 16 B per row (4
+      // full 128-B lines per request; one row per lane was 32 lines per request and cost the gate backward 13 of its 60 us)
+      // -- and transposed to one row per lane through the warp's own staging box once that is free (xpose_pre below).
       float4 pre[8];
-      const bool pre_dz = EPI != EPI_PLAIN && p.gate_mode >= 2 && row_ok && hf * 32 < 64 && !p.etile;
-      const bool pre_add = EPI == EPI_PLAIN && p.add && row_ok && hf * 32 < N && !(p.out2_col0 > 0 && hf * 32 >= p.out2_col0) &&
-                           !p.etile;
-      if (pre_dz) {
-        const float4* dr = reinterpret_cast<const float4*>(p.gate_dz + grow * p.gate_ld_dz + p.gate_c0 + hf * 32);
+      const bool pre_dz = EPI != EPI_PLAIN && p.gate_mode >= 2 && hf * 32 < 64 && !p.etile;
+      const bool pre_add = EPI == EPI_PLAIN && p.add && hf * 32 < N && !(p.out2_col0 > 0 && hf * 32 >= p.out2_col0) && !p.etile;
+      if (pre_dz || pre_add) {
+        const float* src = pre_dz ? p.gate_dz + p.gate_c0 + hf * 32 : p.add + ncol0 + hf * 32;
+        const size_t ld = pre_dz ? (size_t)p.gate_ld_dz : (size_t)p.ldadd;
+        const int tr = t0 + q * 32 + (lane >> 3);
 #pragma unroll
-        for (int j = 0; j < 8; j++) pre[j] = __ldg(dr + j);
-      } else if (pre_add) {
-        const float4* ar = reinterpret_cast<const float4*>(p.add + grow * p.ldadd + ncol0 + hf * 32);
-#pragma unroll
-        for (int j = 0; j < 8; j++) pre[j] = __ldg(ar + j);
+        for (int i = 0; i < 8; i++)
+          pre[i] = (tr + 4 * i < p.T) ? __ldg(reinterpret_cast<const float4*>(src + ((size_t)b * p.T + tr + 4 * i) * ld) + (lane & 7))
+                                      : make_float4(0.f, 0.f, 0.f, 0.f);
       }
+      // pre[] (rows 4i + lane/8, 16-B piece lane%8) -> this lane's own row, pieces 0..7, through `box` (free: the caller has
+      // waited for the bulk store that last read it); rows past T arrive as zeros
+      auto xpose_pre = [&](unsigned char* box) {
+        const uint32_t wb = ptx::smem_u32(box);
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+          const int r = 4 * i + (lane >> 3);
+          ptx::st_shared_v4(wb + r * 128 + (((lane & 7) ^ (r & 7)) << 4), pre[i].x, pre[i].y, pre[i].z, pre[i].w);
+        }
+        __syncwarp();
+        const float4* rr = reinterpret_cast<const float4*>(box + lane * 128);
+#pragma unroll
+        for (int j = 0; j < 8; j++) pre[j] = rr[j ^ (lane & 7)];
+      };
       wait(&dfull[buf], use & 1, NP_E_DFULL);
       ptx::tc_fence_after();
       if (p.etile == 1) {   // this row's 32 dz channels out of the staged tile (rows past T were zero-filled by TMA)
@@ -265,6 +343,15 @@ __global__ void __launch_bounds__(kThreadsN, 1) gemm_nt_tc_kernel(const __grid_c
 #pragma unroll
         for (int j = 0; j < 8; j++) pre[j] = er[j ^ (lane & 7)];
         ptx::mbar_arrive(eempty);
+      }
+      if constexpr (EPI != EPI_GATE_BWD_NOZ) {
+        if (pre_dz || pre_add) {   // (the box the first chunk will be staged in; same wait as before that store)
+          if (lane == 0) {
+            if (box_mask) ptx::bulk_wait_read<1>(); else ptx::bulk_wait_read<0>();
+          }
+          __syncwarp();
+          xpose_pre(stg + (nstore & box_mask) * kStg);
+        }
       }
       if constexpr (EPI == EPI_GATE_BWD_NOZ) {
         // ---- gate backward without the z output (the stack path): two passes of 16 gate channels keep the live
@@ -277,6 +364,7 @@ __global__ void __launch_bounds__(kThreadsN, 1) gemm_nt_tc_kernel(const __grid_c
           __syncwarp();
           if constexpr (PROF) acc[NP_E_BULK] += clock64() - tb;
         }
+        if (pre_dz) xpose_pre(stg);
         const uint32_t sb0 = ptx::smem_u32(stg + lane * 128), sb1 = sb0 + kStg;
         const float4* bsv = reinterpret_cast<const float4*>(p.bias + c0);
         const float4* btv = reinterpret_cast<const float4*>(p.bias2 + c0);
@@ -304,7 +392,7 @@ __global__ void __launch_bounds__(kThreadsN, 1) gemm_nt_tc_kernel(const __grid_c
 #pragma unroll
             for (int k = 0; k < 4; k++) {
               const int i = 4 * jj + k;
-              float dz = (row_ok || p.etile) ? dzs[k] : 0.f;
+              float dz = dzs[k];   // (rows past T: zeros from the loader)
               if (p.gate_mode == 3) dz += dzp[i];
               const float sg = 0.5f * ptx::tanh_approx(0.5f * (a[i] + bsa[k])) + 0.5f;
               const float th = ptx::tanh_approx(g[i] + bta[k]);
@@ -606,15 +694,37 @@ int gemm_nt_tc(const NtTcSeg* segs, int nseg, int N, float* out, int ld_out, con
   Params p;
   memset(&p, 0, sizeof(p));
   const int nbox = gate ? N / 2 : (N > 256 ? 256 : N);   // (gate: two boxes of GC = N/2 rows, sigmoid rows and tanh rows)
+  // resident weights: the segments' column ranges must tile [0, N) front to back -- a range either starts where the
+  // covered prefix ends (its first MMA overwrites) or lies inside it (accumulates)
+  bool wres = opts && opts->resident_weights && !gate && N <= 256 && !(opts->n_blocks > 1) && opts->m_tiles != 2;
+  int wres_bytes = 0, covered = 0;
+  int n_lo[kMaxSeg], n_cnt[kMaxSeg], fresh[kMaxSeg];
+  for (int s = 0; s < nseg && wres; s++) {
+    n_cnt[s] = segs[s].n_cnt > 0 ? segs[s].n_cnt : N;
+    n_lo[s] = segs[s].n_cnt > 0 ? segs[s].n_lo : 0;
+    if (n_cnt[s] % 16 != 0 || n_lo[s] % 32 != 0 || n_lo[s] + n_cnt[s] > N) wres = false;
+    else if (n_lo[s] == covered) { fresh[s] = 1; covered += n_cnt[s]; }
+    else if (n_lo[s] + n_cnt[s] <= covered) fresh[s] = 0;
+    else wres = false;
+    wres_bytes += (segs[s].K / 32) * n_cnt[s] * 128;
+  }
+  if (wres && covered != N) wres = false;
+  if (opts && opts->resident_weights && !wres) {
+    set_error("gemm_nt_tc: resident weights need plain segments whose column ranges tile [0, N)");
+    return WNB_ERR_INVALID;
+  }
   for (int s = 0; s < nseg; s++) {
     if (segs[s].K % 32 != 0) { set_error("gemm_nt_tc: K must be a multiple of 32"); return WNB_ERR_INVALID; }
     if (!map3(&p.maps[s], segs[s].a, segs[s].CA, T, B, kTM) ||
-        !map2(&p.maps[4 + s], segs[s].w, segs[s].w_cols, segs[s].w_rows, nbox)) {
+        !map2(&p.maps[4 + s], segs[s].w, segs[s].w_cols, segs[s].w_rows, wres ? n_cnt[s] : nbox)) {
       set_error("gemm_nt_tc: tensor map creation failed");
       return WNB_ERR_CUDA;
     }
-    p.seg[s] = Seg{s, segs[s].shift, segs[s].K, 4 + s, segs[s].k0, segs[s].n0, -1};
+    p.seg[s] = Seg{s, segs[s].shift, segs[s].K, 4 + s, segs[s].k0, segs[s].n0, -1, wres ? n_lo[s] : 0, wres ? n_cnt[s] : N,
+                   wres ? fresh[s] : (s == 0)};
   }
+  p.wres = wres ? 1 : 0;
+  p.wres_bytes = wres ? wres_bytes : 0;
   for (int s = nseg; s < 4; s++) { p.maps[s] = p.maps[0]; p.maps[4 + s] = p.maps[4]; }
   if (!map3(&p.maps[8], out, ld_out, T, B, 32)) { set_error("gemm_nt_tc: output map failed"); return WNB_ERR_CUDA; }
   p.maps[9] = p.maps[8];
@@ -669,25 +779,32 @@ int gemm_nt_tc(const NtTcSeg* segs, int nseg, int N, float* out, int ld_out, con
   }
   p.stg_boxes = p.mt == 2 ? 1 : 2;
   p.maps[10] = p.maps[8];
-  if (opts && opts->stage_epilogue_operand && p.mt == 1) {
+  static int pf_dist = -1;
+  if (pf_dist < 0) { const char* e = getenv("WNB_NT_PF"); pf_dist = e ? atoi(e) : 1; if (pf_dist < 0 || pf_dist > 4) pf_dist = 1; }
+  p.pf = p.wres ? pf_dist : 0;
+  if (p.mt == 1 && ((opts && opts->stage_epilogue_operand) || p.pf)) {
     // 1: gate-backward dz slice (EPI_GATE_BWD_NOZ, R = 64 shorthand), 2: residual add of a <= 64-column primary output
+    const bool stage = opts && opts->stage_epilogue_operand;
     const bool dz_ok = p.gate_mode >= 2 && p.gate_skip_z && p.gate_R == 64 && p.gate_c0 == 0 && gate_dz &&
                        (reinterpret_cast<uintptr_t>(gate_dz) & 15) == 0 && p.gate_ld_dz % 4 == 0;
     const int primary = out2 ? out2_col0 : N;
     const bool add_ok = !p.gate_mode && add && !mask && primary == 64 && p.nblk == 1 &&
                         (reinterpret_cast<uintptr_t>(add) & 15) == 0 && ldadd % 4 == 0;
-    if (dz_ok && map3ld(&p.maps[10], gate_dz, 64, p.gate_ld_dz, T, B, kTM)) p.etile = 1;
-    else if (add_ok && map3ld(&p.maps[10], add, 64, ldadd, T, B, kTM)) p.etile = 2;
+    int kind = 0;
+    if (dz_ok && map3ld(&p.maps[10], gate_dz, 64, p.gate_ld_dz, T, B, kTM)) kind = 1;
+    else if (add_ok && map3ld(&p.maps[10], add, 64, ldadd, T, B, kTM)) kind = 2;
+    if (stage) p.etile = kind; else p.epf = kind;
   }
   const int ebytes = p.etile ? 2 * kASub : 0;
-  const int stage_bytes = p.mt * kASub + N * 128;
-  int nst = (int)((227 * 1024 - 1024 - 512 - kEpiWarpsN * p.stg_boxes * kStg - ebytes) / stage_bytes);
+  const int stage_bytes = p.mt * kASub + (p.wres ? 0 : N * 128);
+  int nst = (int)((227 * 1024 - 1024 - 512 - kEpiWarpsN * p.stg_boxes * kStg - ebytes - p.wres_bytes) / stage_bytes);
   static int max_stages = 0;
   if (!max_stages) { const char* e = getenv("WNB_NT_MAXSTAGES"); max_stages = e ? atoi(e) : 4; if (max_stages < 2) max_stages = 2; }
-  if (nst > max_stages) nst = max_stages;
+  const int cap = p.wres ? 8 : max_stages;   // (activation-only stages are 16 KB: take what is left)
+  if (nst > cap) nst = cap;
   if (nst < 2) { set_error("gemm_nt_tc: N too large"); return WNB_ERR_INVALID; }
   p.nstages = nst;
-  const size_t smem = (size_t)nst * stage_bytes + kEpiWarpsN * p.stg_boxes * kStg + ebytes + 512 + 1024;
+  const size_t smem = (size_t)p.wres_bytes + (size_t)nst * stage_bytes + kEpiWarpsN * p.stg_boxes * kStg + ebytes + 512 + 1024;
   WNB_CUDA(ensure_dynamic_smem(reinterpret_cast<const void*>(gemm_nt_tc_kernel<false, 0>), smem));
   WNB_CUDA(ensure_dynamic_smem(reinterpret_cast<const void*>(gemm_nt_tc_kernel<false, 1>), smem));
   WNB_CUDA(ensure_dynamic_smem(reinterpret_cast<const void*>(gemm_nt_tc_kernel<false, 2>), smem));

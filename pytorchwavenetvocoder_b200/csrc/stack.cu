@@ -38,6 +38,13 @@ static int stage_epi() {
   return on;
 }
 
+// The gate-backward and dX GEMMs of a block keep their weights (96 / 80 KB) in shared memory for the whole launch instead
+// of streaming them from L2 for every 128-row tile; WNB_NT_WRES=0 restores the streaming ring (A/B runs).
+static int resident_w() {
+  static const int on = [] { const char* e = getenv("WNB_NT_WRES"); return (e && e[0] == '0') ? 0 : 1; }();
+  return on && !stage_epi();
+}
+
 static bool stack_supported(int R, int S, int Ap, int ks, int L) {
   if (!resblock_fwd_z_supported(R, Ap, ks)) return false;
   if (L < 1 || L > 64 /* wnb_stack_bwd's segment table, wgrad kMaxSeg */) return false;
@@ -163,9 +170,12 @@ WNB_API int wnb_stack_bwd(const float* xs, const float* haux, const float* zall,
        // matrix wgate_l = [[W1, 0], [0, W2res^T]] (3R x (K1+R)): accumulator columns 0..2R-1 are the gate
        // pre-activations, columns 2R..3R-1 the residual part of dz; the epilogue turns both into dpre.
       const float* wg = wgate + (size_t)l * 3 * R * (K1 + R);
-      const NtTcSeg sg[4] = {{xin, R, -d, R, wg, 3 * R, K1 + R, 0, 0}, {xin, R, 0, R, wg, 3 * R, K1 + R, R, 0},
-                             {haux, Ap, 0, Ap, wg, 3 * R, K1 + R, 2 * R, 0}, {dout, R, 0, R, wg, 3 * R, K1 + R, K1, 0}};
-      const NtTcOpts o{1, ldz, 1, dout ? 1 : 0, 1, stage_epi()};
+      // (resident weights: the zero blocks are skipped -- the first three segments touch accumulator columns 0..2R-1, the
+      //  dout segment columns 2R..3R-1)
+      const NtTcSeg sg[4] = {{xin, R, -d, R, wg, 3 * R, K1 + R, 0, 0, 0, 2 * R}, {xin, R, 0, R, wg, 3 * R, K1 + R, R, 0, 0, 2 * R},
+                             {haux, Ap, 0, Ap, wg, 3 * R, K1 + R, 2 * R, 0, 0, 2 * R},
+                             {dout, R, 0, R, wg, 3 * R, K1 + R, K1, 0, 2 * R, R}};
+      const NtTcOpts o{1, ldz, 1, dout ? 1 : 0, 1, stage_epi(), resident_w()};
       ProfScope ps(WNB_PROF_GATE_BWD, st);
       if ((rc = gemm_nt_tc(sg, dout ? 4 : 3, dout ? 3 * R : 2 * R, dxin /* z output suppressed */, R,
                            b1 + (size_t)l * 2 * R, nullptr, 0, nullptr, 0, 0, 0, B, T, st, dzl, dpre, nullptr, 0, 0,
@@ -175,15 +185,16 @@ WNB_API int wnb_stack_bwd(const float* xs, const float* haux, const float* zall,
     // dxin = dout + dpre(t+d) W1[:, tap0] + dpre(t) W1[:, tap1]   and   dhaux += dpre(t) W1[:, aux]
     if (dhaux) {
       ProfScope ps(WNB_PROF_DX_GEMM, st);
-      const NtTcSeg sx[2] = {{dpre, 2 * R, d, 2 * R, w1tl, R, 2 * R, 0, 0}, {dpre, 2 * R, 0, 2 * R, w1tl, K1, 2 * R, 0, R}};
-      const NtTcOpts ox{1, 0, 0, 0, 1, stage_epi()};
+      // (the unshifted segment covers all R + Ap columns and goes first; the shifted one only adds to the R dx columns)
+      const NtTcSeg sx[2] = {{dpre, 2 * R, 0, 2 * R, w1tl, K1, 2 * R, 0, R, 0, R + Ap}, {dpre, 2 * R, d, 2 * R, w1tl, R, 2 * R, 0, 0, 0, R}};
+      const NtTcOpts ox{1, 0, 0, 0, 1, stage_epi(), resident_w()};
       if ((rc = gemm_nt_tc(sx, 2, R + Ap, dxin, R, nullptr, nullptr, 0, dout, R, 0, 0, B, T, st, nullptr, nullptr, dhaux,
                            Ap, R, nullptr, &ox)) != WNB_OK)
         return rc;
     } else {
       ProfScope ps(WNB_PROF_DX_GEMM, st);
       const NtTcSeg sx[2] = {{dpre, 2 * R, d, 2 * R, w1tl, K1, 2 * R, 0, 0}, {dpre, 2 * R, 0, 2 * R, w1tl, K1, 2 * R, 0, R}};
-      const NtTcOpts ox{1, 0, 0, 0, 1, stage_epi()};
+      const NtTcOpts ox{1, 0, 0, 0, 1, stage_epi(), resident_w()};
       if ((rc = gemm_nt_tc(sx, 2, R, dxin, R, nullptr, nullptr, 0, dout, R, 0, 0, B, T, st, nullptr, nullptr, nullptr, 0, 0,
                            nullptr, &ox)) != WNB_OK)
         return rc;

@@ -27,7 +27,10 @@ int wgrad_tc(const WgOperand* a_ops, int na_ops, const WgOperand* b_ops, int nb_
 // ---- NT GEMM (gemm_nt_tc.cu):  out[b,t,n] = sum_seg sum_k A_seg[b,t+shift,k] W_seg[n0+n][k0+k]  (+ epilogues) ----
 // One segment: activation tensor (B,T,CA) read at rows t+shift, channels [0,K); weight matrix w (rows x ldw,
 // K-contiguous) rows [n0, n0+N), columns [k0, k0+K).
-struct NtTcSeg { const float* a; int CA; int shift; int K; const float* w; int w_rows; int w_cols; int k0; int n0; };
+struct NtTcSeg { const float* a; int CA; int shift; int K; const float* w; int w_rows; int w_cols; int k0; int n0;
+                 // NtTcOpts::resident_weights only: this segment touches output columns [n_lo, n_lo + n_cnt) (weight rows
+                 // n0 + n_lo ..); n_cnt == 0 means all N.  Lets a block matrix skip its zero blocks.
+                 int n_lo = 0; int n_cnt = 0; };
 // gate epilogue request: mode 1 = forward (z out), 2 = backward (dz in, z + dpre out); channels c0..c0+63 of R
 struct NtTcGate { int mode; int c0; int R; const float* bias_sig; const float* bias_tanh; const float* dz; float* dpre; };
 struct NtTcOpts {
@@ -40,6 +43,8 @@ struct NtTcOpts {
                      //    halves the L2 -> SM weight traffic of the K >= 512 GEMMs (skip, dZ_all, post network)
   int stage_epilogue_operand;   // 1: the gate-backward dz slice / a 64-column residual `add` reaches the epilogue as a TMA
                                 //    tile loaded by the producer warp instead of per-lane row loads (gate backward, dX)
+  int resident_weights;   // 1: all weight chunks live in shared memory for the whole launch (loaded once per CTA), the ring
+                          //    carries activations only; needs sum_seg K * n_cnt * 4 bytes (<= ~140 KB) and m_tiles == 1
 };
 // default of NtTcOpts::m_tiles for the K >= 512 GEMMs: 2, WNB_NT_MT=1 in the environment restores one tile per CTA
 int nt_default_m_tiles();
