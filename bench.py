@@ -451,8 +451,8 @@ TRAFFIC_NCU = {"fp32": None, "tf32": 814.14e6}
 # z / xout stores live in the 126 MB L2), r2_ncu_nt_summary.txt (launch 0 skip GEMM, 5 dZ_all GEMM, 8 gate backward of a
 # block with a residual input, 9 its dX), r2_ncu_wg_summary.txt (2 dW1, 3 dW2res, 4/5 dWskip)
 STACK_KINDS = ["fwd_block", "skip_gemm", "dzall_gemm", "gate_bwd", "dx_gemm", "dw1", "dw2res", "dwskip"]
-TRAFFIC_NCU_STACK = {"fwd_block": 114.46e6, "skip_gemm": 1807.5e6, "dzall_gemm": 1740.2e6, "gate_bwd": 223.97e6,
-                     "dx_gemm": 204.21e6, "dw1": 4896.0e6, "dw2res": 2741.8e6, "dwskip": 1610.2e6}
+TRAFFIC_NCU_STACK = {"fwd_block": 112.8e6, "skip_gemm": 1807.5e6, "dzall_gemm": 1740.2e6, "gate_bwd": 224.3e6,
+                     "dx_gemm": 204.5e6, "dw1": 4896.0e6, "dw2res": 2741.8e6, "dwskip": 1610.2e6}
 
 
 def run_decode(args, dev, rank, world, dist):

@@ -73,6 +73,8 @@ struct alignas(64) Params {
   // 64-80 KB of ring per SM the block kernels were bound by DRAM latency x bytes in flight.  epf: also the epilogue's
   // per-row operand tile (1: dz slice, 2: residual add) through maps[10].
   int pf, epf;
+  int rev;   // NtTcOpts::reverse
+  int grp;   // resident-weights mode: activation chunks issued per group (see the producer)
 };
 
 // barrier layout in smem: full[nstages] empty[nstages] dfull[2] dempty[2]
@@ -164,12 +166,13 @@ __global__ void __launch_bounds__(kThreadsN, 1) gemm_nt_tc_kernel(const __grid_c
         }
       }
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, pit++) {
-        const int tt = tile / p.nblk, ncol0 = (tile - tt * p.nblk) * N;
+        const int te = p.rev ? ntiles - 1 - tile : tile;
+        const int tt = te / p.nblk, ncol0 = (te - tt * p.nblk) * N;
         const int b = tt / tiles_per_b, t0 = (tt - b * tiles_per_b) * rows_per_tile;
         if (p.pf) {
           const int ptile = tile + p.pf * (int)gridDim.x;
           if (ptile < ntiles) {
-            const int ptt = ptile / p.nblk, pb = ptt / tiles_per_b, pt0 = (ptt - pb * tiles_per_b) * rows_per_tile;
+            const int ptt = (p.rev ? ntiles - 1 - ptile : ptile) / p.nblk, pb = ptt / tiles_per_b, pt0 = (ptt - pb * tiles_per_b) * rows_per_tile;
             for (int s = 0; s < p.nseg; s++)
               for (int kc = 0; kc < p.seg[s].K / 32; kc++)
                 for (int mh = 0; mh < p.mt; mh++)
@@ -192,11 +195,26 @@ __global__ void __launch_bounds__(kThreadsN, 1) gemm_nt_tc_kernel(const __grid_c
             wait(&empty[st], ph ^ 1, NP_P_EMPTY);
             ptx::mbar_arrive_expect_tx(&full[st], stage_bytes);
             unsigned char* dst = ring + (size_t)st * stage_bytes;
-            ptx::tma_load_3d(dst, &p.maps[sg.amap], &full[st], kc * 32, t0 + sg.shift, b);
             if (p.wres) {
-              if (++st == (uint32_t)p.nstages) { st = 0; ph ^= 1; }
+              // activation boxes are issued in groups of p.grp consecutive 32-channel chunks (= p.grp x 128 contiguous bytes
+              // of every row) once that many stages are free: DRAM sees whole rows at once instead of one 128-B piece of
+              // every other 256 B now and the next piece a microsecond later
+              int g = sg.K / 32 - kc < p.grp ? sg.K / 32 - kc : p.grp;
+              if (g > p.nstages) g = p.nstages;
+              uint32_t st2 = st, ph2 = ph;
+              for (int i = 1; i < g; i++) {
+                if (++st2 == (uint32_t)p.nstages) { st2 = 0; ph2 ^= 1; }
+                wait(&empty[st2], ph2 ^ 1, NP_P_EMPTY);
+              }
+              for (int i = 0; i < g; i++) {
+                if (i) ptx::mbar_arrive_expect_tx(&full[st], stage_bytes);
+                ptx::tma_load_3d(ring + (size_t)st * stage_bytes, &p.maps[sg.amap], &full[st], (kc + i) * 32, t0 + sg.shift, b);
+                if (++st == (uint32_t)p.nstages) { st = 0; ph ^= 1; }
+              }
+              kc += g - 1;
               continue;
             }
+            ptx::tma_load_3d(dst, &p.maps[sg.amap], &full[st], kc * 32, t0 + sg.shift, b);
             if (p.mt == 2)   // (rows past T are zero-filled by TMA, the matching stores are clipped)
               ptx::tma_load_3d(dst + kASub, &p.maps[sg.amap], &full[st], kc * 32, t0 + kTM + sg.shift, b);
             if (sg.b_n1 >= 0) {   // N = two row ranges of N/2 each (sigmoid rows, tanh rows)
@@ -297,7 +315,8 @@ __global__ void __launch_bounds__(kThreadsN, 1) gemm_nt_tc_kernel(const __grid_c
     uint32_t it = 0, nstore = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
      for (int mh = 0; mh < p.mt; mh++) {     // mt == 2: the two 128-row halves of the tile, accumulator mh each
-      const int tt = tile / p.nblk, ncol0 = (tile - tt * p.nblk) * N;
+      const int te = p.rev ? ntiles - 1 - tile : tile;
+      const int tt = te / p.nblk, ncol0 = (te - tt * p.nblk) * N;
       const int b = tt / tiles_per_b, t0 = (tt - b * tiles_per_b) * rows_per_tile + mh * kTM;
       const int t = t0 + q * 32 + lane;
       const bool row_ok = t < p.T;
@@ -331,9 +350,8 @@ __global__ void __launch_bounds__(kThreadsN, 1) gemm_nt_tc_kernel(const __grid_c
           ptx::st_shared_v4(wb + r * 128 + (((lane & 7) ^ (r & 7)) << 4), pre[i].x, pre[i].y, pre[i].z, pre[i].w);
         }
         __syncwarp();
-        const float4* rr = reinterpret_cast<const float4*>(box + lane * 128);
 #pragma unroll
-        for (int j = 0; j < 8; j++) pre[j] = rr[j ^ (lane & 7)];
+        for (int j = 0; j < 8; j++) pre[j] = ptx::ld_shared_v4(wb + lane * 128 + ((j ^ (lane & 7)) << 4));
       };
       wait(&dfull[buf], use & 1, NP_E_DFULL);
       ptx::tc_fence_after();
@@ -780,7 +798,11 @@ int gemm_nt_tc(const NtTcSeg* segs, int nseg, int N, float* out, int ld_out, con
   p.stg_boxes = p.mt == 2 ? 1 : 2;
   p.maps[10] = p.maps[8];
   static int pf_dist = -1;
-  if (pf_dist < 0) { const char* e = getenv("WNB_NT_PF"); pf_dist = e ? atoi(e) : 1; if (pf_dist < 0 || pf_dist > 4) pf_dist = 1; }
+  if (pf_dist < 0) { const char* e = getenv("WNB_NT_PF"); pf_dist = e ? atoi(e) : 0; if (pf_dist < 0 || pf_dist > 4) pf_dist = 0; }
+  static int grp = 0;
+  if (!grp) { const char* e = getenv("WNB_NT_GRP"); grp = e ? atoi(e) : 1; if (grp < 1 || grp > 4) grp = 1; }
+  p.grp = grp;
+  p.rev = (opts && opts->reverse) ? 1 : 0;
   p.pf = p.wres ? pf_dist : 0;
   if (p.mt == 1 && ((opts && opts->stage_epilogue_operand) || p.pf)) {
     // 1: gate-backward dz slice (EPI_GATE_BWD_NOZ, R = 64 shorthand), 2: residual add of a <= 64-column primary output

@@ -63,7 +63,7 @@ static_assert(8 * B_COUNT + 16 <= 256, "barrier block");
 
 __global__ void __launch_bounds__(kThreadsZ, 1)
 resblock_fwd_z_kernel(const __grid_constant__ Maps maps, const float* __restrict__ b1, const float* __restrict__ b2,
-                      int B, int T, int d, int has_xout, int zcol0, unsigned int* __restrict__ sched) {
+                      int B, int T, int d, int has_xout, int zcol0, unsigned int* __restrict__ sched, int rev) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
@@ -102,7 +102,9 @@ resblock_fwd_z_kernel(const __grid_constant__ Maps maps, const float* __restrict
     // =============================== TMA producer: activation tiles ===============================
     if (ptx::elect_one()) {
       ptx::prefetch_tmap(&maps.x); ptx::prefetch_tmap(&maps.haux);
-      int tile = blockIdx.x;
+      // rev: time tiles from the end of the tensor backwards -- a block whose producer ran front to back finds the rows
+      // that block wrote LAST still in L2 (stack.cu alternates the direction from block to block)
+      int tile = rev ? ntiles - 1 - (int)blockIdx.x : (int)blockIdx.x;
       for (uint32_t it = 0;; it++) {
         tile_ring[it & 1] = tile;                  // publish the tile (or the stop mark) to the other roles
         ptx::mbar_arrive(&bars[B_TILE0 + (it & 1)]);
@@ -118,6 +120,7 @@ resblock_fwd_z_kernel(const __grid_constant__ Maps maps, const float* __restrict
         ptx::tma_load_3d(sA + 4 * kSubBytes, &maps.haux, &bars[B_AFULL], 0, t0, b);
         tile = (int)(atomicAdd(&sched[0], 1u) + gridDim.x);
         if (tile >= ntiles) tile = -1;
+        else if (rev) tile = ntiles - 1 - tile;
         if (tile >= 0) {
           // there is room for only one A stage, so the next tile cannot be loaded yet -- but it can be pulled into
           // L2 now, which turns the exposed DRAM latency of its load into an L2 hit
@@ -374,7 +377,7 @@ bool resblock_fwd_z_supported(int R, int Ap, int ks) { return R == tcz::kR && ks
 // One block in deferred-skip form: xout (B,T,R) or null (last block), z -> zall[:, :, zcol0 : zcol0+R] (row pitch ldz).
 int resblock_fwd_z(const float* xin, const float* haux, const float* w1, const float* b1, const float* w2res,
                    const float* b2res, float* xout, float* zall, int ldz, int zcol0, int B, int T, int d,
-                   cudaStream_t st) {
+                   cudaStream_t st, int reverse) {
   using namespace tcz;
   if ((reinterpret_cast<uintptr_t>(b1) | reinterpret_cast<uintptr_t>(b2res)) & 15) {
     set_error("resblock_fwd_z: b1 / b2 must be 16-byte aligned");
@@ -395,7 +398,7 @@ int resblock_fwd_z(const float* xin, const float* haux, const float* w1, const f
   const int ntiles = B * ((T + kTM - 1) / kTM);
   const int grid = ntiles < sms ? ntiles : sms;
   if (launch_pdl(resblock_fwd_z_kernel, grid, kThreadsZ, kSmemBytes, st, maps, b1, b2res ? b2res : b1, B, T, d,
-                 xout ? 1 : 0, zcol0, sched) != cudaSuccess) { /* reported below */ }
+                 xout ? 1 : 0, zcol0, sched, reverse ? 1 : 0) != cudaSuccess) { /* reported below */ }
   WNB_CHECK_LAUNCH("resblock_fwd_z");
   return WNB_OK;
 }

@@ -45,6 +45,14 @@ static int resident_w() {
   return on && !stage_epi();
 }
 
+// Consecutive kernels of the block chain walk the time tiles in opposite directions (forward: odd blocks backwards;
+// backward: gate backward front to back, dX back to front), so each starts on the rows its producer wrote last -- still
+// in the 126 MB L2 -- instead of on the ones written a tensor ago.  WNB_ALT_DIR=0: every kernel front to back.
+static int alternate_dir() {
+  static const int on = [] { const char* e = getenv("WNB_ALT_DIR"); return (e && e[0] == '0') ? 0 : 1; }();
+  return on;
+}
+
 static bool stack_supported(int R, int S, int Ap, int ks, int L) {
   if (!resblock_fwd_z_supported(R, Ap, ks)) return false;
   if (L < 1 || L > 64 /* wnb_stack_bwd's segment table, wgrad kMaxSeg */) return false;
@@ -107,7 +115,8 @@ WNB_API int wnb_stack_fwd(float* xs, int nxs, const float* haux, const float* w1
     float* xout = (l + 1 < L) ? xs + (size_t)((l + 1) % nxs) * xsz : nullptr;
     ProfScope ps(WNB_PROF_FWD_BLOCK, st);
     if ((rc = resblock_fwd_z(xin, haux, w1 + (size_t)l * 2 * R * K1, b1 + (size_t)l * 2 * R, w2res + (size_t)l * R * R,
-                             b2res + (size_t)l * R, xout, zall, ldz, l * R, B, T, dilations[l], st)) != WNB_OK)
+                             b2res + (size_t)l * R, xout, zall, ldz, l * R, B, T, dilations[l], st,
+                             alternate_dir() ? (l & 1) : 0)) != WNB_OK)
       return rc;
   }
   ProfScope ps(WNB_PROF_SKIP_GEMM, st);
@@ -187,14 +196,14 @@ WNB_API int wnb_stack_bwd(const float* xs, const float* haux, const float* zall,
       ProfScope ps(WNB_PROF_DX_GEMM, st);
       // (the unshifted segment covers all R + Ap columns and goes first; the shifted one only adds to the R dx columns)
       const NtTcSeg sx[2] = {{dpre, 2 * R, 0, 2 * R, w1tl, K1, 2 * R, 0, R, 0, R + Ap}, {dpre, 2 * R, d, 2 * R, w1tl, R, 2 * R, 0, 0, 0, R}};
-      const NtTcOpts ox{1, 0, 0, 0, 1, stage_epi(), resident_w()};
+      const NtTcOpts ox{1, 0, 0, 0, 1, stage_epi(), resident_w(), alternate_dir()};
       if ((rc = gemm_nt_tc(sx, 2, R + Ap, dxin, R, nullptr, nullptr, 0, dout, R, 0, 0, B, T, st, nullptr, nullptr, dhaux,
                            Ap, R, nullptr, &ox)) != WNB_OK)
         return rc;
     } else {
       ProfScope ps(WNB_PROF_DX_GEMM, st);
       const NtTcSeg sx[2] = {{dpre, 2 * R, d, 2 * R, w1tl, K1, 2 * R, 0, 0}, {dpre, 2 * R, 0, 2 * R, w1tl, K1, 2 * R, 0, R}};
-      const NtTcOpts ox{1, 0, 0, 0, 1, stage_epi(), resident_w()};
+      const NtTcOpts ox{1, 0, 0, 0, 1, stage_epi(), resident_w(), alternate_dir()};
       if ((rc = gemm_nt_tc(sx, 2, R, dxin, R, nullptr, nullptr, 0, dout, R, 0, 0, B, T, st, nullptr, nullptr, nullptr, 0, 0,
                            nullptr, &ox)) != WNB_OK)
         return rc;

@@ -45,6 +45,8 @@ struct NtTcOpts {
                                 //    tile loaded by the producer warp instead of per-lane row loads (gate backward, dX)
   int resident_weights;   // 1: all weight chunks live in shared memory for the whole launch (loaded once per CTA), the ring
                           //    carries activations only; needs sum_seg K * n_cnt * 4 bytes (<= ~140 KB) and m_tiles == 1
+  int reverse;            // 1: time tiles are processed from the end of the tensor backwards (a kernel that consumes what the
+                          //    previous launch wrote front to back finds the rows written last still in L2)
 };
 // default of NtTcOpts::m_tiles for the K >= 512 GEMMs: 2, WNB_NT_MT=1 in the environment restores one tile per CTA
 int nt_default_m_tiles();
@@ -57,6 +59,6 @@ int gemm_nt_tc(const NtTcSeg* segs, int nseg, int N, float* out, int ld_out, con
 bool resblock_fwd_z_supported(int R, int Ap, int ks);
 int resblock_fwd_z(const float* xin, const float* haux, const float* w1, const float* b1, const float* w2res,
                    const float* b2res, float* xout, float* zall, int ldz, int zcol0, int B, int T, int d,
-                   cudaStream_t st);
+                   cudaStream_t st, int reverse = 0);   // reverse: time tiles from the end of the tensor backwards
 
 }  // namespace wnb
