@@ -796,6 +796,11 @@ int gemm_nt_tc(const NtTcSeg* segs, int nseg, int N, float* out, int ld_out, con
     return WNB_ERR_INVALID;
   }
   p.stg_boxes = p.mt == 2 ? 1 : 2;
+  {  // resident-weights launches with a plain epilogue: one staging box per warp leaves room for two more activation stages
+    static int one = -1;
+    if (one < 0) { const char* e = getenv("WNB_NT_STG1"); one = (e && e[0] == '0') ? 0 : 1; }   // (dX: 47.4 -> 46.4 us)
+    if (one && p.wres && !p.gate_mode) p.stg_boxes = 1;
+  }
   p.maps[10] = p.maps[8];
   static int pf_dist = -1;
   if (pf_dist < 0) { const char* e = getenv("WNB_NT_PF"); pf_dist = e ? atoi(e) : 0; if (pf_dist < 0 || pf_dist > 4) pf_dist = 0; }
