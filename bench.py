@@ -47,6 +47,15 @@ def _peaks():
         return FALLBACK_HBM_GBS, "fallback"
 
 
+def _tensor_peak():
+    """Sustained dense bf16 TFLOP/s of MEASURED_PEAKS.json (cuBLAS, back to back); kind::tf32 runs at half that rate."""
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["bf16_tflops_sustained"]), "measured"
+    except Exception:
+        return 1443.0, "fallback"
+
+
 class ClockSampler(object):
     """nvidia-smi clocks/throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
 
@@ -351,6 +360,19 @@ def run_ours(args):
                 "unit": "GB/s", "frac": (ach / hbm) if ach else None, "traffic": TRAFFIC_NCU.get(args.math),
                 "peak_source": how, "algorithmic_bytes_per_launch": alg_bytes,
                 "mean_launch_ms": blk, "launches_timed": len(blk_ms)}
+        if not stack and args.math == "tf32" and R * R >= 256 * 256:
+            # shapes of the composed path (the recipes' 512 res / 256 skip): tensor-bound (AI 470 flop/B) -- the
+            # whole step's GEMM FLOPs against the tf32 rate (half the measured sustained bf16 rate)
+            ks_, Q_ = cfg.kernel_size, cfg.n_quantize
+            fwd = L * (2.0 * R * R * (2 * ks_ + 1) + 4.0 * R * A + 2.0 * S * R) + 2.0 * S * S + 2.0 * Q_ * S
+            flops = 3.0 * fwd * float(Bq) * T
+            pk, pk_how = _tensor_peak()
+            ach_tf = flops / (per_step * 1e-3) / 1e12
+            roof = {"kernel": "whole step: every GEMM of the composed tcgen05 path (gemm_nt_tc / wgrad_tc kernels)",
+                    "bound": "tensor", "achieved": ach_tf, "peak": pk / 2, "unit": "TFLOP/s", "frac": ach_tf / (pk / 2),
+                    "traffic": None, "peak_source": pk_how + " bf16_tflops_sustained / 2 (kind::tf32 rate)",
+                    "flops_per_step": flops,
+                    "note": "fwd FLOPs/sample = L*[2R^2(2ks+1)+4RA+2SR]+2S^2+2QS (SURVEY 8d), backward = 2x"}
         roof_all = None
         if stack:
             # algorithmic bytes per launch of every kernel kind of the deferred-skip stack:
