@@ -120,6 +120,19 @@ WNB_API int wnb_make_train_batch(const float* wave, const void* feat, const int3
                                  int64_t* x, int64_t* t, float* h, int B, int T, int Tf, int D, int feat_f64, int mu,
                                  void* stream);
 
+/* ---- f4: MLSA noise-shaping filter for a batch of utterances (bin/noise_shaping.py:46-87: pysptk
+ * Synthesizer(MLSADF(order, alpha), hopsize).synthesis(x, tiled coefficients), i.e. per sample SPTK
+ * mlsadf(x * exp(coef[0]), coef, order, alpha, pd) with a time-invariant coefficient vector) -------------------------
+ * x: the utterances concatenated, int16 (x_is_i16 = 1: the wav samples, converted like np.float64(x)) or float64;
+ * offsets (n_utts + 1 int64, device): utterance u is [offsets[u], offsets[u+1]); coef (order + 1 float64, device) =
+ * pysptk.mc2b output (pass -coef for the inverse filter, noise_shaping.py:55-56); pd = Pade order 4 (pysptk's default) or
+ * 5; gain = exp(coef[0]) computed by the caller; y: same layout as x, float64 or int16 (y_is_i16 = 1: truncation toward
+ * zero like np.int16(y), noise_shaping.py:87).  fp64 arithmetic in SPTK's operation order without FMA contraction;
+ * every utterance starts from a zero filter state (the reference lets the state of one file run on into the next file of
+ * the same worker process). */
+WNB_API int wnb_mlsa_filter(const void* x, int x_is_i16, const long long* offsets, int n_utts, const double* coef, int order,
+                            double alpha, int pd, double gain, void* y, int y_is_i16, void* stream);
+
 /* ---- pack_weights: state_dict layout <-> kernel layout as one launch per direction ----------
  * A table of strided 3-D copies dst[i0*ds0 + i1*ds1 + i2*ds2] = scale * f(src[i0*ss0 + i1*ss1 + i2*ss2]) executed by
  * one kernel (one block row per entry).  `src` / `src2` are absolute device pointers (WNB_PACK_SRC_ABS: the
