@@ -15,9 +15,11 @@ cfg, net = bench.make_model(dev, "tf32")
 net.train()
 xh, hh, th = bench.synth_batch(cfg, 0, bench.BATCH, pinned=False)
 x, h, t = xh.to(dev), hh.to(dev), th.to(dev)
+opt = torch.optim.Adam(net.parameters(), lr=1e-4, fused=True)
 for _ in range(int(os.environ.get("STEPS", "2"))):
     loss = net.forward_loss(x, h, t, cfg.receptive_field)
-    net.zero_grad(set_to_none=True)
+    opt.zero_grad(set_to_none=True)
     loss.backward()
+    opt.step()
     torch.cuda.synchronize()
 print("loss", float(loss))
