@@ -165,7 +165,13 @@ def run_ours(args):
             sync = GradAllReduce(net)
         else:
             sync = None
-        opt = torch.optim.Adam(net.parameters(), lr=1e-4, fused=True)
+        # torch.optim.Adam (reference bin/train.py:457-460) whose step is one wnb_adam_flat launch over the flat gradient
+        # buffer; WNB_TORCH_ADAM=1: torch's own fused multi-tensor step (A/B runs)
+        if os.environ.get("WNB_TORCH_ADAM") == "1":
+            opt = torch.optim.Adam(net.parameters(), lr=1e-4, fused=True)
+        else:
+            from pytorchwavenetvocoder_b200.optim import Adam as WnbAdam
+            opt = WnbAdam(net.parameters(), lr=1e-4, module=net)
         xh, hh, th = synth_batch(cfg, rank, BATCH, pinned=True)
         xd, hd, td = xh.to(dev), hh.to(dev), th.to(dev)
         rf = cfg.receptive_field

@@ -293,7 +293,10 @@ def main():
     logging.info("math_mode = %s" % model.math_mode)
 
     model.cuda()   # before the optimizer: the fused (single multi-tensor kernel) Adam needs CUDA parameters
-    optimizer = torch.optim.Adam(model.parameters(), lr=args.lr, weight_decay=args.weight_decay, fused=True)
+    # torch.optim.Adam (reference :457-460) with a one-launch step over the flat gradient buffer (optim.py); its
+    # state_dict is torch's, so checkpoints stay interchangeable with the reference's
+    from pytorchwavenetvocoder_b200.optim import Adam
+    optimizer = Adam(model.parameters(), lr=args.lr, weight_decay=args.weight_decay, module=model)
 
     scaler = StandardScaler()
     scaler.mean_ = read_hdf5(args.stats, "/" + args.feature_type + "/mean")

@@ -14,7 +14,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libwnb200.so")
-SOURCES = ["elementwise.cu", "resblock_simt.cu", "resblock_tc.cu", "decode.cu", "decode_stream.cu", "wgrad_tc.cu", "decode_warp.cu", "gemm_nt_tc.cu", "resblock_z.cu", "stack.cu", "pack.cu", "loader.cu", "mlsa.cu"]
+SOURCES = ["elementwise.cu", "resblock_simt.cu", "resblock_tc.cu", "decode.cu", "decode_stream.cu", "wgrad_tc.cu", "decode_warp.cu", "gemm_nt_tc.cu", "resblock_z.cu", "stack.cu", "pack.cu", "loader.cu", "mlsa.cu", "adam.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--fmad=true", "-cudart", "static"]
 

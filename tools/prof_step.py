@@ -15,7 +15,8 @@ cfg, net = bench.make_model(dev, "tf32")
 net.train()
 xh, hh, th = bench.synth_batch(cfg, 0, bench.BATCH, pinned=False)
 x, h, t = xh.to(dev), hh.to(dev), th.to(dev)
-opt = torch.optim.Adam(net.parameters(), lr=1e-4, fused=True)
+from pytorchwavenetvocoder_b200.optim import Adam  # noqa: E402
+opt = Adam(net.parameters(), lr=1e-4, module=net)
 for _ in range(int(os.environ.get("STEPS", "2"))):
     loss = net.forward_loss(x, h, t, cfg.receptive_field)
     opt.zero_grad(set_to_none=True)
