@@ -124,9 +124,10 @@ WNB_API int wnb_make_train_batch(const float* wave, const void* feat, const int3
  * p, g, m, v: parameters, gradients (the flat buffer wnb_pack_weights' backward direction fills), first and second moment
  * estimates, n floats each, 16-byte aligned, identical layout.  torch's (fused) Adam arithmetic in fp32: g += weight_decay*p;
  * m += (1-beta1)(g-m); v = beta2 v + (1-beta2) g^2; p -= lr/bias_correction1 * m / (sqrt(v)/sqrt(bias_correction2) + eps)
- * with bias_correction_i = 1 - beta_i^step supplied by the caller (step counted from 1). */
-WNB_API int wnb_adam_flat(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
-                          float weight_decay, float bias_correction1, float bias_correction2, void* stream);
+ * with bias_correction_i = 1 - beta_i^step supplied by the caller (step counted from 1); the scalar hyper-parameters are
+ * doubles, combined in double and rounded to float once, as torch does. */
+WNB_API int wnb_adam_flat(float* p, const float* g, float* m, float* v, int64_t n, double lr, double beta1, double beta2,
+                          double eps, double weight_decay, double bias_correction1, double bias_correction2, void* stream);
 
 /* ---- f4: MLSA noise-shaping filter for a batch of utterances (bin/noise_shaping.py:46-87: pysptk
  * Synthesizer(MLSADF(order, alpha), hopsize).synthesis(x, tiled coefficients), i.e. per sample SPTK

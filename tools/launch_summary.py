@@ -42,7 +42,7 @@ def main(path):
         if lib == "libwnb200":
             ours += us
         print("%-86s %3d launches %9.1f us  %5.1f %%  %s" % (name, n, us, 100 * us / tot, lib))
-    print("\nsum of kernel time %.1f us in %d launches: libwnb200 %.1f us, torch %.1f us (fused Adam multi-tensor kernels)"
+    print("\nsum of kernel time %.1f us in %d launches: libwnb200 %.1f us, torch %.1f us (scalar helpers: loss scale, the optimizer step counter)"
           % (tot, len(step), ours, tot - ours))
 
 
