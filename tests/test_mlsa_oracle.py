@@ -95,3 +95,32 @@ def test_against_pysptk_when_available():
     syn = pysptk.synthesis.Synthesizer(pysptk.synthesis.MLSADF(order=24, alpha=0.41), hopsize=80)
     want = syn.synthesis(x, np.tile(b, [len(x) // 80 + 1, 1]))
     np.testing.assert_array_equal(M.filter_const(x, b, 0.41), want)
+
+
+def test_cli_writes_the_filter_coefficients_like_the_reference(tmp_path):
+    """bin/noise_shaping.py main() up to the filter launch (an empty wav directory: no GPU needed): /mlsa/coef and
+    /mlsa/alpha are derived from <feature_type>/mean exactly as reference noise_shaping.py:171-177 does and are not
+    recomputed when they already exist."""
+    from pytorchwavenetvocoder_b200.bin import noise_shaping as ns
+    from pytorchwavenetvocoder_b200.utils import check_hdf5, read_hdf5, write_hdf5
+    rng = np.random.RandomState(11)
+    stats = str(tmp_path / "stats.npz")
+    mean = rng.randn(28)
+    write_hdf5(stats, "/world/mean", mean)
+    (tmp_path / "wav").mkdir()
+    argv = ["--waveforms", str(tmp_path / "wav"), "--stats", stats, "--outdir", str(tmp_path / "out"), "--mag", "0.5",
+            "--mcep_alpha", "0.41", "--verbose", "0"]
+    ns.main(argv)
+    assert check_hdf5(stats, "/mlsa/coef") and (tmp_path / "out").is_dir()
+    want = M.convert_mcep_to_mlsa_coef(mean[2:27], 0.5, 0.41)
+    assert np.array_equal(read_hdf5(stats, "/mlsa/coef"), want) and float(read_hdf5(stats, "/mlsa/alpha")) == 0.41
+    assert np.array_equal(read_hdf5(stats, "/world/mean"), mean)          # the stats themselves are untouched
+    write_hdf5(stats, "/mlsa/coef", want * 2.0)                            # an existing coefficient set is used as is
+    ns.main(argv)
+    assert np.array_equal(read_hdf5(stats, "/mlsa/coef"), want * 2.0)
+    # mcep features: the whole mean vector is the mel-cepstrum (reference :173-175)
+    stats2 = str(tmp_path / "stats2.npz")
+    write_hdf5(stats2, "/mcep/mean", mean[:25])
+    ns.main(["--waveforms", str(tmp_path / "wav"), "--stats", stats2, "--outdir", str(tmp_path / "out"), "--feature_type", "mcep",
+             "--verbose", "0"])
+    assert np.array_equal(read_hdf5(stats2, "/mlsa/coef"), M.convert_mcep_to_mlsa_coef(mean[:25], 0.5, 0.41))
